@@ -1,0 +1,199 @@
+/*
+ * nk_b200.h -- C ABI of the B200-native per-timestep particle loop of Nano-kappa.
+ *
+ * The reference (brunohs1993/Nanokappa) is pure Python and has no FFI; the seam this library
+ * replaces is the body of the Python methods on the hot path.  Each entry point
+ * below cites the reference method whose arithmetic it performs on the GPU.  Conventions:
+ *
+ *   - plain C types only; every function returns 0 on success, <0 on error
+ *     (message: nk_last_error).  Nothing throws across the ABI.
+ *   - "host" pointers are read during the call and copied; "dev" pointers are CUDA device
+ *     pointers owned by the caller (torch tensors in the Python host layer), borrowed until
+ *     nk_destroy / the next nk_bind_particles.
+ *   - one nk_ctx per GPU per process; a ctx is not thread-safe.  All work is enqueued on the
+ *     stream given to nk_set_stream (default: the legacy default stream); calls that return a host
+ *     scalar synchronise that stream, the others do not.
+ *   - flat mode index m = q * J + j everywhere (reference keeps (q, j) pairs, Population.py:133).
+ *   - boundary-condition codes: 0 = T (isothermal reservoir), 1 = P (periodic), 2 = R (rough),
+ *     3 = F (flux reservoir, treated like T as upstream does, Population.py:1569).
+ */
+#ifndef NK_B200_H
+#define NK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nk_ctx nk_ctx;
+
+#define NK_BC_T 0
+#define NK_BC_P 1
+#define NK_BC_R 2
+#define NK_BC_F 3
+
+#define NK_INTERP_NEAREST 0   /* --temp_interp nearest (Population.py:570-573) */
+#define NK_INTERP_LINEAR  1   /* --temp_interp linear, slice subvolumes only (Population.py:570-571) */
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int         nk_create(int device, nk_ctx** out);
+void        nk_destroy(nk_ctx* ctx);
+const char* nk_last_error(nk_ctx* ctx);          /* ctx may be NULL: last error of nk_create */
+int         nk_version(void);
+int         nk_set_stream(nk_ctx* ctx, void* cuda_stream);   /* cudaStream_t */
+int         nk_synchronize(nk_ctx* ctx);
+
+/* ---- static tables (host pointers, copied) ---------------------------------------------------- */
+
+/* Triangle planes and facets: Mesh.get_faces_properties / get_facets_properties / get_face_k
+ * (Mesh.py:205-243, :244-308, :323-327) and the BC assignment of Geometry.get_bound_facets /
+ * check_facet_connections (Geometry.py:652-726).
+ *   face_*      : F triangles; basis = face_basis_matrix (F,3,3) row-major (columns b1, b2, n)
+ *   face_vertices (F,3,3), face_areas (F): used by Mesh.sample_surface (Mesh.py:923-951)
+ *   facet_*     : n_facets coplanar groups; partner = periodic partner or -1; res = reservoir index
+ *                 or -1; rough = index into the rough-facet LUTs or -1
+ *   facet_faces_ptr (n_facets+1), facet_faces: CSR list of the triangles of each facet
+ *   bounds (2,3): mesh bounding box                                                            */
+int nk_set_mesh(nk_ctx* ctx, int n_faces,
+                const double* face_normals, const double* face_k,
+                const double* face_lo, const double* face_hi,
+                const double* face_origins, const double* face_basis,
+                const int32_t* face_facets, const double* face_vertices, const double* face_areas,
+                int n_facets, const int32_t* facet_bc, const int32_t* facet_partner,
+                const int32_t* facet_res, const int32_t* facet_rough,
+                const double* facet_normal, const double* facet_centroid, const double* facet_area,
+                const int32_t* facet_faces_ptr, const int32_t* facet_faces,
+                const double* bounds);
+
+/* Subvolume centres and the particle-temperature rule: Geometry.set_subvolumes (Geometry.py:446-544),
+ * SubvolClassifier (Geometry.py:1198-1213), Population.assign_temperatures (Population.py:570-590). */
+int nk_set_subvols(nk_ctx* ctx, int n_subvols, const double* centres, const double* volumes,
+                   int is_slice, int slice_axis, int temp_interp);
+
+/* Mode tables: Phonon.load_base_properties / calculate_lifetime / initialise_temperature_function
+ * (Phonon.py:66-151, :326-336, :372-390).  omega (Q,J) rad THz, group_vel (Q,J,3) A THz,
+ * tau (NT,Q,J) ps (0 where gamma <= 0), T_grid (NT) K, energy_array/T_array (nE) the E(T) table. */
+int nk_set_phonon(nk_ctx* ctx, int Q, int J, int NT, const double* T_grid,
+                  const double* omega, const double* group_vel, const double* tau,
+                  double hbar, double kb, double volume_unitcell, int64_t n_active_modes,
+                  int nE, const double* energy_array, const double* T_array);
+
+/* Population constants (Population.py:35-125) and physical unit factors (Constants.py:7-12).
+ * hot_T_lo/hi: expected temperature window; only used to choose which tau slabs are packed next to
+ * each mode (any T outside still takes the exact full-table path). */
+int nk_set_population(nk_ctx* ctx, double dt, int norm_mean, double particle_density,
+                      int n_dt_to_conv, uint64_t seed, double eVpsa2_in_Wm2, double a_in_m,
+                      double hot_T_lo, double hot_T_hi);
+
+/* Reservoirs: Population.initialise_reservoirs / enter_probability (Population.py:146-161, :323-354).
+ * enter_prob, res_counter (R,Q,J). */
+int nk_set_reservoirs(nk_ctx* ctx, int R, const int32_t* res_facet, const double* res_T,
+                      const double* enter_prob, const double* res_counter);
+int nk_get_res_counter(nk_ctx* ctx, double* res_counter_host);
+
+/* Rough-wall tables: calculate_fbz_specularity / find_specular_correspondences /
+ * diffuse_scat_probability (Population.py:852-939, :1042-1461).  All (Fr, Q*J); spec_out is the
+ * flat outgoing mode of specular_function(-n_f, q, j) (Population.py:959-961) or -1. */
+int nk_set_boundary_luts(nk_ctx* ctx, int n_rough, const double* specularity,
+                         const uint8_t* true_specular, const int32_t* spec_out, const double* roulette);
+
+/* ---- particle state (device pointers, borrowed) ----------------------------------------------- */
+
+/* The 13 per-particle arrays of Population.delete_particles (Population.py:838-850) reduced to the
+ * ones that are state; omega / group_vel / wavevectors are gathered from the mode tables.
+ *   px,py,pz   positions [A]            tc   n_timesteps (time to next collision, in dt)
+ *   occ        occupation               mode flat mode (v_g, tau); -1 marks a free slot
+ *   omode      flat mode whose omega the particle carries (differs from mode after a specular
+ *              reflection, Population.py:955-971)
+ *   cfacet,cx,cy,cz  collision_facets / collision_positions      pid  stable particle id        */
+int nk_bind_particles(nk_ctx* ctx, int64_t capacity,
+                      double* px, double* py, double* pz, double* tc, double* occ,
+                      int32_t* mode, int32_t* omode, int32_t* cfacet,
+                      double* cx, double* cy, double* cz, int64_t* pid);
+int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots);     /* slots [0, n_slots) are in use or free-listed */
+int nk_get_slot_count(nk_ctx* ctx, int64_t* n_slots, int64_t* n_alive);
+int nk_set_sv_temperature(nk_ctx* ctx, const double* T_sv_host);   /* Population.subvol_temperature */
+int nk_get_sv_temperature(nk_ctx* ctx, double* T_sv_host);
+int nk_set_timestep(nk_ctx* ctx, int64_t current_timestep);
+int nk_get_timestep(nk_ctx* ctx, int64_t* current_timestep);
+
+/* ---- operator seams (device pointers; (n,3) arrays are row-major like the reference's) ---------- */
+
+/* Mesh.find_boundary(x, v) -> (xc, tc, fc)   Mesh.py:806-856.  fc int32, -1 = no hit (tc = inf). */
+int nk_find_boundary(nk_ctx* ctx, int64_t n, const double* x, const double* v,
+                     double* xc, double* tc, int32_t* fc);
+/* SubvolClassifier.predict(x) + Population.get_subvol_id counts  Geometry.py:1212, Population.py:671-683.
+ * counts (n_subvols) int64 may be NULL. */
+int nk_classify(nk_ctx* ctx, int64_t n, const double* x, int32_t* sv, int64_t* counts);
+/* Phonon.calculate_occupation(T, omega)   Phonon.py:338-345 */
+int nk_occupation(nk_ctx* ctx, int64_t n, const double* T, const double* omega, double* occ);
+/* Phonon.lifetime_function([T, q, j])     Phonon.py:326-336 */
+int nk_lifetime(nk_ctx* ctx, int64_t n, const double* T, const int32_t* mode, double* tau);
+/* Phonon.temperature_function(E) / crystal_energy_function(T)   Phonon.py:387-390 */
+int nk_temperature_of_energy(nk_ctx* ctx, int64_t n, const double* E, double* T);
+int nk_energy_of_temperature(nk_ctx* ctx, int64_t n, const double* T, double* E);
+/* temperature_interpolator(x) of Population.refresh_temperatures with the ctx's current T_sv
+ * (Population.py:694-702) */
+int nk_particle_temperature(nk_ctx* ctx, int64_t n, const double* x, double* T);
+
+/* ---- the timestep ------------------------------------------------------------------------------ */
+
+/* Population.timesteps_to_boundary for every live particle + get_collision_condition
+ * (Population.py:308-316): fills tc, cfacet, cx,cy,cz from the bound SoA. */
+int nk_init_collisions(nk_ctx* ctx);
+
+/* n_steps x Population.run_timestep without the every-100-step output branch
+ * (Population.py:1743-1769): drift, reservoir emission (fill_reservoirs + add_reservoir_particles),
+ * boundary_scattering, refresh_temperatures, lifetime_scattering, and every n_dt_to_conv steps
+ * calculate_heat_flux / calculate_kappa / adjust_reservoir_balance.  Enqueued; no host sync. */
+int nk_step(nk_ctx* ctx, int n_steps);
+
+/* Make `occ` hold the post-lifetime_scattering occupation (the step kernel defers the relaxation of
+ * step k to the head of step k+1; outputs that read occupation call this first). */
+int nk_flush_relaxation(nk_ctx* ctx);
+
+/* Per-subvolume results of the last completed step (host buffers, any may be NULL):
+ *   T_sv, E_sv (S)  subvol_temperature / subvol_energy   Population.py:692, :704-728
+ *   N_sv (S) int64  subvol_N_p                            Population.py:679
+ *   flux (S,3)      subvol_heat_flux of the last convergence step [W/m2]  Population.py:730-747
+ *   kappa_sv (S), kappa (1)                               Population.py:749-771 (slice)
+ *   res_E_bal (R), res_flux (R,3): adjust_reservoir_balance values of the last convergence step
+ *   N_leaving (R) int64: Population.N_leaving of the last step
+ *   total_energy (1): sum of particle energies [eV]       Population.py:2034                      */
+int nk_get_results(nk_ctx* ctx, double* T_sv, double* E_sv, int64_t* N_sv, double* flux,
+                   double* kappa_sv, double* kappa, double* res_E_bal, double* res_flux,
+                   int64_t* N_leaving, double* total_energy);
+
+/* Population.contains_check (Population.py:1712-1722): not yet on the GPU path. */
+
+/* ---- host-buffer end-to-end call ---------------------------------------------------------------- */
+
+/* Upload n particles (host SoA, pinned or pageable), run n_steps, download the state and the per-SV
+ * results.  This is the call bench.py times as `e2e`: host<->device copies are inside it. */
+int nk_advance_host(nk_ctx* ctx, int64_t n_in, int n_steps,
+                    double* px, double* py, double* pz, double* tc, double* occ,
+                    int32_t* mode, int32_t* omode, int32_t* cfacet,
+                    double* cx, double* cy, double* cz, int64_t* pid,
+                    int64_t* n_out, double* T_sv_out, double* E_sv_out, int64_t* N_sv_out);
+
+/* ---- multi-GPU ------------------------------------------------------------------------------------ */
+
+/* Particle shards: each rank owns a block of particles and a mode-range of every reservoir's
+ * emission table; the only exchange is the per-step sum of the per-SV / per-reservoir accumulators.
+ * nk_acc_buffer exposes that vector (device pointer + length in doubles) so the host layer can run
+ * ncclAllReduce on it between the two halves of a step (nk_step_local / nk_step_finalize), or
+ * register peer buffers for the fused one-shot exchange (nk_comm_*). */
+int nk_set_rank(nk_ctx* ctx, int rank, int world);
+int nk_acc_buffer(nk_ctx* ctx, double** dev_ptr, int64_t* n_doubles);
+int nk_step_local(nk_ctx* ctx);      /* kernels of one step up to the accumulators */
+int nk_step_finalize(nk_ctx* ctx);   /* accumulators -> T_sv, results; closes the step */
+/* fused exchange over NVLink peer memory: every rank exports its mailbox, imports the others */
+int nk_comm_export(nk_ctx* ctx, void* handle_out_64B);
+int nk_comm_import(nk_ctx* ctx, int peer_rank, const void* handle_64B);
+int nk_comm_enable(nk_ctx* ctx, int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NK_B200_H */

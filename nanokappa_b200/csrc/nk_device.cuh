@@ -1,0 +1,295 @@
+// nk_device.cuh -- device functions of the particle loop.  All arithmetic is IEEE f64 with explicit
+// round-to-nearest mul/add (no FMA contraction) wherever the reference's NumPy expression order is
+// what decides an integer result (facet, subvolume, mode index).
+#pragma once
+#include "nk_types.cuh"
+#include <math_constants.h>
+
+#define NK_DEVI __device__ __forceinline__
+
+NK_DEVI double nk_mul(double a, double b) { return __dmul_rn(a, b); }
+NK_DEVI double nk_add(double a, double b) { return __dadd_rn(a, b); }
+NK_DEVI double nk_sub(double a, double b) { return __dsub_rn(a, b); }
+NK_DEVI double nk_div(double a, double b) { return __ddiv_rn(a, b); }
+// np.sum over a length-3 axis is left-associated: (a+b)+c
+NK_DEVI double dot3(double ax, double ay, double az, double bx, double by, double bz) {
+    return nk_add(nk_add(nk_mul(ax, bx), nk_mul(ay, by)), nk_mul(az, bz));
+}
+NK_DEVI double norm3(double x, double y, double z) { return sqrt(dot3(x, y, z, x, y, z)); }
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 keyed by (particle id, step, stream); see oracle/philox.py for the contract
+// ------------------------------------------------------------------------------------------------
+#define NK_STREAM_EMIT_A 0u
+#define NK_STREAM_EMIT_B 1u
+#define NK_STREAM_ROUGH0 2u
+
+NK_DEVI void philox4x32_10(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3,
+                           unsigned int k0, unsigned int k1, unsigned int out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// two doubles in [0,1) built like NumPy's random_sample: ((a>>5)*2^26 + (b>>6)) / 2^53
+NK_DEVI void nk_uniforms(const NkP& P, long long id, long long step, unsigned int stream, double& u0, double& u1) {
+    unsigned int r[4];
+    unsigned long long uid = (unsigned long long)id;
+    philox4x32_10((unsigned int)(uid & 0xFFFFFFFFull), (unsigned int)(uid >> 32), (unsigned int)step, stream,
+                  P.seed_lo, P.seed_hi, r);
+    u0 = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6)) / 9007199254740992.0;
+    u1 = ((double)(r[2] >> 5) * 67108864.0 + (double)(r[3] >> 6)) / 9007199254740992.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mode-table functions
+// ------------------------------------------------------------------------------------------------
+// Phonon.calculate_occupation (Phonon.py:338-345): 1/(exp(omega*hbar/(T*kb)) - 1), 0 if T<=0 or omega<=0
+NK_DEVI double nk_bose(const NkP& P, double T, double omega) {
+    if (!(T > 0.0) || !(omega > 0.0)) return 0.0;
+    double x = nk_div(nk_mul(omega, P.hbar), nk_mul(T, P.kb));
+    return nk_div(1.0, nk_sub(exp(x), 1.0));
+}
+
+// index i with Tg[i] <= T < Tg[i+1], clipped to [0, NT-2]  (searchsorted(right)-1)
+NK_DEVI int nk_T_index(const NkP& P, double T) {
+    int i = (int)floor((T - __ldg(P.Tg)) * P.Tg_inv_d);
+    i = max(0, min(i, P.NT - 2));
+    while (i > 0 && T < __ldg(P.Tg + i)) --i;
+    while (i < P.NT - 2 && T >= __ldg(P.Tg + i + 1)) ++i;
+    return i;
+}
+
+// Phonon.lifetime_function (Phonon.py:326-336) at integer (q,j): linear in T between two slabs
+NK_DEVI double nk_tau(const NkP& P, double T, int m) {
+    int i = nk_T_index(P, T);
+    double t0 = __ldg(P.Tg + i), t1 = __ldg(P.Tg + i + 1);
+    double w = nk_div(nk_sub(T, t0), nk_sub(t1, t0));
+    double lo, hi;
+    int r = i - P.tau_i0;
+    if (r >= 0 && r <= 2) {
+        const double4 q = *reinterpret_cast<const double4*>(P.tau4 + m);     // one 32 B sector
+        lo = r == 0 ? q.x : (r == 1 ? q.y : q.z);
+        hi = r == 0 ? q.y : (r == 1 ? q.z : q.w);
+    } else {
+        lo = __ldg(P.tau + (size_t)i * P.M + m);
+        hi = __ldg(P.tau + (size_t)(i + 1) * P.M + m);
+    }
+    return nk_add(nk_mul(lo, nk_sub(1.0, w)), nk_mul(hi, w));
+}
+
+// np.interp(x, xp, fp) with interp1d's (below, above) fill values (Phonon.py:387-390)
+NK_DEVI double nk_interp_table(const double* xp, const double* fp, int n, double x, double below, double above) {
+    if (x != x) return x;
+    if (x < xp[0]) return below;
+    if (x > xp[n - 1]) return above;
+    int lo = 0, hi = n - 1;            // invariant xp[lo] <= x, lo < n
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (xp[mid] <= x) lo = mid; else hi = mid;
+    }
+    if (x >= xp[n - 1]) return fp[n - 1];
+    if (xp[lo] == x) return fp[lo];
+    double slope = nk_div(nk_sub(fp[lo + 1], fp[lo]), nk_sub(xp[lo + 1], xp[lo]));
+    return nk_add(nk_mul(slope, nk_sub(x, xp[lo])), fp[lo]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// subvolumes
+// ------------------------------------------------------------------------------------------------
+NK_DEVI double nk_dist2(const double* c, double x, double y, double z) {
+    double dx = nk_sub(x, c[0]), dy = nk_sub(y, c[1]), dz = nk_sub(z, c[2]);
+    return dot3(dx, dy, dz, dx, dy, dz);
+}
+
+// searchsorted(a, v, side='left') on an almost uniform ascending array with spacing 1/inv_d
+NK_DEVI int nk_searchsorted_left(const double* a, int n, double v, double inv_d) {
+    int g = (int)floor((v - a[0]) * inv_d) + 1;
+    g = max(0, min(g, n));
+    while (g > 0 && a[g - 1] >= v) --g;
+    while (g < n && a[g] < v) ++g;
+    return g;
+}
+
+// SubvolClassifier.predict (Geometry.py:1198-1213): nearest centre, squared distances summed in
+// x,y,z order; exact ties (undefined upstream) resolve to the lowest index.
+// `svc`, `sv_axis`, `sv_mid` may point to shared memory copies.
+NK_DEVI int nk_classify(const NkP& P, const double* svc, const double* sv_mid, double x, double y, double z) {
+    if (P.is_slice) {
+        double xa = P.axis == 0 ? x : (P.axis == 1 ? y : z);
+        int g = P.S > 1 ? nk_searchsorted_left(sv_mid, P.S - 1, xa, P.sv_inv_dx) : 0;
+        int best = g; double dbest = nk_dist2(svc + 3 * g, x, y, z);
+        if (g > 0) { double d = nk_dist2(svc + 3 * (g - 1), x, y, z); if (d <= dbest) { dbest = d; best = g - 1; } }
+        if (g + 1 < P.S) { double d = nk_dist2(svc + 3 * (g + 1), x, y, z); if (d < dbest) { dbest = d; best = g + 1; } }
+        return best;
+    }
+    int best = 0; double dbest = nk_dist2(svc, x, y, z);
+    for (int s = 1; s < P.S; ++s) {
+        double d = nk_dist2(svc + 3 * s, x, y, z);
+        if (d < dbest) { dbest = d; best = s; }
+    }
+    return best;
+}
+
+// temperature_interpolator(x) (Population.py:570-590, :694-702; scipy interp1d formulas restated in
+// oracle/nk_oracle.py:particle_temperature).  `sv` is the particle's subvolume if already known (-1
+// otherwise); it is only used by the non-slice nearest rule.
+NK_DEVI double nk_particle_T(const NkP& P, const double* svc, const double* sv_axis, const double* sv_mid,
+                             const double* T_sv, double x, double y, double z, int sv) {
+    if (P.is_slice) {
+        double xa = P.axis == 0 ? x : (P.axis == 1 ? y : z);
+        if (P.interp == NK_INTERP_LINEAR && P.S > 1) {
+            int idx = nk_searchsorted_left(sv_axis, P.S, xa, P.sv_inv_dx);
+            idx = max(1, min(idx, P.S - 1));
+            double xl = sv_axis[idx - 1], xh = sv_axis[idx];
+            double den = nk_sub(xh, xl);
+            return nk_add(nk_mul(nk_div(nk_sub(xa, xl), den), T_sv[idx]), nk_mul(nk_div(nk_sub(xh, xa), den), T_sv[idx - 1]));
+        }
+        int idx = P.S > 1 ? nk_searchsorted_left(sv_mid, P.S - 1, xa, P.sv_inv_dx) : 0;
+        return T_sv[min(idx, P.S - 1)];
+    }
+    if (sv < 0) sv = nk_classify(P, svc, sv_mid, x, y, z);
+    return T_sv[sv];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mesh.find_boundary (Mesh.py:806-856) for one ray.  `faces` may point to shared memory.
+// ------------------------------------------------------------------------------------------------
+NK_DEVI void nk_ray_faces(const NkFace* faces, int F, double x, double y, double z, double vx, double vy, double vz,
+                          double& tbest, int& fbest) {
+    for (int f = 0; f < F; ++f) {
+        const NkFace& T = faces[f];
+        double num = nk_add(dot3(x, y, z, T.nx, T.ny, T.nz), T.k);
+        double den = dot3(vx, vy, vz, T.nx, T.ny, T.nz);
+        double t = -nk_div(num, den);
+        if (!(t >= NK_TOL) || isinf(t)) continue;                 // also rejects NaN
+        if (!(t < tbest)) continue;                               // cannot become the first minimum
+        double cx = nk_add(x, nk_mul(t, vx)), cy = nk_add(y, nk_mul(t, vy)), cz = nk_add(z, nk_mul(t, vz));
+        if (!(cx >= T.lox && cy >= T.loy && cz >= T.loz && cx <= T.hix && cy <= T.hiy && cz <= T.hiz)) continue;
+        double dx = nk_sub(cx, T.ox), dy = nk_sub(cy, T.oy), dz = nk_sub(cz, T.oz);
+        double a = T.ia0 * dx + T.ia1 * dy + T.ia2 * dz;
+        double b = T.ib0 * dx + T.ib1 * dy + T.ib2 * dz;
+        double w = nk_sub(1.0, nk_add(a, b));
+        const double lo = -NK_TOL, hi = 1.0 + NK_TOL;
+        if (!(a >= lo && a <= hi && b >= lo && b <= hi && w >= lo && w <= hi)) continue;
+        tbest = t; fbest = (int)T.facet;
+    }
+}
+
+NK_DEVI void nk_find_boundary_1(const NkP& P, const NkFace* faces, double x, double y, double z,
+                                double vx, double vy, double vz,
+                                double& xc, double& yc, double& zc, double& tc, int& fc) {
+    double tbest = CUDART_INF; int fbest = -1;
+    nk_ray_faces(faces, P.F, x, y, z, vx, vy, vz, tbest, fbest);
+    tc = tbest; fc = fbest;
+    xc = nk_add(x, nk_mul(tbest, vx)); yc = nk_add(y, nk_mul(tbest, vy)); zc = nk_add(z, nk_mul(tbest, vz));   // inf*0 = NaN like NumPy
+}
+
+// ------------------------------------------------------------------------------------------------
+// one particle in registers
+// ------------------------------------------------------------------------------------------------
+struct NkParticle {
+    double x, y, z, tc, occ;
+    int mode, omode;
+    double omega, vx, vy, vz;
+    int cf; double cx, cy, cz;
+    long long id;
+    bool alive;
+};
+
+// Boundary loop of one particle whose next collision lies inside the current step
+// (Population.boundary_scattering :1546-1683 with periodic_boundary_condition :1463-1489 and
+// roughness_boundary_condition :1491-1544 / select_reflected_modes :941-988 /
+// pick_diffuse_modes :990-1015), executed as a sequence of events.  `acc` receives the reservoir
+// statistics (:1585-1602).  Returns with p.alive == false when the particle was absorbed.
+__device__ __noinline__ void nk_boundary_events(const NkP& P, NkParticle& p, long long step, double* acc) {
+    const NkFace* faces = P.faces;
+    double done = 0.0;
+    double ts = p.tc;
+    unsigned int ev = 0;
+    const double dt = P.dt;
+    for (int it = 0; it < 4096; ++it) {
+        int cfi = p.cf < 0 ? P.nf - 1 : p.cf;                    // bound_cond[-1] for escaped rays (:667, :1487)
+        int cond = P.facet_bc[cfi];
+        double rem = nk_sub(1.0, done);
+        if (rem > ts) {
+            if (cond == NK_BC_T || cond == NK_BC_F) {
+                // I. absorbed by a reservoir (:1565-1608)
+                int r = P.facet_res[cfi];
+                if (r >= 0) {
+                    double e = nk_mul(nk_mul(P.hbar, p.omega), nk_sub(p.occ, nk_bose(P, P.res_T[r], p.omega)));
+                    const double* n = P.facet_normal + 3 * cfi;
+                    double vn = dot3(p.vx, p.vy, p.vz, n[0], n[1], n[2]);
+                    atomicAdd(acc + NK_ACC_NLEAVE(P.S, P.R) + r, 1.0);
+                    atomicAdd(acc + NK_ACC_EBAL(P.S, P.R) + r, -e);
+                    atomicAdd(acc + NK_ACC_RFLUX(P.S, P.R) + 3 * r + 0, nk_div(nk_mul(e, p.vx), vn));
+                    atomicAdd(acc + NK_ACC_RFLUX(P.S, P.R) + 3 * r + 1, nk_div(nk_mul(e, p.vy), vn));
+                    atomicAdd(acc + NK_ACC_RFLUX(P.S, P.R) + 3 * r + 2, nk_div(nk_mul(e, p.vz), vn));
+                }
+                p.alive = false;
+                return;
+            }
+            // start of the path segment that ends at the collision point (:1472-1474, :1504-1508)
+            double qx = p.x, qy = p.y, qz = p.z;
+            if (done == 0.0) { qx = nk_sub(qx, nk_mul(p.vx, dt)); qy = nk_sub(qy, nk_mul(p.vy, dt)); qz = nk_sub(qz, nk_mul(p.vz, dt)); }
+            double dist = norm3(nk_sub(p.cx, qx), nk_sub(p.cy, qy), nk_sub(p.cz, qz));
+            if (cond == NK_BC_P) {
+                // II. periodic wrap (:1463-1489)
+                int g = p.cf >= 0 ? P.facet_partner[p.cf] : -1;
+                if (g < 0) { P.dyn->error |= NK_ERR_EVENTS; break; }
+                const double* cg = P.facet_centroid + 3 * g; const double* ch = P.facet_centroid + 3 * p.cf;
+                double nx = nk_add(p.cx, nk_sub(cg[0], ch[0])), ny = nk_add(p.cy, nk_sub(cg[1], ch[1])), nz = nk_add(p.cz, nk_sub(cg[2], ch[2]));
+                done = nk_add(done, nk_div(dist, norm3(nk_mul(p.vx, dt), nk_mul(p.vy, dt), nk_mul(p.vz, dt))));
+                p.x = nx; p.y = ny; p.z = nz;
+                double t;
+                nk_find_boundary_1(P, faces, nx, ny, nz, p.vx, p.vy, p.vz, p.cx, p.cy, p.cz, t, p.cf);
+                ts = nk_div(t, dt);
+            } else {
+                // III. rough facet: specular or diffuse (:1491-1544, :941-1015)
+                done = nk_add(done, nk_div(dist, nk_mul(norm3(p.vx, p.vy, p.vz), dt)));
+                p.x = p.cx; p.y = p.cy; p.z = p.cz;
+                int fr = P.facet_rough[cfi];
+                double u_dice, u_pick;
+                nk_uniforms(P, p.id, step, NK_STREAM_ROUGH0 + ev, u_dice, u_pick);
+                ++ev;
+                size_t li = (size_t)fr * P.M + p.mode;
+                bool spec = P.true_spec[li] && (u_dice <= P.specularity[li]);
+                if (spec) {
+                    p.mode = P.spec_out[li];                         // omega and occupation are kept (:955-971)
+                } else {
+                    const double* rou = P.roulette + (size_t)fr * P.M;
+                    double target = nk_mul(u_pick, rou[P.M - 1]);
+                    int lo = 0, hi = P.M;                            // searchsorted left
+                    while (lo < hi) { int mid = (lo + hi) >> 1; if (rou[mid] < target) lo = mid + 1; else hi = mid; }
+                    p.mode = min(lo, P.M - 1);
+                    p.omode = p.mode;
+                    p.omega = P.mprop[p.mode].omega;
+                    double Tc = nk_particle_T(P, P.svc, P.sv_axis, P.sv_mid, P.T_sv, p.cx, p.cy, p.cz, -1);
+                    p.occ = nk_bose(P, Tc, p.omega);
+                }
+                NkMode m = P.mprop[p.mode];
+                p.vx = m.vx; p.vy = m.vy; p.vz = m.vz;
+                double t;
+                nk_find_boundary_1(P, faces, p.x, p.y, p.z, p.vx, p.vy, p.vz, p.cx, p.cy, p.cz, t, p.cf);
+                ts = nk_div(t, dt);
+            }
+            continue;
+        }
+        // IV. no further collision in this step (:1670-1681).  rem == ts never terminates upstream;
+        // here it takes this branch.
+        p.x = nk_add(p.x, nk_mul(nk_mul(p.vx, dt), rem));
+        p.y = nk_add(p.y, nk_mul(nk_mul(p.vy, dt), rem));
+        p.z = nk_add(p.z, nk_mul(nk_mul(p.vz, dt), rem));
+        ts = nk_sub(ts, rem);
+        p.tc = ts;
+        return;
+    }
+    P.dyn->error |= NK_ERR_EVENTS;
+    p.tc = ts;
+}

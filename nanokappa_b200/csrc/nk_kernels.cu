@@ -1,0 +1,1051 @@
+// nk_kernels.cu -- sm_100a kernels + C ABI of the Nano-kappa particle loop (see include/nk_b200.h).
+//
+// One timestep = four launches on one stream, no host synchronisation, replayable as a CUDA graph:
+//
+//   k_step      streaming pass over the particle SoA (84 algorithmic bytes per particle):
+//               [lifetime relaxation of the previous step] -> drift -> nearest-subvolume ->
+//               block-privatised per-SV energy/count/flux bins.  Particles whose next collision
+//               falls inside this step are only appended to a hit list.
+//   k_emit      reservoir emission over the (R, Q*J) entry table (fill_reservoirs +
+//               add_reservoir_particles), recycling free slots.
+//   k_boundary  one thread per hit-list entry: absorb / periodic / rough event loop.
+//   k_finalize  per-SV sums -> energy density -> temperature (table inversion), heat flux and
+//               kappa on convergence steps, reservoir balances; resets the accumulators.
+//
+// lifetime_scattering(k) needs T_sv(k), a grid-wide dependency; instead of a second pass over the
+// particles it is applied at the head of k_step(k+1) (nothing reads `occ` in between except
+// outputs, which call nk_flush_relaxation).  Energies use the pre-relaxation occupation and the
+// previous step's T_sv exactly like the reference (Population.py:704-713, :1754-1756).
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cmath>
+
+#include "../../include/nk_b200.h"
+#include "nk_device.cuh"
+
+// =================================================================================================
+// kernels
+// =================================================================================================
+
+// ---- shared-memory copy of the subvolume tables used by the streaming kernels --------------------
+struct NkSvSmem {
+    double* svc; double* sv_axis; double* sv_mid; double* T_sv;
+};
+__device__ __forceinline__ NkSvSmem nk_load_sv(const NkP& P, double* sm) {
+    NkSvSmem s;
+    s.svc = sm; s.sv_axis = sm + 3 * P.S; s.sv_mid = s.sv_axis + P.S; s.T_sv = s.sv_mid + P.S;
+    for (int i = threadIdx.x; i < 3 * P.S; i += blockDim.x) s.svc[i] = P.svc[i];
+    for (int i = threadIdx.x; i < P.S; i += blockDim.x) {
+        s.sv_axis[i] = P.sv_axis[i];
+        s.T_sv[i] = P.T_sv[i];
+        if (i < P.S - 1) s.sv_mid[i] = P.sv_mid[i];
+    }
+    return s;
+}
+__host__ __device__ static inline size_t nk_sv_smem_doubles(int S) { return (size_t)6 * S; }
+
+// Mesh.find_boundary operator seam: one ray per thread, triangles staged through shared memory.
+#define NK_FACE_TILE 256
+__global__ void __launch_bounds__(256) k_find_boundary(NkP P, long long n, const double* __restrict__ x,
+                                                        const double* __restrict__ v, double* __restrict__ xc,
+                                                        double* __restrict__ tc, int* __restrict__ fc) {
+    __shared__ NkFace sf[NK_FACE_TILE];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0;
+    if (i < n) { px = x[3 * i]; py = x[3 * i + 1]; pz = x[3 * i + 2]; vx = v[3 * i]; vy = v[3 * i + 1]; vz = v[3 * i + 2]; }
+    double tbest = CUDART_INF; int fbest = -1;
+    for (int f0 = 0; f0 < P.F; f0 += NK_FACE_TILE) {
+        int nt = min(NK_FACE_TILE, P.F - f0);
+        __syncthreads();
+        const double* src = reinterpret_cast<const double*>(P.faces + f0);
+        double* dst = reinterpret_cast<double*>(sf);
+        for (int k = threadIdx.x; k < nt * (int)(sizeof(NkFace) / 8); k += blockDim.x) dst[k] = src[k];
+        __syncthreads();
+        if (i < n) nk_ray_faces(sf, nt, px, py, pz, vx, vy, vz, tbest, fbest);
+    }
+    if (i < n) {
+        tc[i] = tbest; fc[i] = fbest;
+        xc[3 * i] = nk_add(px, nk_mul(tbest, vx)); xc[3 * i + 1] = nk_add(py, nk_mul(tbest, vy)); xc[3 * i + 2] = nk_add(pz, nk_mul(tbest, vz));
+    }
+}
+
+// first collision of every live slot (Population.py:308-316)
+__global__ void __launch_bounds__(256) k_init_collisions(NkP P) {
+    __shared__ NkFace sf[NK_FACE_TILE];
+    const long long n = P.dyn->n_slots;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
+        long long i = base + threadIdx.x;
+        bool live = i < n && P.mode[i] >= 0;
+        double px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0;
+        if (live) { NkMode m = P.mprop[P.mode[i]]; px = P.px[i]; py = P.py[i]; pz = P.pz[i]; vx = m.vx; vy = m.vy; vz = m.vz; }
+        double tbest = CUDART_INF; int fbest = -1;
+        for (int f0 = 0; f0 < P.F; f0 += NK_FACE_TILE) {
+            int nt = min(NK_FACE_TILE, P.F - f0);
+            __syncthreads();
+            const double* src = reinterpret_cast<const double*>(P.faces + f0);
+            double* dst = reinterpret_cast<double*>(sf);
+            for (int k = threadIdx.x; k < nt * (int)(sizeof(NkFace) / 8); k += blockDim.x) dst[k] = src[k];
+            __syncthreads();
+            if (live) nk_ray_faces(sf, nt, px, py, pz, vx, vy, vz, tbest, fbest);
+        }
+        if (live) {
+            P.tc[i] = nk_div(tbest, P.dt); P.cfacet[i] = fbest;
+            P.cx[i] = nk_add(px, nk_mul(tbest, vx)); P.cy[i] = nk_add(py, nk_mul(tbest, vy)); P.cz[i] = nk_add(pz, nk_mul(tbest, vz));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_classify(NkP P, long long n, const double* __restrict__ x, int* __restrict__ sv,
+                                                   unsigned long long* __restrict__ counts) {
+    extern __shared__ double sm[];
+    NkSvSmem s = nk_load_sv(P, sm);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(sm + nk_sv_smem_doubles(P.S));
+    for (int i = threadIdx.x; i < P.S; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int r = nk_classify(P, s.svc, s.sv_mid, x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+        sv[i] = r;
+        if (counts) atomicAdd(hist + r, 1u);
+    }
+    __syncthreads();
+    if (counts) for (int i = threadIdx.x; i < P.S; i += blockDim.x) if (hist[i]) atomicAdd(counts + i, (unsigned long long)hist[i]);
+}
+
+__global__ void k_occupation(NkP P, long long n, const double* T, const double* omega, double* occ) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        occ[i] = nk_bose(P, T[i], omega[i]);
+}
+__global__ void k_lifetime(NkP P, long long n, const double* T, const int* mode, double* tau) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        tau[i] = nk_tau(P, T[i], mode[i]);
+}
+__global__ void k_table(NkP P, long long n, const double* in, double* out, int e_to_t) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = e_to_t ? nk_interp_table(P.Ea, P.Ta, P.nE, in[i], P.Ta[0], P.Ta[P.nE - 1])
+                        : nk_interp_table(P.Ta, P.Ea, P.nE, in[i], P.Ea[0], P.Ea[P.nE - 1]);
+}
+__global__ void k_particle_T(NkP P, long long n, const double* x, double* T) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        T[i] = nk_particle_T(P, P.svc, P.sv_axis, P.sv_mid, P.T_sv, x[3 * i], x[3 * i + 1], x[3 * i + 2], -1);
+}
+
+// ---- lifetime_scattering of one particle (Population.py:1701-1710) ---------------------------------
+__device__ __forceinline__ double nk_relax(const NkP& P, double T, int mode, double omega, double occ) {
+    double tau = nk_tau(P, T, mode);
+    double n0 = nk_bose(P, T, omega);
+    if (tau > 0.0) return nk_add(n0, nk_mul(nk_sub(occ, n0), exp(nk_div(-P.dt, tau))));
+    return n0;
+}
+
+// ---- the streaming kernel ----------------------------------------------------------------------------
+#define NK_STEP_THREADS 256
+template <bool HAS_ROUGH>
+__global__ void __launch_bounds__(NK_STEP_THREADS, 3) k_step(NkP P) {
+    extern __shared__ double sm[];
+    NkSvSmem s = nk_load_sv(P, sm);
+    const int S = P.S;
+    double* binE = sm + nk_sv_smem_doubles(S);             // S
+    double* binF = binE + S;                               // 3S
+    unsigned int* binC = reinterpret_cast<unsigned int*>(binF + 3 * S);   // S
+    for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0.0; binC[i] = 0u; binF[3 * i] = 0.0; binF[3 * i + 1] = 0.0; binF[3 * i + 2] = 0.0; }
+    __syncthreads();
+
+    const long long n = P.dyn->n_slots;
+    const long long step = P.dyn->step;
+    const bool relax = P.dyn->relax_pending != 0;
+    const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
+    const double dt = P.dt;
+    const unsigned int lane = threadIdx.x & 31u;
+
+    // the loop bound is WARP-uniform (lane 0's index) because the hit-list append below uses
+    // full-mask warp votes; lanes past the end carry dead slots
+    for (long long wbase = 2 * ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); wbase < n;
+         wbase += 2 * (long long)gridDim.x * blockDim.x) {
+        const long long base = wbase + 2 * lane;
+        const bool inb = base < n;
+        double2 X = make_double2(0, 0), Y = X, Z = X, TC = X, OC = X;
+        int2 MD = make_int2(-1, -1), OM = MD;
+        if (inb) {
+            X = *reinterpret_cast<const double2*>(P.px + base);
+            Y = *reinterpret_cast<const double2*>(P.py + base);
+            Z = *reinterpret_cast<const double2*>(P.pz + base);
+            TC = *reinterpret_cast<const double2*>(P.tc + base);
+            OC = *reinterpret_cast<const double2*>(P.occ + base);
+            MD = *reinterpret_cast<const int2*>(P.mode + base);
+            OM = MD;
+            if (HAS_ROUGH) OM = *reinterpret_cast<const int2*>(P.omode + base);
+        }
+        double xs[2] = {X.x, X.y}, ys[2] = {Y.x, Y.y}, zs[2] = {Z.x, Z.y}, tcs[2] = {TC.x, TC.y}, ocs[2] = {OC.x, OC.y};
+        int mds[2] = {MD.x, MD.y}, oms[2] = {OM.x, OM.y};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            bool live = (base + k < n) && mds[k] >= 0;
+            bool hit = false;
+            if (live) {
+                NkMode mp = P.mprop[mds[k]];
+                double omega = mp.omega;
+                if (HAS_ROUGH && oms[k] != mds[k]) omega = P.mprop[oms[k]].omega;
+                double x = xs[k], y = ys[k], z = zs[k], occ = ocs[k];
+                if (relax) {
+                    double Ti = nk_particle_T(P, s.svc, s.sv_axis, s.sv_mid, s.T_sv, x, y, z, -1);
+                    occ = nk_relax(P, Ti, mds[k], omega, occ);
+                }
+                x = nk_add(x, nk_mul(mp.vx, dt)); y = nk_add(y, nk_mul(mp.vy, dt)); z = nk_add(z, nk_mul(mp.vz, dt));
+                double tcn = nk_sub(tcs[k], 1.0);
+                xs[k] = x; ys[k] = y; zs[k] = z; tcs[k] = tcn; ocs[k] = occ;
+                hit = tcn < 0.0;
+                if (!hit) {
+                    int sv = nk_classify(P, s.svc, s.sv_mid, x, y, z);
+                    double e = nk_mul(nk_mul(P.hbar, omega), nk_sub(occ, nk_bose(P, s.T_sv[sv], omega)));
+                    atomicAdd(binE + sv, e);
+                    atomicAdd(binC + sv, 1u);
+                    if (with_flux) {
+                        atomicAdd(binF + 3 * sv, nk_mul(mp.vx, e));
+                        atomicAdd(binF + 3 * sv + 1, nk_mul(mp.vy, e));
+                        atomicAdd(binF + 3 * sv + 2, nk_mul(mp.vz, e));
+                    }
+                }
+            }
+            // warp-aggregated append to the hit list
+            unsigned int m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                unsigned int leader = __ffs(m) - 1u, pos = 0;
+                if (lane == leader) pos = atomicAdd(&P.dyn->n_hits, __popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, leader);
+                if (hit) P.hitlist[pos + __popc(m & ((1u << lane) - 1u))] = (int)(base + k);
+            }
+        }
+        if (inb) {
+            *reinterpret_cast<double2*>(P.px + base) = make_double2(xs[0], xs[1]);
+            *reinterpret_cast<double2*>(P.py + base) = make_double2(ys[0], ys[1]);
+            *reinterpret_cast<double2*>(P.pz + base) = make_double2(zs[0], zs[1]);
+            *reinterpret_cast<double2*>(P.tc + base) = make_double2(tcs[0], tcs[1]);
+            *reinterpret_cast<double2*>(P.occ + base) = make_double2(ocs[0], ocs[1]);
+        }
+    }
+    __syncthreads();
+    double* acc = P.acc;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        if (binC[i]) {
+            atomicAdd(acc + NK_ACC_E(S, P.R) + i, binE[i]);
+            atomicAdd(acc + NK_ACC_CNT(S, P.R) + i, (double)binC[i]);
+            if (with_flux) {
+                atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i, binF[3 * i]);
+                atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i + 1, binF[3 * i + 1]);
+                atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i + 2, binF[3 * i + 2]);
+            }
+        }
+    }
+}
+
+// ---- helpers shared by the rare-path kernels ------------------------------------------------------------
+__device__ __forceinline__ void nk_store_particle(const NkP& P, long long i, const NkParticle& p) {
+    P.px[i] = p.x; P.py[i] = p.y; P.pz[i] = p.z; P.tc[i] = p.tc; P.occ[i] = p.occ;
+    P.mode[i] = p.mode; P.omode[i] = p.omode; P.cfacet[i] = p.cf; P.cx[i] = p.cx; P.cy[i] = p.cy; P.cz[i] = p.cz;
+}
+// refresh_temperatures contribution of one particle handled outside k_step
+__device__ __forceinline__ void nk_accumulate_global(const NkP& P, const NkParticle& p, bool with_flux) {
+    int sv = nk_classify(P, P.svc, P.sv_mid, p.x, p.y, p.z);
+    double e = nk_mul(nk_mul(P.hbar, p.omega), nk_sub(p.occ, nk_bose(P, P.T_sv[sv], p.omega)));
+    atomicAdd(P.acc + NK_ACC_E(P.S, P.R) + sv, e);
+    atomicAdd(P.acc + NK_ACC_CNT(P.S, P.R) + sv, 1.0);
+    if (with_flux) {
+        atomicAdd(P.acc + NK_ACC_FLUX(P.S, P.R) + 3 * sv, nk_mul(p.vx, e));
+        atomicAdd(P.acc + NK_ACC_FLUX(P.S, P.R) + 3 * sv + 1, nk_mul(p.vy, e));
+        atomicAdd(P.acc + NK_ACC_FLUX(P.S, P.R) + 3 * sv + 2, nk_mul(p.vz, e));
+    }
+}
+__device__ __forceinline__ void nk_kill(const NkP& P, long long i) {
+    P.mode[i] = -1;
+    long long k = atomicAdd((unsigned long long*)&P.dyn->n_free, 1ull);
+    P.freelist[k] = (int)i;
+    atomicAdd((unsigned long long*)&P.dyn->n_alive, (unsigned long long)(-1LL));
+    atomicAdd(P.acc + NK_ACC_NABS(P.S, P.R), 1.0);
+}
+
+// ---- boundary events of the hit list ----------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_boundary(NkP P) {
+    const unsigned int nh = P.dyn->n_hits;
+    const long long step = P.dyn->step;
+    const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
+    for (unsigned int h = blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += gridDim.x * blockDim.x) {
+        long long i = P.hitlist[h];
+        NkParticle p;
+        p.x = P.px[i]; p.y = P.py[i]; p.z = P.pz[i]; p.tc = P.tc[i]; p.occ = P.occ[i];
+        p.mode = P.mode[i]; p.omode = P.omode[i];
+        NkMode m = P.mprop[p.mode];
+        p.vx = m.vx; p.vy = m.vy; p.vz = m.vz;
+        p.omega = (p.omode == p.mode) ? m.omega : P.mprop[p.omode].omega;
+        p.cf = P.cfacet[i]; p.cx = P.cx[i]; p.cy = P.cy[i]; p.cz = P.cz[i];
+        p.id = P.pid[i]; p.alive = true;
+        nk_boundary_events(P, p, step, P.acc);
+        if (p.alive) {
+            nk_store_particle(P, i, p);
+            nk_accumulate_global(P, p, with_flux);
+        } else {
+            nk_kill(P, i);
+        }
+    }
+}
+
+// ---- reservoir emission (Population.fill_reservoirs 'constant' :356-406, :491-508 and
+//      add_reservoir_particles :525-552; Mesh.sample_surface Mesh.py:923-951) ---------------------------------
+__global__ void __launch_bounds__(128) k_emit(NkP P) {
+    const long long step = P.dyn->step;
+    const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
+    const int mspan = P.emit_m_hi - P.emit_m_lo;
+    const long long total = (long long)P.R * mspan;
+    const double dt = P.dt;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int r = (int)(e / mspan);
+        int m = P.emit_m_lo + (int)(e % mspan);
+        size_t idx = (size_t)r * P.M + m;
+        double prob = P.enter_prob[idx];
+        double fixed = floor(prob);
+        double cnt = nk_add(P.res_counter[idx], nk_sub(prob, fixed));
+        int extra = cnt >= 1.0 ? 1 : 0;
+        cnt = nk_sub(cnt, (double)extra);
+        P.res_counter[idx] = cnt;
+        int n_new = (int)fixed + extra;
+        if (n_new == 0) continue;
+        if (n_new > NK_EMIT_CMAX) { P.dyn->error |= NK_ERR_CMAX; n_new = NK_EMIT_CMAX; }
+        NkMode mp = P.mprop[m];
+        for (int c = n_new; c >= 1; --c) {
+            NkParticle p;
+            p.id = NK_EMIT_ID_BASE + (((step * P.R + r) * (long long)P.M + m) * NK_EMIT_CMAX + (c - 1));
+            double ua, uface, us, ur;
+            nk_uniforms(P, p.id, step, NK_STREAM_EMIT_A, ua, uface);
+            nk_uniforms(P, p.id, step, NK_STREAM_EMIT_B, us, ur);
+            double dt_in = (c == 1) ? nk_mul(dt, nk_sub(1.0, nk_div(cnt, prob)))
+                                    : nk_mul(dt, nk_sub(1.0, nk_div(nk_add((double)(c - 1), ua), prob)));
+            // face ~ area: searchsorted(cdf, u, side='right') as np.random.choice does
+            int f0 = P.res_face_ptr[r], f1 = P.res_face_ptr[r + 1];
+            int lo = f0, hi = f1;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (P.res_face_cdf[mid] <= uface) lo = mid + 1; else hi = mid; }
+            int face = P.res_faces[min(lo, f1 - 1)];
+            const double* V = P.face_vertices + 9 * (size_t)face;
+            double rs = sqrt(us);
+            double a0 = nk_sub(1.0, rs), a1 = nk_mul(nk_sub(1.0, ur), rs), a2 = nk_mul(ur, rs);
+            double x0 = nk_add(nk_add(nk_mul(a0, V[0]), nk_mul(a1, V[3])), nk_mul(a2, V[6]));
+            double y0 = nk_add(nk_add(nk_mul(a0, V[1]), nk_mul(a1, V[4])), nk_mul(a2, V[7]));
+            double z0 = nk_add(nk_add(nk_mul(a0, V[2]), nk_mul(a1, V[5])), nk_mul(a2, V[8]));
+            p.mode = m; p.omode = m; p.omega = mp.omega; p.vx = mp.vx; p.vy = mp.vy; p.vz = mp.vz;
+            double t;
+            nk_find_boundary_1(P, P.faces, x0, y0, z0, p.vx, p.vy, p.vz, p.cx, p.cy, p.cz, t, p.cf);
+            p.tc = nk_sub(nk_div(t, dt), nk_div(dt_in, dt));
+            p.x = nk_add(x0, nk_mul(p.vx, dt_in)); p.y = nk_add(y0, nk_mul(p.vy, dt_in)); p.z = nk_add(z0, nk_mul(p.vz, dt_in));
+            p.occ = nk_bose(P, P.res_T[r], p.omega);
+            p.alive = true;
+            atomicAdd(P.acc + NK_ACC_NEMIT(P.S, P.R), 1.0);
+            if (p.tc < 0.0) nk_boundary_events(P, p, step, P.acc);
+            if (!p.alive) { atomicAdd(P.acc + NK_ACC_NABS(P.S, P.R), 1.0); continue; }   // crossed the whole domain within the step
+            // slot: recycle a free one, else append
+            long long slot;
+            long long old = (long long)atomicAdd((unsigned long long*)&P.dyn->n_free, (unsigned long long)(-1LL));
+            if (old > 0) slot = P.freelist[old - 1];
+            else {
+                // empty: undo the pop (keeps n_free >= 0 once the kernel has drained) and append
+                atomicAdd((unsigned long long*)&P.dyn->n_free, 1ull);
+                slot = (long long)atomicAdd((unsigned long long*)&P.dyn->n_slots, 1ull);
+            }
+            if (slot >= P.cap) {
+                atomicAdd((unsigned long long*)&P.dyn->n_slots, (unsigned long long)(-1LL));
+                atomicOr(&P.dyn->error, NK_ERR_CAPACITY);
+                continue;
+            }
+            nk_store_particle(P, slot, p);
+            P.pid[slot] = p.id;
+            atomicAdd((unsigned long long*)&P.dyn->n_alive, 1ull);
+            nk_accumulate_global(P, p, with_flux);
+        }
+    }
+}
+
+// ---- close the step: calculate_energy normalisation, temperature_function, heat flux, kappa,
+//      reservoir balances (Population.py:704-728, :692, :730-788, :1685-1699) ------------------------------------
+__global__ void __launch_bounds__(1024) k_finalize(NkP P) {
+    extern __shared__ double sm[];
+    const int S = P.S, R = P.R;
+    double* sT = sm;             // new T_sv
+    double* sPhi = sm + S;       // flux along the slice axis
+    double* sN = sm + 2 * S;     // counts
+    double* acc = P.acc; double* out = P.out;
+    const long long step_done = P.dyn->step + 1;
+    const bool conv = (step_done % P.n_dt_to_conv) == 0;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        double cnt = acc[NK_ACC_CNT(S, R) + s];
+        double esum = acc[NK_ACC_E(S, R) + s];
+        double norm;
+        if (P.norm_mean) { norm = nk_div(P.n_active, cnt); if (norm != norm) norm = 0.0; }
+        else norm = nk_div(P.n_active, nk_mul(P.particle_density, P.sv_volume[s]));
+        double Tprev = P.T_sv[s];
+        double ref = nk_interp_table(P.Ta, P.Ea, P.nE, Tprev, P.Ea[0], P.Ea[P.nE - 1]);
+        double E = nk_add(nk_div(nk_mul(esum, norm), P.dens_norm), ref);
+        double Tn = nk_interp_table(P.Ea, P.Ta, P.nE, E, P.Ta[0], P.Ta[P.nE - 1]);
+        sT[s] = Tn; sN[s] = cnt;
+        out[NK_OUT_T(S, R) + s] = Tn;
+        out[NK_OUT_E(S, R) + s] = E;
+        out[NK_OUT_N(S, R) + s] = cnt;
+        if (conv) {
+            double f[3];
+            for (int k = 0; k < 3; ++k) {
+                f[k] = nk_mul(nk_div(nk_mul(acc[NK_ACC_FLUX(S, R) + 3 * s + k], norm), P.dens_norm), P.eVpsa2_in_Wm2);
+                out[NK_OUT_FLUX(S, R) + 3 * s + k] = f[k];
+            }
+            sPhi[s] = f[P.axis];
+        }
+    }
+    __syncthreads();
+    // reservoirs: accumulate this step, normalise on convergence steps
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        out[NK_OUT_NLEAVE(S, R) + r] = acc[NK_ACC_NLEAVE(S, R) + r];
+        double eb = nk_add(P.res_acc[r], acc[NK_ACC_EBAL(S, R) + r]);
+        double fx[3];
+        for (int k = 0; k < 3; ++k) fx[k] = nk_add(P.res_acc[R + 3 * r + k], acc[NK_ACC_RFLUX(S, R) + 3 * r + k]);
+        if (conv) {
+            double area = P.facet_area[P.res_facet[r]];
+            double den = nk_mul(nk_mul(nk_mul(P.particle_density, P.dt), (double)P.n_dt_to_conv), area);
+            double cf = nk_div(P.n_active, den);
+            for (int k = 0; k < 3; ++k) out[NK_OUT_RFLUX(S, R) + 3 * r + k] = nk_mul(nk_div(nk_mul(fx[k], cf), P.dens_norm), P.eVpsa2_in_Wm2);
+            double ce = nk_div(P.n_active, nk_mul(nk_mul(P.particle_density, P.dt), (double)P.n_dt_to_conv));
+            out[NK_OUT_REBAL(S, R) + r] = nk_div(nk_mul(eb, ce), P.dens_norm);
+            eb = 0.0; fx[0] = fx[1] = fx[2] = 0.0;
+        }
+        P.res_acc[r] = eb;
+        for (int k = 0; k < 3; ++k) P.res_acc[R + 3 * r + k] = fx[k];
+    }
+    if (threadIdx.x == 0) {
+        double np = 0.0, et = 0.0;
+        for (int s = 0; s < S; ++s) { np += sN[s]; et += acc[NK_ACC_E(S, R) + s]; }
+        out[NK_OUT_NP(S, R)] = np;
+        out[NK_OUT_ETOT(S, R)] = et;
+        if (conv && P.is_slice && R == 2) {
+            // calculate_kappa, slice subvolumes (Population.py:750-771)
+            double L = nk_sub(P.bhi[P.axis], P.blo[P.axis]);
+            double dx = nk_div(nk_mul(nk_mul(2.0, L), P.a_in_m), (double)S);
+            double DX = nk_div(nk_mul(nk_mul(L, P.a_in_m), (double)(1 + S)), (double)S);
+            double T0 = P.res_T[0], T1 = P.res_T[1];
+            double sum = 0.0;
+            for (int s = 0; s < S; ++s) {
+                double Tm = s == 0 ? T0 : sT[s - 1];
+                double Tp = s == S - 1 ? T1 : sT[s + 1];
+                double k = nk_div(nk_mul(-sPhi[s], dx), nk_sub(Tp, Tm));
+                if (isinf(k)) k = 0.0;
+                out[NK_OUT_KSV(S, R) + s] = k;
+                sum += nk_mul(sPhi[s], sN[s]);
+            }
+            out[NK_OUT_KAPPA(S, R)] = nk_div(nk_mul(-sum, nk_div(DX, nk_sub(T1, T0))), np);
+        }
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < S; s += blockDim.x) P.T_sv[s] = sT[s];
+    for (int i = threadIdx.x; i < nk_acc_len(S, R); i += blockDim.x) acc[i] = 0.0;
+    if (threadIdx.x == 0) {
+        NkDyn* d = P.dyn;
+        d->step = step_done;
+        d->relax_pending = 1;
+        d->n_hits = 0;
+        if (d->n_free < 0) d->n_free = 0;
+    }
+}
+
+// apply the deferred lifetime_scattering so that `occ` is what the reference holds after run_timestep
+__global__ void __launch_bounds__(256) k_flush_relax(NkP P) {
+    extern __shared__ double sm[];
+    NkSvSmem s = nk_load_sv(P, sm);
+    __syncthreads();
+    if (!P.dyn->relax_pending) return;
+    const long long n = P.dyn->n_slots;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int md = P.mode[i];
+        if (md < 0) continue;
+        int om = P.omode[i];
+        double omega = P.mprop[om].omega;
+        double Ti = nk_particle_T(P, s.svc, s.sv_axis, s.sv_mid, s.T_sv, P.px[i], P.py[i], P.pz[i], -1);
+        P.occ[i] = nk_relax(P, Ti, md, omega, P.occ[i]);
+    }
+}
+__global__ void k_clear_relax(NkP P) { P.dyn->relax_pending = 0; }
+
+// =================================================================================================
+// host side
+// =================================================================================================
+struct nk_ctx {
+    int device = 0;
+    NkP P;
+    cudaStream_t stream = 0;
+    std::string err;
+    std::vector<void*> owned;      // device allocations freed in nk_destroy
+    int n_sm = 148;
+    int has_rough = 0;
+    bool particles_bound = false;
+    // host mirrors needed to rebuild derived tables
+    std::vector<double> h_tau, h_Tg;
+    double hot_lo = 0, hot_hi = 0;
+    int step_blocks = 0;
+};
+
+static std::string g_create_err;
+
+#define NK_CK(call)                                                                          \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+            return -1;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+template <class T>
+static T* nk_upload(nk_ctx* ctx, const T* h, size_t n) {
+    T* d = nullptr;
+    size_t bytes = (n ? n : 1) * sizeof(T);
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+    ctx->owned.push_back(d);
+    if (n && h) {
+        if (cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    } else {
+        cudaMemset(d, 0, bytes);
+    }
+    return d;
+}
+#define NK_UP(dst, T, h, n)                                                     \
+    do {                                                                        \
+        dst = nk_upload<T>(ctx, h, n);                                          \
+        if (!dst) { ctx->err = "device allocation/upload failed: " #dst; return -1; } \
+    } while (0)
+
+extern "C" {
+
+int nk_version(void) { return 100; }
+
+const char* nk_last_error(nk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int nk_create(int device, nk_ctx** out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return -1;
+    }
+    if (device < 0 || device >= n) { g_create_err = "device index out of range"; return -1; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return -1; }
+    nk_ctx* ctx = new nk_ctx();
+    memset(&ctx->P, 0, sizeof(NkP));
+    ctx->device = device;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->n_sm = prop.multiProcessorCount;
+    ctx->P.world = 1;
+    NkDyn z; memset(&z, 0, sizeof(z));
+    ctx->P.dyn = nk_upload<NkDyn>(ctx, &z, 1);
+    *out = ctx;
+    return 0;
+}
+
+void nk_destroy(nk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (void* p : ctx->owned) cudaFree(p);
+    delete ctx;
+}
+
+int nk_set_stream(nk_ctx* ctx, void* s) { ctx->stream = (cudaStream_t)s; return 0; }
+int nk_synchronize(nk_ctx* ctx) { NK_CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+
+int nk_set_mesh(nk_ctx* ctx, int F, const double* fn, const double* fk, const double* flo, const double* fhi,
+                const double* fo, const double* fb, const int32_t* ff, const double* fverts, const double* fareas,
+                int nf, const int32_t* bc, const int32_t* partner, const int32_t* fres, const int32_t* frough,
+                const double* fnormal, const double* fcentroid, const double* farea,
+                const int32_t* ffptr, const int32_t* ffaces, const double* bounds) {
+    cudaSetDevice(ctx->device);
+    std::vector<NkFace> faces(F);
+    for (int f = 0; f < F; ++f) {
+        NkFace& T = faces[f];
+        T.nx = fn[3 * f]; T.ny = fn[3 * f + 1]; T.nz = fn[3 * f + 2]; T.k = fk[f];
+        T.lox = flo[3 * f] - NK_TOL; T.loy = flo[3 * f + 1] - NK_TOL; T.loz = flo[3 * f + 2] - NK_TOL;
+        T.hix = fhi[3 * f] + NK_TOL; T.hiy = fhi[3 * f + 1] + NK_TOL; T.hiz = fhi[3 * f + 2] + NK_TOL;
+        T.ox = fo[3 * f]; T.oy = fo[3 * f + 1]; T.oz = fo[3 * f + 2];
+        // inverse of A = face_basis_matrix (columns b1, b2, n), rows 0 and 1, by cofactors
+        const double* A = fb + 9 * f;
+        double a = A[0], b = A[1], c = A[2], d = A[3], e = A[4], g = A[5], h = A[6], i = A[7], j = A[8];
+        double det = a * (e * j - g * i) - b * (d * j - g * h) + c * (d * i - e * h);
+        T.ia0 = (e * j - g * i) / det; T.ia1 = (c * i - b * j) / det; T.ia2 = (b * g - c * e) / det;
+        T.ib0 = (g * h - d * j) / det; T.ib1 = (a * j - c * h) / det; T.ib2 = (c * d - a * g) / det;
+        T.facet = (double)ff[f];
+    }
+    NkP& P = ctx->P;
+    P.F = F; P.nf = nf;
+    NkFace* dfaces; NK_UP(dfaces, NkFace, faces.data(), (size_t)F); P.faces = dfaces;
+    int* di; double* dd;
+    NK_UP(di, int, bc, nf); P.facet_bc = di;
+    NK_UP(di, int, partner, nf); P.facet_partner = di;
+    NK_UP(di, int, fres, nf); P.facet_res = di;
+    NK_UP(di, int, frough, nf); P.facet_rough = di;
+    NK_UP(dd, double, fnormal, 3 * (size_t)nf); P.facet_normal = dd;
+    NK_UP(dd, double, fcentroid, 3 * (size_t)nf); P.facet_centroid = dd;
+    NK_UP(dd, double, farea, nf); P.facet_area = dd;
+    NK_UP(dd, double, fverts, 9 * (size_t)F); P.face_vertices = dd;
+    for (int k = 0; k < 3; ++k) { P.blo[k] = bounds[k]; P.bhi[k] = bounds[3 + k]; }
+    // reservoir sampling tables: facets with res >= 0, in reservoir order
+    int R = 0;
+    for (int f = 0; f < nf; ++f) if (fres[f] >= 0) R = std::max(R, fres[f] + 1);
+    std::vector<int> rptr(R + 1, 0), rfaces; std::vector<double> rcdf;
+    for (int r = 0; r < R; ++r) {
+        int facet = -1;
+        for (int f = 0; f < nf; ++f) if (fres[f] == r) facet = f;
+        rptr[r] = (int)rfaces.size();
+        if (facet >= 0) {
+            // np.random.choice(faces, p = areas/areas.sum()): cdf = cumsum(p); cdf /= cdf[-1]
+            double tot = 0.0;
+            for (int q = ffptr[facet]; q < ffptr[facet + 1]; ++q) tot += fareas[ffaces[q]];
+            std::vector<double> cdf; double run = 0.0;
+            for (int q = ffptr[facet]; q < ffptr[facet + 1]; ++q) { run += fareas[ffaces[q]] / tot; cdf.push_back(run); rfaces.push_back(ffaces[q]); }
+            for (double& cval : cdf) cval /= run;
+            rcdf.insert(rcdf.end(), cdf.begin(), cdf.end());
+        }
+    }
+    rptr[R] = (int)rfaces.size();
+    NK_UP(di, int, rptr.data(), rptr.size()); P.res_face_ptr = di;
+    NK_UP(di, int, rfaces.data(), rfaces.size()); P.res_faces = di;
+    NK_UP(dd, double, rcdf.data(), rcdf.size()); P.res_face_cdf = dd;
+    return 0;
+}
+
+int nk_set_subvols(nk_ctx* ctx, int S, const double* centres, const double* volumes, int is_slice, int axis, int interp) {
+    cudaSetDevice(ctx->device);
+    NkP& P = ctx->P;
+    if (S < 1) { ctx->err = "n_subvols must be >= 1"; return -1; }
+    if (interp == NK_INTERP_LINEAR && !is_slice) { ctx->err = "linear temperature interpolation needs slice subvolumes (radial/RBF not on the GPU path yet)"; return -1; }
+    P.S = S; P.is_slice = is_slice; P.axis = axis; P.interp = interp;
+    double* dd;
+    NK_UP(dd, double, centres, 3 * (size_t)S); P.svc = dd;
+    NK_UP(dd, double, volumes, S); P.sv_volume = dd;
+    std::vector<double> ax(S), mid(S > 1 ? S - 1 : 1, 0.0);
+    for (int s = 0; s < S; ++s) ax[s] = centres[3 * s + axis];
+    for (int s = 0; s + 1 < S; ++s) mid[s] = ax[s + 1] / 2.0 + ax[s] / 2.0;   // x_bds = x/2; x_bds[1:] + x_bds[:-1]
+    NK_UP(dd, double, ax.data(), S); P.sv_axis = dd;
+    NK_UP(dd, double, mid.data(), mid.size()); P.sv_mid = dd;
+    P.sv_inv_dx = (S > 1 && ax[S - 1] != ax[0]) ? (S - 1) / (ax[S - 1] - ax[0]) : 0.0;
+    std::vector<double> T0(S, 0.0);
+    NK_UP(P.T_sv, double, T0.data(), S);
+    return 0;
+}
+
+static int nk_build_tau4(nk_ctx* ctx) {
+    NkP& P = ctx->P;
+    if (ctx->h_tau.empty()) return 0;
+    int NT = P.NT, M = P.M;
+    // slabs i0..i0+3 cover [Tg[i0], Tg[i0+3]]: centre the window on the expected temperature range
+    int ilo = 0;
+    while (ilo + 1 < NT - 1 && ctx->h_Tg[ilo + 1] <= ctx->hot_lo) ++ilo;
+    int ihi = ilo;
+    while (ihi + 1 < NT - 1 && ctx->h_Tg[ihi + 1] <= ctx->hot_hi) ++ihi;
+    int i0 = ilo - std::max(0, (2 - (ihi - ilo)) / 2);
+    i0 = std::max(0, std::min(i0, NT - 4));
+    if (NT < 4) i0 = 0;
+    std::vector<NkTau4> t4(M);
+    for (int m = 0; m < M; ++m)
+        for (int k = 0; k < 4; ++k) t4[m].t[k] = (i0 + k < NT) ? ctx->h_tau[(size_t)(i0 + k) * M + m] : 0.0;
+    NkTau4* d; NK_UP(d, NkTau4, t4.data(), (size_t)M);
+    P.tau4 = d; P.tau_i0 = (NT >= 4) ? i0 : -1000000;
+    return 0;
+}
+
+int nk_set_phonon(nk_ctx* ctx, int Q, int J, int NT, const double* Tg, const double* omega, const double* vg,
+                  const double* tau, double hbar, double kb, double V_uc, int64_t n_active,
+                  int nE, const double* Ea, const double* Ta) {
+    cudaSetDevice(ctx->device);
+    NkP& P = ctx->P;
+    if (NT < 2) { ctx->err = "need at least two temperatures"; return -1; }
+    P.Q = Q; P.J = J; P.M = Q * J; P.NT = NT;
+    int M = P.M;
+    std::vector<NkMode> mp(M);
+    for (int m = 0; m < M; ++m) { mp[m].omega = omega[m]; mp[m].vx = vg[3 * m]; mp[m].vy = vg[3 * m + 1]; mp[m].vz = vg[3 * m + 2]; }
+    NkMode* dm; NK_UP(dm, NkMode, mp.data(), (size_t)M); P.mprop = dm;
+    double* dd;
+    NK_UP(dd, double, Tg, NT); P.Tg = dd;
+    NK_UP(dd, double, tau, (size_t)NT * M); P.tau = dd;
+    NK_UP(dd, double, Ea, nE); P.Ea = dd;
+    NK_UP(dd, double, Ta, nE); P.Ta = dd;
+    P.nE = nE; P.hbar = hbar; P.kb = kb; P.V_uc = V_uc; P.n_active = (double)n_active;
+    P.dens_norm = (double)Q * V_uc;
+    P.Tg_inv_d = 1.0 / (Tg[1] - Tg[0]);
+    ctx->h_tau.assign(tau, tau + (size_t)NT * M);
+    ctx->h_Tg.assign(Tg, Tg + NT);
+    if (ctx->hot_hi == 0) { ctx->hot_lo = 295.0; ctx->hot_hi = 305.0; }
+    P.emit_m_lo = 0; P.emit_m_hi = M;
+    return nk_build_tau4(ctx);
+}
+
+int nk_set_population(nk_ctx* ctx, double dt, int norm_mean, double density, int n_dt_to_conv, uint64_t seed,
+                      double unit_flux, double a_in_m, double hot_lo, double hot_hi) {
+    cudaSetDevice(ctx->device);
+    NkP& P = ctx->P;
+    P.dt = dt; P.norm_mean = norm_mean; P.particle_density = density; P.n_dt_to_conv = n_dt_to_conv;
+    P.seed_lo = (unsigned int)(seed & 0xFFFFFFFFull); P.seed_hi = (unsigned int)(seed >> 32);
+    P.eVpsa2_in_Wm2 = unit_flux; P.a_in_m = a_in_m;
+    ctx->hot_lo = hot_lo; ctx->hot_hi = hot_hi;
+    return nk_build_tau4(ctx);
+}
+
+static int nk_alloc_scratch(nk_ctx* ctx) {
+    NkP& P = ctx->P;
+    double* dd;
+    NK_UP(dd, double, (const double*)nullptr, (size_t)nk_acc_len(P.S, P.R)); P.acc = dd;
+    NK_UP(dd, double, (const double*)nullptr, (size_t)4 * std::max(P.R, 1)); P.res_acc = dd;
+    NK_UP(dd, double, (const double*)nullptr, (size_t)nk_out_len(P.S, P.R)); P.out = dd;
+    return 0;
+}
+
+int nk_set_reservoirs(nk_ctx* ctx, int R, const int32_t* res_facet, const double* res_T, const double* enter_prob,
+                      const double* res_counter) {
+    cudaSetDevice(ctx->device);
+    NkP& P = ctx->P;
+    if (P.M == 0 || P.S == 0) { ctx->err = "call nk_set_phonon and nk_set_subvols before nk_set_reservoirs"; return -1; }
+    P.R = R;
+    int* di; double* dd;
+    NK_UP(di, int, res_facet, R); P.res_facet = di;
+    NK_UP(dd, double, res_T, R); P.res_T = dd;
+    NK_UP(dd, double, enter_prob, (size_t)R * P.M); P.enter_prob = dd;
+    NK_UP(dd, double, res_counter, (size_t)R * P.M); P.res_counter = dd;
+    return nk_alloc_scratch(ctx);
+}
+
+int nk_get_res_counter(nk_ctx* ctx, double* h) {
+    cudaSetDevice(ctx->device);
+    NK_CK(cudaStreamSynchronize(ctx->stream));
+    NK_CK(cudaMemcpy(h, ctx->P.res_counter, (size_t)ctx->P.R * ctx->P.M * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int nk_set_boundary_luts(nk_ctx* ctx, int Fr, const double* spec, const uint8_t* ts, const int32_t* so, const double* rou) {
+    cudaSetDevice(ctx->device);
+    NkP& P = ctx->P;
+    P.Fr = Fr;
+    size_t n = (size_t)Fr * P.M;
+    double* dd; unsigned char* du; int* di;
+    NK_UP(dd, double, spec, n); P.specularity = dd;
+    NK_UP(du, unsigned char, ts, n); P.true_spec = du;
+    NK_UP(di, int, so, n); P.spec_out = di;
+    NK_UP(dd, double, rou, n); P.roulette = dd;
+    ctx->has_rough = Fr > 0;
+    return 0;
+}
+
+int nk_bind_particles(nk_ctx* ctx, int64_t cap, double* px, double* py, double* pz, double* tc, double* occ,
+                      int32_t* mode, int32_t* omode, int32_t* cfacet, double* cx, double* cy, double* cz, int64_t* pid) {
+    cudaSetDevice(ctx->device);
+    NkP& P = ctx->P;
+    if (cap < 2 || (cap & 1)) { ctx->err = "capacity must be even and >= 2"; return -1; }
+    if (cap > 2147483646LL) { ctx->err = "capacity above 2^31-2 slots per GPU is not supported"; return -1; }
+    if (((uintptr_t)px | (uintptr_t)py | (uintptr_t)pz | (uintptr_t)tc | (uintptr_t)occ) & 15) { ctx->err = "particle arrays must be 16-byte aligned"; return -1; }
+    if (((uintptr_t)mode | (uintptr_t)omode) & 7) { ctx->err = "mode arrays must be 8-byte aligned"; return -1; }
+    P.cap = cap; P.px = px; P.py = py; P.pz = pz; P.tc = tc; P.occ = occ; P.mode = mode; P.omode = omode; P.cfacet = cfacet;
+    P.cx = cx; P.cy = cy; P.cz = cz; P.pid = (long long*)pid;
+    int* di;
+    NK_UP(di, int, (const int*)nullptr, (size_t)cap); P.hitlist = di;
+    NK_UP(di, int, (const int*)nullptr, (size_t)cap); P.freelist = di;
+    ctx->particles_bound = true;
+    return 0;
+}
+
+static int nk_read_dyn(nk_ctx* ctx, NkDyn* d) {
+    NK_CK(cudaStreamSynchronize(ctx->stream));
+    NK_CK(cudaMemcpy(d, ctx->P.dyn, sizeof(NkDyn), cudaMemcpyDeviceToHost));
+    return 0;
+}
+static int nk_write_dyn(nk_ctx* ctx, const NkDyn* d) {
+    NK_CK(cudaStreamSynchronize(ctx->stream));
+    NK_CK(cudaMemcpy(ctx->P.dyn, d, sizeof(NkDyn), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// count live slots (mode >= 0) on the host side of a tiny kernel-free path: done with a reduction kernel
+__global__ void k_count_alive(NkP P, unsigned long long* out) {
+    const long long n = P.dyn->n_slots;
+    unsigned long long c = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) c += P.mode[i] >= 0;
+    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots) {
+    cudaSetDevice(ctx->device);
+    if (!ctx->particles_bound) { ctx->err = "nk_bind_particles first"; return -1; }
+    if (n_slots < 0 || n_slots > ctx->P.cap) { ctx->err = "n_slots out of range"; return -1; }
+    NkDyn d; if (nk_read_dyn(ctx, &d)) return -1;
+    d.n_slots = n_slots; d.n_free = 0; d.n_hits = 0;
+    if (nk_write_dyn(ctx, &d)) return -1;
+    unsigned long long* dc; NK_CK(cudaMalloc(&dc, 8)); NK_CK(cudaMemset(dc, 0, 8));
+    k_count_alive<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->P, dc);
+    unsigned long long hc = 0;
+    NK_CK(cudaStreamSynchronize(ctx->stream));
+    NK_CK(cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost));
+    cudaFree(dc);
+    if (nk_read_dyn(ctx, &d)) return -1;
+    d.n_alive = (long long)hc;
+    return nk_write_dyn(ctx, &d);
+}
+
+int nk_get_slot_count(nk_ctx* ctx, int64_t* n_slots, int64_t* n_alive) {
+    cudaSetDevice(ctx->device);
+    NkDyn d; if (nk_read_dyn(ctx, &d)) return -1;
+    if (d.error) {
+        ctx->err = std::string("device error bits: ") + ((d.error & NK_ERR_CAPACITY) ? "[particle capacity exhausted] " : "") +
+                   ((d.error & NK_ERR_EVENTS) ? "[boundary event cap / broken periodic pair] " : "") +
+                   ((d.error & NK_ERR_CMAX) ? "[more than 64 copies of one mode emitted in a step] " : "");
+        return -2;
+    }
+    if (n_slots) *n_slots = d.n_slots;
+    if (n_alive) *n_alive = d.n_alive;
+    return 0;
+}
+
+int nk_set_sv_temperature(nk_ctx* ctx, const double* T) {
+    cudaSetDevice(ctx->device);
+    NK_CK(cudaStreamSynchronize(ctx->stream));
+    NK_CK(cudaMemcpy(ctx->P.T_sv, T, ctx->P.S * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+int nk_get_sv_temperature(nk_ctx* ctx, double* T) {
+    cudaSetDevice(ctx->device);
+    NK_CK(cudaStreamSynchronize(ctx->stream));
+    NK_CK(cudaMemcpy(T, ctx->P.T_sv, ctx->P.S * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int nk_set_timestep(nk_ctx* ctx, int64_t k) {
+    cudaSetDevice(ctx->device);
+    NkDyn d; if (nk_read_dyn(ctx, &d)) return -1;
+    d.step = k; d.relax_pending = 0;
+    return nk_write_dyn(ctx, &d);
+}
+int nk_get_timestep(nk_ctx* ctx, int64_t* k) {
+    cudaSetDevice(ctx->device);
+    NkDyn d; if (nk_read_dyn(ctx, &d)) return -1;
+    *k = d.step; return 0;
+}
+
+// ---- operator seams ----------------------------------------------------------------------------------------
+static inline int nk_grid(long long n, int threads, int cap_blocks) {
+    long long b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (cap_blocks > 0 && b > cap_blocks) b = cap_blocks;
+    return (int)b;
+}
+
+int nk_find_boundary(nk_ctx* ctx, int64_t n, const double* x, const double* v, double* xc, double* tc, int32_t* fc) {
+    cudaSetDevice(ctx->device);
+    if (n <= 0) return 0;
+    k_find_boundary<<<nk_grid(n, 256, 0), 256, 0, ctx->stream>>>(ctx->P, n, x, v, xc, tc, fc);
+    NK_CK(cudaGetLastError());
+    return 0;
+}
+int nk_classify(nk_ctx* ctx, int64_t n, const double* x, int32_t* sv, int64_t* counts) {
+    cudaSetDevice(ctx->device);
+    if (counts) NK_CK(cudaMemsetAsync(counts, 0, ctx->P.S * sizeof(int64_t), ctx->stream));
+    if (n <= 0) return 0;
+    size_t smem = nk_sv_smem_doubles(ctx->P.S) * 8 + ctx->P.S * 4;
+    k_classify<<<nk_grid(n, 256, ctx->n_sm * 8), 256, smem, ctx->stream>>>(ctx->P, n, x, sv, (unsigned long long*)counts);
+    NK_CK(cudaGetLastError());
+    return 0;
+}
+int nk_occupation(nk_ctx* ctx, int64_t n, const double* T, const double* omega, double* occ) {
+    cudaSetDevice(ctx->device);
+    if (n <= 0) return 0;
+    k_occupation<<<nk_grid(n, 256, ctx->n_sm * 8), 256, 0, ctx->stream>>>(ctx->P, n, T, omega, occ);
+    NK_CK(cudaGetLastError());
+    return 0;
+}
+int nk_lifetime(nk_ctx* ctx, int64_t n, const double* T, const int32_t* mode, double* tau) {
+    cudaSetDevice(ctx->device);
+    if (n <= 0) return 0;
+    k_lifetime<<<nk_grid(n, 256, ctx->n_sm * 8), 256, 0, ctx->stream>>>(ctx->P, n, T, mode, tau);
+    NK_CK(cudaGetLastError());
+    return 0;
+}
+int nk_temperature_of_energy(nk_ctx* ctx, int64_t n, const double* E, double* T) {
+    cudaSetDevice(ctx->device);
+    if (n <= 0) return 0;
+    k_table<<<nk_grid(n, 256, ctx->n_sm * 8), 256, 0, ctx->stream>>>(ctx->P, n, E, T, 1);
+    NK_CK(cudaGetLastError());
+    return 0;
+}
+int nk_energy_of_temperature(nk_ctx* ctx, int64_t n, const double* T, double* E) {
+    cudaSetDevice(ctx->device);
+    if (n <= 0) return 0;
+    k_table<<<nk_grid(n, 256, ctx->n_sm * 8), 256, 0, ctx->stream>>>(ctx->P, n, T, E, 0);
+    NK_CK(cudaGetLastError());
+    return 0;
+}
+int nk_particle_temperature(nk_ctx* ctx, int64_t n, const double* x, double* T) {
+    cudaSetDevice(ctx->device);
+    if (n <= 0) return 0;
+    k_particle_T<<<nk_grid(n, 256, ctx->n_sm * 8), 256, 0, ctx->stream>>>(ctx->P, n, x, T);
+    NK_CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- the timestep ---------------------------------------------------------------------------------------------
+static int nk_check_ready(nk_ctx* ctx) {
+    const NkP& P = ctx->P;
+    if (!ctx->particles_bound) { ctx->err = "particles not bound"; return -1; }
+    if (!P.faces || !P.svc || !P.mprop || !P.acc) { ctx->err = "tables missing: call nk_set_mesh, nk_set_subvols, nk_set_phonon, nk_set_population, nk_set_reservoirs first"; return -1; }
+    if (P.dt <= 0) { ctx->err = "nk_set_population not called"; return -1; }
+    return 0;
+}
+
+int nk_init_collisions(nk_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    if (nk_check_ready(ctx)) return -1;
+    k_init_collisions<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(ctx->P);
+    NK_CK(cudaGetLastError());
+    return 0;
+}
+
+static size_t nk_step_smem(const NkP& P) { return (nk_sv_smem_doubles(P.S) + 4 * (size_t)P.S) * 8 + (size_t)P.S * 4 + 8; }
+
+int nk_step_local(nk_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    if (nk_check_ready(ctx)) return -1;
+    const NkP& P = ctx->P;
+    size_t smem = nk_step_smem(P);
+    if (!ctx->step_blocks) {
+        int per_sm = 0;
+        if (ctx->has_rough) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step<true>, NK_STEP_THREADS, smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step<false>, NK_STEP_THREADS, smem);
+        if (per_sm < 1) per_sm = 1;
+        ctx->step_blocks = per_sm * ctx->n_sm;
+    }
+    if (ctx->has_rough) k_step<true><<<ctx->step_blocks, NK_STEP_THREADS, smem, ctx->stream>>>(P);
+    else k_step<false><<<ctx->step_blocks, NK_STEP_THREADS, smem, ctx->stream>>>(P);
+    NK_CK(cudaGetLastError());
+    if (P.R > 0) {
+        long long total = (long long)P.R * (P.emit_m_hi - P.emit_m_lo);
+        k_emit<<<nk_grid(total, 128, ctx->n_sm * 16), 128, 0, ctx->stream>>>(P);
+        NK_CK(cudaGetLastError());
+    }
+    k_boundary<<<ctx->n_sm * 4, 128, 0, ctx->stream>>>(P);
+    NK_CK(cudaGetLastError());
+    return 0;
+}
+
+int nk_step_finalize(nk_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    const NkP& P = ctx->P;
+    int threads = 32;
+    while (threads < P.S && threads < 1024) threads <<= 1;
+    k_finalize<<<1, threads, 3 * (size_t)P.S * 8, ctx->stream>>>(P);
+    NK_CK(cudaGetLastError());
+    return 0;
+}
+
+int nk_step(nk_ctx* ctx, int n_steps) {
+    for (int k = 0; k < n_steps; ++k) {
+        if (nk_step_local(ctx)) return -1;
+        if (nk_step_finalize(ctx)) return -1;
+    }
+    return 0;
+}
+
+int nk_flush_relaxation(nk_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    if (nk_check_ready(ctx)) return -1;
+    size_t smem = nk_sv_smem_doubles(ctx->P.S) * 8;
+    k_flush_relax<<<ctx->n_sm * 8, 256, smem, ctx->stream>>>(ctx->P);
+    NK_CK(cudaGetLastError());
+    k_clear_relax<<<1, 1, 0, ctx->stream>>>(ctx->P);
+    NK_CK(cudaGetLastError());
+    return 0;
+}
+
+int nk_get_results(nk_ctx* ctx, double* T_sv, double* E_sv, int64_t* N_sv, double* flux, double* kappa_sv, double* kappa,
+                   double* res_E_bal, double* res_flux, int64_t* N_leaving, double* total_energy) {
+    cudaSetDevice(ctx->device);
+    const NkP& P = ctx->P;
+    const int S = P.S, R = P.R;
+    std::vector<double> h(nk_out_len(S, R));
+    NK_CK(cudaStreamSynchronize(ctx->stream));
+    NK_CK(cudaMemcpy(h.data(), P.out, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    if (T_sv) memcpy(T_sv, &h[NK_OUT_T(S, R)], S * 8);
+    if (E_sv) memcpy(E_sv, &h[NK_OUT_E(S, R)], S * 8);
+    if (N_sv) for (int s = 0; s < S; ++s) N_sv[s] = (int64_t)h[NK_OUT_N(S, R) + s];
+    if (flux) memcpy(flux, &h[NK_OUT_FLUX(S, R)], 3 * S * 8);
+    if (kappa_sv) memcpy(kappa_sv, &h[NK_OUT_KSV(S, R)], S * 8);
+    if (kappa) *kappa = h[NK_OUT_KAPPA(S, R)];
+    if (res_E_bal) memcpy(res_E_bal, &h[NK_OUT_REBAL(S, R)], R * 8);
+    if (res_flux) memcpy(res_flux, &h[NK_OUT_RFLUX(S, R)], 3 * R * 8);
+    if (N_leaving) for (int r = 0; r < R; ++r) N_leaving[r] = (int64_t)h[NK_OUT_NLEAVE(S, R) + r];
+    if (total_energy) *total_energy = h[NK_OUT_ETOT(S, R)];
+    return 0;
+}
+
+int nk_advance_host(nk_ctx* ctx, int64_t n_in, int n_steps, double* px, double* py, double* pz, double* tc, double* occ,
+                    int32_t* mode, int32_t* omode, int32_t* cfacet, double* cx, double* cy, double* cz, int64_t* pid,
+                    int64_t* n_out, double* T_sv_out, double* E_sv_out, int64_t* N_sv_out) {
+    cudaSetDevice(ctx->device);
+    if (nk_check_ready(ctx)) return -1;
+    NkP& P = ctx->P;
+    if (n_in > P.cap) { ctx->err = "n_in exceeds bound capacity"; return -1; }
+    cudaStream_t st = ctx->stream;
+    size_t n = (size_t)n_in;
+    NK_CK(cudaMemcpyAsync(P.px, px, n * 8, cudaMemcpyHostToDevice, st));
+    NK_CK(cudaMemcpyAsync(P.py, py, n * 8, cudaMemcpyHostToDevice, st));
+    NK_CK(cudaMemcpyAsync(P.pz, pz, n * 8, cudaMemcpyHostToDevice, st));
+    NK_CK(cudaMemcpyAsync(P.tc, tc, n * 8, cudaMemcpyHostToDevice, st));
+    NK_CK(cudaMemcpyAsync(P.occ, occ, n * 8, cudaMemcpyHostToDevice, st));
+    NK_CK(cudaMemcpyAsync(P.mode, mode, n * 4, cudaMemcpyHostToDevice, st));
+    NK_CK(cudaMemcpyAsync(P.omode, omode, n * 4, cudaMemcpyHostToDevice, st));
+    NK_CK(cudaMemcpyAsync(P.cfacet, cfacet, n * 4, cudaMemcpyHostToDevice, st));
+    NK_CK(cudaMemcpyAsync(P.cx, cx, n * 8, cudaMemcpyHostToDevice, st));
+    NK_CK(cudaMemcpyAsync(P.cy, cy, n * 8, cudaMemcpyHostToDevice, st));
+    NK_CK(cudaMemcpyAsync(P.cz, cz, n * 8, cudaMemcpyHostToDevice, st));
+    NK_CK(cudaMemcpyAsync(P.pid, pid, n * 8, cudaMemcpyHostToDevice, st));
+    if (nk_set_slot_count(ctx, n_in)) return -1;
+    if (nk_step(ctx, n_steps)) return -1;
+    if (nk_flush_relaxation(ctx)) return -1;
+    int64_t ns = 0, na = 0;
+    if (nk_get_slot_count(ctx, &ns, &na)) return -1;
+    size_t m = (size_t)ns;
+    NK_CK(cudaMemcpyAsync(px, P.px, m * 8, cudaMemcpyDeviceToHost, st));
+    NK_CK(cudaMemcpyAsync(py, P.py, m * 8, cudaMemcpyDeviceToHost, st));
+    NK_CK(cudaMemcpyAsync(pz, P.pz, m * 8, cudaMemcpyDeviceToHost, st));
+    NK_CK(cudaMemcpyAsync(tc, P.tc, m * 8, cudaMemcpyDeviceToHost, st));
+    NK_CK(cudaMemcpyAsync(occ, P.occ, m * 8, cudaMemcpyDeviceToHost, st));
+    NK_CK(cudaMemcpyAsync(mode, P.mode, m * 4, cudaMemcpyDeviceToHost, st));
+    NK_CK(cudaMemcpyAsync(omode, P.omode, m * 4, cudaMemcpyDeviceToHost, st));
+    NK_CK(cudaMemcpyAsync(cfacet, P.cfacet, m * 4, cudaMemcpyDeviceToHost, st));
+    NK_CK(cudaMemcpyAsync(cx, P.cx, m * 8, cudaMemcpyDeviceToHost, st));
+    NK_CK(cudaMemcpyAsync(cy, P.cy, m * 8, cudaMemcpyDeviceToHost, st));
+    NK_CK(cudaMemcpyAsync(cz, P.cz, m * 8, cudaMemcpyDeviceToHost, st));
+    NK_CK(cudaMemcpyAsync(pid, P.pid, m * 8, cudaMemcpyDeviceToHost, st));
+    NK_CK(cudaStreamSynchronize(st));
+    if (n_out) *n_out = ns;
+    return nk_get_results(ctx, T_sv_out, E_sv_out, N_sv_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+// ---- multi-GPU plumbing ---------------------------------------------------------------------------------------
+int nk_set_rank(nk_ctx* ctx, int rank, int world) {
+    NkP& P = ctx->P;
+    if (world < 1 || rank < 0 || rank >= world) { ctx->err = "bad rank/world"; return -1; }
+    if (P.M == 0) { ctx->err = "nk_set_phonon first"; return -1; }
+    P.rank = rank; P.world = world;
+    long long M = P.M;
+    P.emit_m_lo = (int)(M * rank / world);
+    P.emit_m_hi = (int)(M * (rank + 1) / world);
+    return 0;
+}
+int nk_acc_buffer(nk_ctx* ctx, double** p, int64_t* n) {
+    if (!ctx->P.acc) { ctx->err = "accumulators not allocated yet"; return -1; }
+    *p = ctx->P.acc; *n = nk_acc_len(ctx->P.S, ctx->P.R);
+    return 0;
+}
+int nk_comm_export(nk_ctx* ctx, void*) { ctx->err = "fused peer exchange not built yet"; return -1; }
+int nk_comm_import(nk_ctx* ctx, int, const void*) { ctx->err = "fused peer exchange not built yet"; return -1; }
+int nk_comm_enable(nk_ctx* ctx, int) { ctx->err = "fused peer exchange not built yet"; return -1; }
+
+}  // extern "C"

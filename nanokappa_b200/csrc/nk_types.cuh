@@ -1,0 +1,129 @@
+// nk_types.cuh -- device-visible parameter blocks of the particle loop.
+//
+// NkP is passed BY VALUE to every kernel (constant bank, no pointer chasing); it only holds
+// pointers and scalars that never change between nk_set_* calls, so a captured CUDA graph of a
+// timestep stays valid.  Everything that changes from step to step lives in NkDyn (device memory).
+#pragma once
+#include <stdint.h>
+
+#define NK_TOL 1e-10            // Mesh.py:24
+#define NK_EMIT_CMAX 64         // copies of one mode a reservoir may emit per step (id packing)
+#define NK_EMIT_ID_BASE (1LL << 62)
+
+// one triangle, everything find_boundary needs (Mesh.py:806-856), 20 doubles = 160 B
+struct NkFace {
+    double nx, ny, nz, k;        // plane: x.n + k = 0
+    double lox, loy, loz;        // face AABB already widened by -tol / +tol (Mesh.py:828-829)
+    double hix, hiy, hiz;
+    double ox, oy, oz;           // vertex 0
+    double ia0, ia1, ia2;        // row 0 of [b1 b2 n]^-1  -> barycentric a
+    double ib0, ib1, ib2;        // row 1                  -> barycentric b
+    double facet;                // facet id stored as double to keep the record homogeneous
+};
+
+// per-mode record gathered once per particle per step: exactly one 32 B sector
+struct __align__(32) NkMode {
+    double omega, vx, vy, vz;
+};
+
+// four consecutive tau(T) slabs of a mode starting at NkP::tau_i0: one 32 B sector
+struct __align__(32) NkTau4 {
+    double t[4];
+};
+
+struct NkDyn {                   // device-resident, mutated by kernels
+    long long n_slots;           // slots [0, n_slots) are live or on the free list
+    long long n_free;            // free-list height (may dip below 0 inside nk_emit_kernel)
+    long long n_alive;
+    long long step;              // Population.current_timestep
+    unsigned int n_hits;         // particles whose collision falls inside this step
+    unsigned int n_hits_done;
+    int relax_pending;           // lifetime_scattering of step-1 still to be applied to `occ`
+    int error;                   // sticky device-side error bits
+    unsigned int blocks_done;    // last-block detection
+    unsigned int pad;
+};
+
+#define NK_ERR_CAPACITY 1        // emission ran out of slots
+#define NK_ERR_EVENTS   2        // a particle exceeded the per-step event cap
+#define NK_ERR_CMAX     4        // a mode emitted more than NK_EMIT_CMAX copies in one step
+
+struct NkP {
+    // ---- mesh
+    int F, nf;
+    const NkFace* faces;
+    const int* facet_bc; const int* facet_partner; const int* facet_res; const int* facet_rough;
+    const double* facet_normal; const double* facet_centroid; const double* facet_area;
+    // reservoir surface sampling (Mesh.sample_surface): per reservoir a CSR slice of faces + area cdf
+    const int* res_face_ptr; const int* res_faces; const double* res_face_cdf;
+    const double* face_vertices;      // (F,3,3)
+    double blo[3], bhi[3];
+    // ---- subvolumes
+    int S, is_slice, axis, interp;
+    const double* svc;                // (S,3)
+    const double* sv_axis;            // (S)   centres on the slice axis
+    const double* sv_mid;             // (S-1) x/2+x/2 midpoints (scipy interp1d 'nearest')
+    const double* sv_volume;
+    double sv_inv_dx;                 // 1 / slice spacing (guess only; exactness comes from fix-up)
+    // ---- modes
+    int Q, J, M, NT;
+    const double* Tg;                 // (NT)
+    const NkMode* mprop;              // (M)
+    const double* tau;                // (NT, M)
+    const NkTau4* tau4;               // (M) slabs tau_i0 .. tau_i0+3
+    int tau_i0;
+    double Tg_inv_d;                  // 1 / (Tg[1]-Tg[0]) guess
+    int nE; const double* Ea; const double* Ta;
+    double hbar, kb, V_uc, n_active, dens_norm;   // dens_norm = Q * V_uc
+    // ---- population
+    double dt, particle_density, eVpsa2_in_Wm2, a_in_m;
+    int norm_mean, n_dt_to_conv;
+    unsigned int seed_lo, seed_hi;
+    // ---- reservoirs
+    int R; const int* res_facet; const double* res_T; const double* enter_prob; double* res_counter;
+    int emit_m_lo, emit_m_hi;         // this rank's share of every reservoir's mode table
+    // ---- rough-wall LUTs (Fr, M)
+    int Fr; const double* specularity; const unsigned char* true_spec; const int* spec_out; const double* roulette;
+    // ---- particles (borrowed)
+    long long cap;
+    double *px, *py, *pz, *tc, *occ;
+    int *mode, *omode, *cfacet;
+    double *cx, *cy, *cz;
+    long long* pid;
+    // ---- scratch owned by the ctx
+    int* hitlist; int* freelist;
+    double* T_sv;                     // (S) current subvolume temperatures
+    double* acc;                      // per-step accumulators, see layout below
+    double* res_acc;                  // (R*4) E_bal + flux accumulated over the convergence window
+    double* out;                      // results block, see NK_OUT_* offsets
+    NkDyn* dyn;
+    int rank, world;
+};
+
+// accumulator layout (all double so that ONE f64 all-reduce covers it)
+//   [0,S) sum e   [S,2S) count   [2S,5S) sum v*e   then per reservoir: N_leaving, E_bal, flux(3)
+//   then 2 scalars: particles emitted, particles absorbed
+__host__ __device__ inline int nk_acc_len(int S, int R) { return 5 * S + 5 * R + 2; }
+#define NK_ACC_E(S, R)      0
+#define NK_ACC_CNT(S, R)    (S)
+#define NK_ACC_FLUX(S, R)   (2 * (S))
+#define NK_ACC_NLEAVE(S, R) (5 * (S))
+#define NK_ACC_EBAL(S, R)   (5 * (S) + (R))
+#define NK_ACC_RFLUX(S, R)  (5 * (S) + 2 * (R))
+#define NK_ACC_NEMIT(S, R)  (5 * (S) + 5 * (R))
+#define NK_ACC_NABS(S, R)   (5 * (S) + 5 * (R) + 1)
+
+// results block layout (doubles)
+//   T_sv(S) E_sv(S) N_sv(S) flux(3S) kappa_sv(S) kappa(1) res_E_bal(R) res_flux(3R) N_leaving(R) total_energy(1) N_p(1)
+__host__ __device__ inline int nk_out_len(int S, int R) { return 7 * S + 5 * R + 3; }
+#define NK_OUT_T(S, R)      0
+#define NK_OUT_E(S, R)      (S)
+#define NK_OUT_N(S, R)      (2 * (S))
+#define NK_OUT_FLUX(S, R)   (3 * (S))
+#define NK_OUT_KSV(S, R)    (6 * (S))
+#define NK_OUT_KAPPA(S, R)  (7 * (S))
+#define NK_OUT_REBAL(S, R)  (7 * (S) + 1)
+#define NK_OUT_RFLUX(S, R)  (7 * (S) + 1 + (R))
+#define NK_OUT_NLEAVE(S, R) (7 * (S) + 1 + 4 * (R))
+#define NK_OUT_ETOT(S, R)   (7 * (S) + 1 + 5 * (R))
+#define NK_OUT_NP(S, R)     (7 * (S) + 2 + 5 * (R))

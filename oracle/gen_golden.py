@@ -1,0 +1,157 @@
+"""TEST INFRASTRUCTURE -- regenerate ``tests/golden/*.npz`` by EXECUTING the unmodified reference.
+
+Run in the build container (needs ``/root/reference``):
+
+    python -m oracle.gen_golden
+
+Each fixture holds, for one small configuration:
+  tb_*   the static tables the reference computed (oracle/extract.py)
+  st0_*  the particle state right after ``Population.__init__``
+  ref{k}_* the reference's own arrays after k steps driven by NumPy's global generator seeded with
+         SEED_STEPS (``reference_step`` = run_timestep without the every-100-step output branch)
+The fixtures pin ``oracle/nk_oracle.py`` (sequence RNG, bit-exact) on machines without the
+reference, and give the GPU tests reference-built tables (specular LUTs, roulette, mesh planes).
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+from . import extract, nk_oracle as nko, ref_harness as rh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SEED_INIT = 7
+SEED_STEPS = 12345
+CHECK_STEPS = (1, 10, 20)
+
+PARAMS_C1 = """
+--mat_folder test_material/Si/ --hdf_file kappa-m313131.hdf5 --poscar_file POSCAR
+--geometry box --dimensions 5e3 1e3 1e3 --scale 1 1 1 --geo_rotation 0 0 0 xyz
+--subvolumes slice 10 0
+--bound_pos relative -0.1 0.5 0.5 1.1 0.5 0.5 0.5 0.5 -0.1 0.5 0.5 1.1
+--bound_cond T T R R P --connect_pos relative 0.5 -0.1 0.5 0.5 1.1 0.5
+--bound_values 302 298 {eta} {eta}
+--reference_temp local --temp_dist cold --temp_interp linear
+--particles total {n} --part_dist random_subvol --timestep 1 --iterations 1000
+--n_mean 10 --results_folder x --conv_crit 0 10 --colormap jet --output screen --max_sim_time 0-00:00:00
+"""
+
+# README cross-plane thin film (README.md:97-110) scaled down: T,T + periodic sides, nearest T
+PARAMS_C2 = """
+--mat_folder test_material/Si/ --hdf_file kappa-m313131.hdf5 --poscar_file POSCAR
+--geometry box --dimensions 20e3 20e3 20e3 --scale 1 1 1 --geo_rotation 0 0 0 xyz
+--subvolumes slice 20 0
+--bound_pos relative -0.1 0.5 0.5 1.1 0.5 0.5
+--bound_cond T T P
+--connect_pos relative 0.5 -0.1 0.5 0.5 1.1 0.5 0.5 0.5 -0.1 0.5 0.5 1.1
+--bound_values 302 298
+--reference_temp local --temp_dist cold --temp_interp nearest
+--particles total {n} --part_dist random_subvol --timestep 1 --iterations 1000
+--n_mean 10 --results_folder x --conv_crit 0 10 --colormap jet --output screen --max_sim_time 0-00:00:00
+"""
+
+CONFIGS = {
+    # name: (parameter text, table mesh n, lattice)
+    "c1_specular": (PARAMS_C1.format(eta=0, n=4000), 5),
+    "c1_diffuse": (PARAMS_C1.format(eta=10, n=4000), 5),
+    "c1_mixed": (PARAMS_C1.format(eta=0.5, n=4000), 5),
+    "c2_crossplane": (PARAMS_C2.format(n=6000), 5),
+}
+
+STATE_FIELDS = ("positions", "modes", "omega", "group_vel", "occupation", "n_timesteps", "collision_facets",
+                "collision_positions", "collision_cond", "temperatures", "ids", "subvol_temperature", "res_counter",
+                "subvol_id", "energies", "subvol_energy", "subvol_N_p", "subvol_heat_flux", "res_energy_balance",
+                "res_heat_flux", "omega_modes")
+REF_FIELDS = ("positions", "modes", "omega", "occupation", "n_timesteps", "collision_facets", "collision_positions",
+              "subvol_id", "subvol_energy", "subvol_temperature", "subvol_N_p", "res_counter", "N_leaving", "temperatures")
+
+
+def build_reference(text, n_mesh, results="/tmp/nk_golden_results"):
+    from nanokappa_b200 import synthetic
+    args = rh.parse_parameters_text(text, results, overrides=dict(fig_plot=[], output=["screen"]))
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+        geo = rh.make_geometry(args)
+        ph = rh.make_phonon(args, synthetic.make_table(n_mesh))
+        pop = rh.make_population(args, geo, ph, seed=SEED_INIT)
+    return args, geo, ph, pop
+
+
+def pack_tables(tb):
+    out = {}
+    for k, v in tb.items():
+        out["tb_" + k] = np.asarray(v)
+    return out
+
+
+def unpack(npz, prefix):
+    out = {}
+    for k in npz.files:
+        if k.startswith(prefix):
+            v = npz[k]
+            out[k[len(prefix):]] = v.item() if v.shape == () else v
+    return out
+
+
+def load_fixture(path):
+    """-> (tb, st0, refs{k: dict})  used by the tests."""
+    z = np.load(path, allow_pickle=False)
+    tb = unpack(z, "tb_")
+    for k in ("temp_interp",):
+        tb[k] = str(tb[k])
+    s0 = unpack(z, "st0_")
+    st = nko.State(**{k: s0[k] for k in ("positions", "modes", "omega", "group_vel", "occupation", "n_timesteps",
+                                         "collision_facets", "collision_positions", "collision_cond", "temperatures",
+                                         "ids", "subvol_temperature", "res_counter")})
+    for k in ("subvol_id", "energies", "subvol_energy", "subvol_N_p", "subvol_heat_flux", "res_energy_balance",
+              "res_heat_flux", "omega_modes"):
+        setattr(st, k, s0[k])
+    st.N_p = int(st.subvol_N_p.sum())
+    st.N_leaving = np.zeros(tb["res_facet"].shape[0], dtype=int)
+    st.current_timestep = 0
+    refs = {}
+    for k in z.files:
+        if k.startswith("ref") and "_" in k:
+            step, name = k[3:].split("_", 1)
+            refs.setdefault(int(step), {})[name] = z[k]
+    return tb, st, refs
+
+
+def generate(name, text, n_mesh):
+    args, geo, ph, pop = build_reference(text, n_mesh)
+    tb = extract.tables_from_reference(geo, ph, pop)
+    st0 = extract.state_from_reference(ph, pop)
+    data = pack_tables(tb)
+    for f in STATE_FIELDS:
+        data["st0_" + f] = np.array(getattr(st0, f), copy=True)
+    np.random.seed(SEED_STEPS)
+    with np.errstate(all="ignore"):
+        for k in range(1, max(CHECK_STEPS) + 1):
+            conv = extract.reference_step(pop, geo, ph)
+            if k in CHECK_STEPS:
+                for f in REF_FIELDS:
+                    data[f"ref{k}_{f}"] = np.array(getattr(pop, f), copy=True)
+                data[f"ref{k}_collision_cond"] = np.array([nko.BC_CODE[c] for c in pop.collision_cond], dtype=np.int8)
+            if conv is not None:
+                for f, v in conv.items():
+                    data[f"ref{k}_conv_{f}"] = np.array(v, copy=True)
+    os.makedirs(GOLDEN, exist_ok=True)
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, **data)
+    print(f"{name}: N0={st0.positions.shape[0]} N{max(CHECK_STEPS)}={pop.positions.shape[0]} -> {path} "
+          f"({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
+def main(argv=None):
+    names = (argv or sys.argv[1:]) or list(CONFIGS)
+    for name in names:
+        text, n_mesh = CONFIGS[name]
+        generate(name, text, n_mesh)
+
+
+if __name__ == "__main__":
+    main()

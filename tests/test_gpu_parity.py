@@ -1,0 +1,214 @@
+"""GPU parity: the CUDA path through the C ABI against the oracle restatement on identical inputs
+and identical keyed random draws.  Integer results (facet, subvolume, mode, particle census) must be
+bit-exact; floating-point per-particle state within 1e-9 and per-SV T / energy / flux / kappa within
+1e-6 relative (north_star tolerance; observed ~1e-13)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gen_golden, nk_oracle as nko
+
+pytestmark = pytest.mark.gpu
+
+FIXTURES = sorted(gen_golden.CONFIGS)
+SEED = 2024
+RTOL_PARTICLE = 1e-9
+RTOL_SV = 1e-6
+
+
+def _engine(tb, st, cap_factor=2.0, seed=SEED):
+    from nanokappa_b200.engine import Engine
+    J = tb["omega"].shape[1]
+    eng = Engine(0, seed=seed)
+    eng.set_tables(tb, res_counter=st.res_counter)
+    eng.allocate(int(st.positions.shape[0] * cap_factor) + 64)
+    eng.load_particles(st.positions, st.modes[:, 0] * J + st.modes[:, 1], st.occupation, ids=st.ids,
+                       omodes=st.omega_modes, n_timesteps=st.n_timesteps, collision_facets=st.collision_facets,
+                       collision_positions=st.collision_positions)
+    eng.set_sv_temperature(st.subvol_temperature)
+    eng.set_timestep(0)
+    return eng
+
+
+def _load(name, golden_dir):
+    return gen_golden.load_fixture(os.path.join(golden_dir, name + ".npz"))
+
+
+def _close(name, got, want, rtol, atol=0.0):
+    got = np.asarray(got, dtype=float); want = np.asarray(want, dtype=float)
+    assert got.shape == want.shape, f"{name}: shape {got.shape} vs {want.shape}"
+    both_nan = np.isnan(got) & np.isnan(want)
+    same_inf = np.isinf(want) & (got == want)
+    ok = both_nan | same_inf | (np.abs(got - want) <= atol + rtol * np.abs(want))
+    assert ok.all(), f"{name}: {np.count_nonzero(~ok)} of {ok.size} outside rtol {rtol}; worst {np.nanmax(np.abs(got - want)[~ok])}"
+
+
+@pytest.mark.parametrize("name", ["c1_mixed", "c2_crossplane"])
+def test_find_boundary_operator(name, golden_dir):
+    tb, st, _ = _load(name, golden_dir)
+    eng = _engine(tb, st)
+    r = np.random.default_rng(1)
+    lo, hi = tb["bounds"]
+    x = lo + r.random((20000, 3)) * (hi - lo)
+    v = r.standard_normal((20000, 3)) * 50
+    v[:200, 1] = 0.0; v[200:400, 2] = 0.0; v[400:500, 0] = 0.0          # axis-parallel rays
+    x = np.vstack([x, st.positions, st.collision_positions[np.isfinite(st.collision_positions).all(axis=1)][:1000]])
+    v = np.vstack([v, st.group_vel, st.group_vel[np.isfinite(st.collision_positions).all(axis=1)][:1000]])
+    with np.errstate(all="ignore"):
+        xc0, tc0, fc0 = nko.find_boundary(tb, x, v)
+    xc, tc, fc = eng.find_boundary(x, v)
+    assert np.array_equal(fc, fc0), f"{np.count_nonzero(fc != fc0)} facet mismatches"
+    _close("tc", tc, tc0, 1e-12)
+    _close("xc", xc, xc0, 1e-12, atol=1e-9)
+    assert (fc0 == -1).sum() < x.shape[0]
+
+
+def test_find_boundary_empty(golden_dir):
+    tb, st, _ = _load("c1_mixed", golden_dir)
+    eng = _engine(tb, st)
+    xc, tc, fc = eng.find_boundary(np.zeros((0, 3)), np.zeros((0, 3)))
+    assert xc.shape == (0, 3) and tc.shape == (0,) and fc.shape == (0,)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_init_collisions_matches_reference_init(name, golden_dir):
+    """nk_init_collisions against the arrays the reference produced in Population.__init__."""
+    tb, st, _ = _load(name, golden_dir)
+    eng = _engine(tb, st)
+    eng.init_collisions()
+    p = eng.particles(flush=False)
+    assert np.array_equal(p["collision_facets"], st.collision_facets)
+    _close("n_timesteps", p["n_timesteps"], st.n_timesteps, 1e-12)
+    _close("collision_positions", p["collision_positions"], st.collision_positions, 1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["c1_mixed", "c2_crossplane"])
+def test_table_operators(name, golden_dir):
+    tb, st, _ = _load(name, golden_dir)
+    eng = _engine(tb, st)
+    r = np.random.default_rng(2)
+    lo, hi = tb["bounds"]
+    x = lo - 0.05 * (hi - lo) + r.random((50000, 3)) * (hi - lo) * 1.1
+    sv, counts = eng.classify(x, counts=True)
+    sv0 = nko.classify(tb, x)
+    assert np.array_equal(sv, sv0)
+    assert np.array_equal(counts, np.bincount(sv0, minlength=tb["sv_centres"].shape[0]))
+    Q, J = tb["omega"].shape
+    T = 200 + 200 * r.random(20000)
+    q = r.integers(0, Q, 20000); j = r.integers(0, J, 20000)
+    om = tb["omega"][q, j]
+    _close("occupation", eng.calculate_occupation(T, om), nko.calculate_occupation(tb, T, om), 1e-13)
+    assert (eng.calculate_occupation(np.array([0.0, -1.0, 300.0]), np.array([1.0, 1.0, 0.0])) == 0).all()
+    _close("lifetime", eng.lifetime_function(np.stack([T, q, j], axis=1)),
+           nko.lifetime_function(tb, T, np.stack([q, j], axis=1)), 1e-14)
+    Tg = tb["T_grid"]
+    Tn = np.concatenate([Tg[:-1], Tg[1:]])            # exactly on the grid nodes
+    qn = r.integers(0, Q, Tn.shape[0]); jn = r.integers(0, J, Tn.shape[0])
+    _close("lifetime@nodes", eng.lifetime_function(np.stack([Tn, qn, jn], axis=1)),
+           nko.lifetime_function(tb, Tn, np.stack([qn, jn], axis=1)), 1e-14)
+    E = np.concatenate([tb["energy_array"][[0, 5, -1]], tb["energy_array"][0] + r.random(5000) * np.ptp(tb["energy_array"]),
+                        [tb["energy_array"][0] - 1.0, tb["energy_array"][-1] + 1.0]])
+    _close("T(E)", eng.temperature_function(E), nko.temperature_function(tb, E), 1e-14)
+    Tq = np.concatenate([[-3.0, 0.0, 1000.0, 1500.0], 1000 * r.random(5000)])
+    _close("E(T)", eng.crystal_energy_function(Tq), nko.crystal_energy_function(tb, Tq), 1e-14)
+    T_sv = 298 + 4 * r.random(tb["sv_centres"].shape[0])
+    eng.set_sv_temperature(T_sv)
+    _close("particle T", eng.particle_temperature(x), nko.particle_temperature(tb, T_sv, x), 1e-14)
+
+
+def _compare_step(k, eng, st, tb):
+    p = eng.particles()
+    order = np.argsort(st.ids)
+    assert np.array_equal(p["ids"], st.ids[order]), f"step {k}: particle census differs (gpu {p['ids'].shape[0]}, oracle {st.ids.shape[0]})"
+    assert np.array_equal(p["modes"], st.modes[order]), f"step {k}: mode indices differ"
+    assert np.array_equal(p["omega_modes"], st.omega_modes[order]), f"step {k}: omega-carrying modes differ"
+    assert np.array_equal(p["collision_facets"], st.collision_facets[order]), f"step {k}: collision facets differ"
+    _close(f"step {k} positions", p["positions"], st.positions[order], RTOL_PARTICLE, atol=1e-9)
+    _close(f"step {k} occupation", p["occupation"], st.occupation[order], RTOL_PARTICLE)
+    _close(f"step {k} n_timesteps", p["n_timesteps"], st.n_timesteps[order], RTOL_PARTICLE, atol=1e-9)
+    _close(f"step {k} collision_positions", p["collision_positions"], st.collision_positions[order], RTOL_PARTICLE, atol=1e-9)
+    res = eng.results()
+    assert np.array_equal(res["subvol_N_p"], st.subvol_N_p), f"step {k}: per-SV particle counts differ"
+    assert np.array_equal(res["N_leaving"], st.N_leaving), f"step {k}: absorbed counts differ"
+    _close(f"step {k} T_sv", res["subvol_temperature"], st.subvol_temperature, RTOL_SV)
+    _close(f"step {k} E_sv", res["subvol_energy"], st.subvol_energy, RTOL_SV)
+    _close(f"step {k} res_counter", eng.res_counter().reshape(st.res_counter.shape), st.res_counter, 1e-12, atol=1e-12)
+    return res
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_step_parity_fixed_draws(name, golden_dir):
+    tb, st, _ = _load(name, golden_dir)
+    eng = _engine(tb, st)
+    rng = nko.KeyedRNG(SEED)
+    conv = {}
+    n_steps = 30
+    with np.errstate(all="ignore"):
+        for k in range(1, n_steps + 1):
+            nko.run_timestep(tb, st, rng, on_convergence=lambda s: conv.update(
+                subvol_heat_flux=s.subvol_heat_flux.copy(), res_heat_flux=s.res_heat_flux.copy(),
+                res_energy_balance=s.res_energy_balance.copy(), subvol_kappa=s.subvol_kappa.copy(), kappa=s.kappa))
+            eng.step(1)
+            if k in (1, 2, 5, 10, 20, 30):
+                res = _compare_step(k, eng, st, tb)
+                if k % tb["n_dt_to_conv"] == 0:
+                    scale = np.abs(conv["subvol_heat_flux"]).max()
+                    _close(f"step {k} heat flux", res["subvol_heat_flux"], conv["subvol_heat_flux"], RTOL_SV, atol=RTOL_SV * scale)
+                    # kappa_s = -phi dx / (T[s+1] - T[s-1]) is ill-conditioned where the profile is still flat:
+                    # allow the error a 2e-9 K disagreement in T (7e-12 relative) produces, on top of RTOL_SV
+                    Tpad = np.concatenate(([tb["res_T"][0]], st.subvol_temperature, [tb["res_T"][-1]]))
+                    dT = np.abs(Tpad[2:] - Tpad[:-2])
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        cond = np.where(dT > 0, 2e-9 / dT, np.inf)
+                    kref = conv["subvol_kappa"]
+                    bad = np.abs(res["subvol_kappa"] - kref) > RTOL_SV * np.abs(kref) + cond * np.abs(kref) + 1e-300
+                    assert not bad.any(), f"step {k} kappa_sv: {res['subvol_kappa'][bad]} vs {kref[bad]} (dT {dT[bad]})"
+                    _close(f"step {k} kappa", res["kappa"], conv["kappa"], RTOL_SV)
+                    _close(f"step {k} res flux", res["res_heat_flux"], conv["res_heat_flux"], RTOL_SV, atol=RTOL_SV * np.abs(conv["res_heat_flux"]).max())
+                    _close(f"step {k} res balance", res["res_energy_balance"], conv["res_energy_balance"], RTOL_SV, atol=RTOL_SV * np.abs(conv["res_energy_balance"]).max())
+    assert eng.timestep() == n_steps
+
+
+def test_multi_step_call_equals_single_steps(golden_dir):
+    """nk_step(n) in one call == n calls, and flushing the deferred relaxation in between is neutral."""
+    tb, st, _ = _load("c1_mixed", golden_dir)
+    a = _engine(tb, st.copy()); b = _engine(tb, st.copy())
+    a.step(12)
+    for _ in range(12):
+        b.step(1); b.flush_relaxation()
+    pa, pb = a.particles(), b.particles()
+    for f in pa:
+        assert np.array_equal(pa[f], pb[f], equal_nan=True), f
+    ra, rb = a.results(), b.results()
+    assert np.array_equal(ra["subvol_N_p"], rb["subvol_N_p"])
+    _close("T", ra["subvol_temperature"], rb["subvol_temperature"], 1e-13)
+
+
+def test_slot_recycling_and_census(golden_dir):
+    """Absorbed particles free their slot, emitted ones reuse it: slots stay bounded, live count = N_p."""
+    tb, st, _ = _load("c2_crossplane", golden_dir)
+    eng = _engine(tb, st, cap_factor=1.2)
+    n0 = st.positions.shape[0]
+    eng.step(60)
+    slots, alive = eng.slot_count()
+    res = eng.results()
+    assert alive == res["N_p"]
+    assert slots <= n0 * 1.1 + 64
+    p = eng.particles()
+    assert p["ids"].shape[0] == alive and np.unique(p["ids"]).shape[0] == alive
+
+
+def test_capacity_overflow_is_reported(golden_dir):
+    tb, st, _ = _load("c2_crossplane", golden_dir)
+    from nanokappa_b200._lib import NkError
+    eng = _engine(tb, st, cap_factor=1.0)
+    eng.allocate(st.positions.shape[0])
+    J = tb["omega"].shape[1]
+    eng.load_particles(st.positions, st.modes[:, 0] * J + st.modes[:, 1], st.occupation, ids=st.ids,
+                       n_timesteps=np.full(st.positions.shape[0], 1e9), collision_facets=st.collision_facets,
+                       collision_positions=st.collision_positions)        # nobody ever leaves, emission must overflow
+    eng.set_sv_temperature(st.subvol_temperature)
+    eng.step(5)
+    with pytest.raises(NkError):
+        eng.slot_count()

@@ -1,0 +1,116 @@
+"""Pin the oracle restatement (oracle/nk_oracle.py) against the reference itself.
+
+* fixtures: tests/golden/*.npz were produced by executing the unmodified reference
+  (oracle/gen_golden.py); the restatement, fed the same NumPy stream, must reproduce every particle
+  array and per-SV vector BIT FOR BIT after 1, 10 and 20 steps.
+* live: where /root/reference exists the same comparison runs against the live reference on a
+  configuration that is not in the fixtures.
+"""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gen_golden, nk_oracle as nko, ref_harness
+
+FIXTURES = sorted(gen_golden.CONFIGS)
+
+
+def _eq(name, a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    assert a.shape == b.shape, f"{name}: shape {a.shape} vs {b.shape}"
+    assert np.array_equal(a, b, equal_nan=True), f"{name}: max abs diff {np.nanmax(np.abs(a.astype(float) - b.astype(float)))}"
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_restatement_matches_reference_fixture(name, golden_dir):
+    tb, st, refs = gen_golden.load_fixture(os.path.join(golden_dir, name + ".npz"))
+    rng = nko.SequenceRNG()
+    np.random.seed(gen_golden.SEED_STEPS)
+    conv = {}
+    with np.errstate(all="ignore"):
+        for k in range(1, max(refs) + 1):
+            nko.run_timestep(tb, st, rng, on_convergence=lambda s: conv.update(
+                subvol_heat_flux=s.subvol_heat_flux.copy(), res_heat_flux=s.res_heat_flux.copy(),
+                res_energy_balance=s.res_energy_balance.copy(), subvol_kappa=s.subvol_kappa.copy(), kappa=s.kappa))
+            if k in refs:
+                ref = refs[k]
+                for f in gen_golden.REF_FIELDS + ("collision_cond",):
+                    _eq(f"step {k} {f}", ref[f], getattr(st, f))
+                for f in ("subvol_heat_flux", "res_heat_flux", "res_energy_balance", "subvol_kappa", "kappa"):
+                    if "conv_" + f in ref:
+                        _eq(f"step {k} conv {f}", ref["conv_" + f], conv[f])
+
+
+def test_fixture_covers_every_branch(golden_dir):
+    """The fixtures must actually exercise absorption, emission, periodic wrap, specular and diffuse."""
+    tb, st, refs = gen_golden.load_fixture(os.path.join(golden_dir, "c1_mixed.npz"))
+    last = refs[max(refs)]
+    assert last["positions"].shape[0] != st.positions.shape[0] or last["N_leaving"].sum() > 0
+    J = tb["omega"].shape[1]
+    om_of_mode = tb["omega"][last["modes"][:, 0], last["modes"][:, 1]]
+    assert (om_of_mode != last["omega"]).any(), "no specular reflection kept its old omega"
+    assert set(np.unique(tb["facet_bc"])) == {nko.BC_T, nko.BC_P, nko.BC_R}
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference not present on this box")
+def test_restatement_matches_live_reference():
+    from oracle import extract
+    text = gen_golden.PARAMS_C1.format(eta=2, n=2500).replace("slice 10 0", "slice 7 0")
+    with contextlib.redirect_stdout(io.StringIO()):
+        args, geo, ph, pop = gen_golden.build_reference(text, 5, results="/tmp/nk_pin_live")
+    tb = extract.tables_from_reference(geo, ph, pop)
+    st = extract.state_from_reference(ph, pop)
+    rng = nko.SequenceRNG()
+    np.random.seed(99)
+    with np.errstate(all="ignore"):
+        for k in range(12):
+            state = np.random.get_state()
+            extract.reference_step(pop, geo, ph)
+            after = np.random.get_state()
+            np.random.set_state(state)
+            nko.run_timestep(tb, st, rng)
+            assert np.array_equal(after[1], np.random.get_state()[1]), "random streams diverged"
+            for f in gen_golden.REF_FIELDS:
+                _eq(f"step {k} {f}", getattr(pop, f), getattr(st, f))
+
+
+@pytest.mark.parametrize("name", ["c1_mixed", "c2_crossplane"])
+def test_restated_thirdparty_formulas(name, golden_dir):
+    """interp1d / RegularGridInterpolator / cKDTree restatements against SciPy itself."""
+    from scipy.interpolate import RegularGridInterpolator, interp1d
+    from scipy.spatial import cKDTree
+    tb, st, _ = gen_golden.load_fixture(os.path.join(golden_dir, name + ".npz"))
+    r = np.random.default_rng(0)
+    lo, hi = tb["bounds"]
+    x = r.random((5000, 3)) * (hi - lo) * 1.2 + lo - 0.1 * (hi - lo)
+    assert np.array_equal(nko.classify(tb, x), cKDTree(tb["sv_centres"]).query(x)[1])
+    T_sv = 298 + 4 * r.random(tb["sv_centres"].shape[0])
+    ax = int(tb["slice_axis"])
+    f = interp1d(tb["sv_centres"][:, ax], T_sv, kind=tb["temp_interp"], fill_value="extrapolate")
+    assert np.array_equal(nko.particle_temperature(tb, T_sv, x), f(x[:, ax]))
+    Q, J = tb["omega"].shape
+    T = 250 + 100 * r.random(4000)
+    modes = np.stack([r.integers(0, Q, 4000), r.integers(0, J, 4000)], axis=1)
+    rgi = RegularGridInterpolator((tb["T_grid"], np.arange(Q), np.arange(J)), tb["tau"])
+    assert np.array_equal(nko.lifetime_function(tb, T, modes), rgi(np.hstack((T.reshape(-1, 1), modes))))
+    E = np.concatenate([tb["energy_array"][[0, -1]], tb["energy_array"][0] + r.random(3000) * np.ptp(tb["energy_array"]),
+                        [tb["energy_array"][0] - 1, tb["energy_array"][-1] + 1]])
+    tf = interp1d(tb["energy_array"], tb["T_array"], kind="linear", fill_value=(tb["T_array"].min(), tb["T_array"].max()), bounds_error=False)
+    assert np.array_equal(nko.temperature_function(tb, E), tf(E))
+    ef = interp1d(tb["T_array"], tb["energy_array"], kind="linear", fill_value=(tb["energy_array"].min(), tb["energy_array"].max()), bounds_error=False)
+    Tq = np.concatenate([[-5.0, 0.0, 1000.0, 1200.0], 1000 * r.random(2000)])
+    assert np.array_equal(nko.crystal_energy_function(tb, Tq), ef(Tq))
+
+
+def test_philox_known_answers():
+    """Random123 Philox4x32-10 known-answer vectors."""
+    from oracle.philox import philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for c, k, want in kat:
+        got = tuple(int(v) for v in philox4x32_10(*c, *k))
+        assert got == want
