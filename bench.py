@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- particle-timestep updates/s of the Nano-kappa particle loop on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+    python bench.py --impl reference --steps K --warmup W     CPU arm: the oracle port on host cores
+
+Workload (BASELINE.json configs[1] geometry at configs[4] scale): Si cross-plane thin film, box
+(2e4 A)^3, reservoirs 302 K / 298 K on the x faces, periodic y/z walls, 20 slice subvolumes on x,
+nearest-subvolume particle temperature, dt = 1 ps, synthetic 31^3 x 6 mode table (the phono3py hdf5
+is not shipped), `--particles` per GPU (default 1e8: 8.4 GB of hot particle state, far beyond the
+126 MB L2, so every step streams from HBM).  One "step" = one Population.run_timestep.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import ctypes as C
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_UPDATE = 84.0   # x,y,z r/w 48 + tc r/w 16 + occupation r/w 16 + mode id read 4
+
+PARAMS = """
+--mat_folder {mat} --hdf_file synthetic:{mesh} --poscar_file POSCAR
+--geometry box --dimensions 20e3 20e3 20e3 --scale 1 1 1 --geo_rotation 0 0 0 xyz
+--subvolumes slice 20 0
+--bound_pos relative -0.1 0.5 0.5 1.1 0.5 0.5
+--bound_cond T T P
+--connect_pos relative 0.5 -0.1 0.5 0.5 1.1 0.5 0.5 0.5 -0.1 0.5 0.5 1.1
+--bound_values 302 298
+--reference_temp local --temp_dist cold --temp_interp nearest
+--particles total {n} --part_dist random_subvol --timestep 1 --iterations 10000
+--n_mean 10 --results_folder bench --conv_crit 0 10 --output screen --max_sim_time 0-00:00:00
+"""
+
+
+def workload(n_total, mesh):
+    """Geometry / Phonon / host set-up tables of the benchmark case (no GPU needed)."""
+    import argument_parser as ap
+    from nanokappa_b200.classes.Geometry import Geometry
+    from nanokappa_b200.classes.Phonon import Phonon
+    from nanokappa_b200.classes.Population import PopulationSetup
+    text = PARAMS.format(mat="/nonexistent_material_folder/", mesh=mesh, n=int(n_total))
+    args = ap.initialise_parser(False).parse_args(text.split())
+    args.results_folder = "/tmp"
+    with contextlib.redirect_stdout(io.StringIO()):
+        geo = Geometry(args)
+        ph = Phonon(args, 0)
+        np.random.seed(0)
+        setup = PopulationSetup(args, geo, ph, seed=0)
+    return args, geo, ph, setup, setup.tables(geo, ph)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); smax.append(float(p[1])); power.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (NumPy restatement + the SciPy objects the reference itself calls)
+# --------------------------------------------------------------------------------------------------
+def cpu_run(n_particles, steps, warmup, mesh):
+    from oracle import nk_oracle as nko
+    args, geo, ph, setup, tb = workload(n_particles, mesh)
+    rs = np.random.RandomState(1)
+    lo, hi = tb["bounds"]
+    pos = lo + rs.random_sample((n_particles, 3)) * (hi - lo)
+    act = np.vstack(np.where(~ph.inactive_modes_mask)).T
+    modes = act[np.arange(n_particles) % act.shape[0]]
+    T0 = np.full(tb["sv_centres"].shape[0], float(np.min(tb["res_T"])))
+    st = nko.make_state(tb, pos, modes, T0, setup.res_counter)
+    backend = nko.SciPyBackend(tb, collect_garbage=True)
+    rng = nko.SequenceRNG()
+    np.random.seed(2)
+    with np.errstate(all="ignore"):
+        for _ in range(warmup):
+            nko.run_timestep(tb, st, rng, backend=backend)
+        updates = 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            nko.run_timestep(tb, st, rng, backend=backend)
+            updates += st.N_p
+        dt = time.perf_counter() - t0
+    return updates / dt, dt, updates
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n = int(a.cpu_particles)
+    value, dt, updates = cpu_run(n, a.steps, a.warmup, a.mesh)
+    line = {
+        "impl": "reference", "metric": "particle-timestep updates/s", "value": value, "unit": "updates/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(a, n, "cpu"),
+        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": 1, "kind": "port",
+                         "sample": f"{n} particles x {a.steps} timesteps of the same thin-film case (oracle/nk_oracle.py + SciPy cKDTree / "
+                                   f"RegularGridInterpolator + gc.collect as the reference calls them; the reference is single-threaded; "
+                                   f"host has {os.cpu_count()} cores)"},
+        "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(a, n_per_gpu, where):
+    return {"workload": "si_thin_film_crossplane: box (2e4 A)^3, T 302/298 K on x faces, periodic sides, 20 slice SVs, nearest T, dt 1 ps "
+                        "(BASELINE configs[1] geometry at configs[4] scale)",
+            "particles_per_gpu": int(n_per_gpu), "mode_table": f"synthetic {a.mesh}^3 x 6", "subvolumes": 20,
+            "l2_policy": "inputs larger than L2 (no flush)" if n_per_gpu * 44 > 2.6e8 else "state fits L2; L2 flushed between timed steps",
+            "parallelism": f"particle shards x{a.gpus}, per-step all-reduce of the per-SV vectors" if a.gpus > 1 else "single GPU"}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def gpu_arm(a):
+    import torch
+    import torch.distributed as dist
+    from nanokappa_b200.engine import Engine, _dp
+    from nanokappa_b200._lib import check
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n = int(a.particles)
+    n_total = n * world
+    args, geo, ph, setup, tb = workload(n_total, a.mesh)
+    S = tb["sv_centres"].shape[0]
+    eng = Engine(local, seed=1234)
+    eng.set_tables(tb, res_counter=setup.res_counter)
+    eng.allocate(int(n * 1.05) + 4096)
+    if world > 1:
+        check(eng.ctx, eng.L.nk_set_rank(eng.ctx, rank, world), "nk_set_rank")
+
+    # ---- synthetic ensemble, created on the device (uniform in the box, modes tiled over the active
+    #      modes as Population.initialise_modes does for >= 1 particle per mode and subvolume, T = 298 K)
+    g = torch.Generator(device=dev); g.manual_seed(100 + rank)
+    lo = torch.as_tensor(tb["bounds"][0], device=dev); ext = torch.as_tensor(tb["bounds"][1] - tb["bounds"][0], device=dev)
+    t = eng.t
+    for k, name in enumerate(("px", "py", "pz")):
+        t[name][:n] = lo[k] + torch.rand(n, generator=g, dtype=torch.float64, device=dev) * ext[k]
+    act = torch.as_tensor(np.nonzero(~ph.inactive_modes_mask.reshape(-1))[0].astype(np.int32), device=dev)
+    idx = (torch.arange(n, device=dev, dtype=torch.int64) + rank * n) % act.numel()
+    t["mode"][:n] = act[idx]; t["omode"][:n] = act[idx]; t["mode"][n:] = -1
+    t["pid"][:n] = torch.arange(n, device=dev, dtype=torch.int64) + rank * n
+    omega_d = torch.as_tensor(tb["omega"].reshape(-1), device=dev)[t["mode"][:n].long()]
+    T0 = float(np.min(tb["res_T"]))
+    Td = torch.full((n,), T0, dtype=torch.float64, device=dev)
+    check(eng.ctx, eng.L.nk_occupation(eng.ctx, n, _dp(Td), _dp(omega_d), _dp(t["occ"])), "nk_occupation")
+    del omega_d, Td, idx
+    torch.cuda.synchronize()
+    check(eng.ctx, eng.L.nk_set_slot_count(eng.ctx, n), "nk_set_slot_count")
+    eng.set_sv_temperature(np.full(S, T0))
+    eng.set_timestep(0)
+    eng.init_collisions()
+    eng.synchronize()
+
+    acc_t = None
+    if world > 1:
+        ptr = C.c_void_p(); ln = C.c_int64()
+        check(eng.ctx, eng.L.nk_acc_buffer(eng.ctx, C.byref(ptr), C.byref(ln)), "nk_acc_buffer")
+
+        class _Acc:
+            __cuda_array_interface__ = {"shape": (ln.value,), "typestr": "<f8", "data": (ptr.value, False), "version": 3}
+        acc_t = torch.as_tensor(_Acc(), device=dev)
+
+    flush_buf = None
+    if n * 44 <= 2.6e8:
+        flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def one_step():
+        if flush_buf is not None:
+            flush_buf.zero_()
+        if world > 1:
+            eng.step_local()
+            dist.all_reduce(acc_t)
+            eng.step_finalize()
+        else:
+            eng.step(1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        one_step()
+    barrier()
+    n_alive0 = eng.results()["N_p"]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    eng.profile_begin()
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        one_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof, nprof = eng.profile_end()
+    clocks = sampler.stop() if rank == 0 else None
+    n_alive1 = eng.results()["N_p"]
+    slots, alive_local = eng.slot_count()
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    updates = 0.5 * (n_alive0 + n_alive1) * a.steps          # N_p is the global live count (all ranks)
+    value = updates / (ms * 1e-3)
+
+    # ---- roofline of the streaming kernel: algorithmic bytes = 84 B x live particles of this rank per launch
+    peak, peak_src = load_peaks()
+    step_ms = prof["k_step"] / max(nprof, 1)
+    achieved = BYTES_PER_UPDATE * alive_local / (step_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "bytes_per_update": BYTES_PER_UPDATE, "updates_per_launch": int(alive_local),
+                "avg_launch_ms": step_ms,
+                "kernel_share_of_step": {k: v / max(sum(prof.values()), 1e-12) for k, v in prof.items()}}
+
+    # ---- end to end through host buffers (pinned): full particle state H2D, one timestep, state + per-SV results D2H
+    e2e = e2e_run(a, eng, n, world, rank, one_step, dev)
+
+    if world > 1:
+        e2e_t = torch.tensor([e2e["seconds"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e["seconds"] = float(e2e_t.item())
+    e2e_value = e2e["updates_global"] / e2e["seconds"]
+
+    if rank == 0:
+        cpu_val, cpu_dt, cpu_upd = (None, None, None)
+        cpu = None
+        if world == 1 and not a.no_cpu:
+            cpu_val, cpu_dt, cpu_upd = cpu_run(int(a.cpu_particles), a.cpu_steps, 1, a.mesh)
+            cpu = {"value": cpu_val, "unit": "updates/s", "cores": 1, "kind": "port",
+                   "sample": f"{int(a.cpu_particles)} particles x {a.cpu_steps} timesteps of the same case, {cpu_dt:.1f} s "
+                             f"(oracle port with the SciPy calls + gc.collect the reference makes; single-threaded like the reference; "
+                             f"host has {os.cpu_count()} cores)"}
+        line = {
+            "metric": "particle-timestep updates/s", "value": value, "unit": "updates/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(a, n, "gpu"),
+            "clocks": clocks, "gpu_launches": int(4 * a.steps),
+            "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                    "timesteps_per_call": 1, "calls": e2e["calls"], "api": e2e["api"]},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "particles_alive": int(n_alive1),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def e2e_run(a, eng, n, world, rank, one_step, dev):
+    """One public-API call per step with HOST particle arrays: upload the state, advance one timestep,
+    download the state and the per-subvolume results.  N=1 goes through the C-ABI host-buffer entry
+    point nk_advance_host; N>1 composes the same copies around step_local / all-reduce / finalize."""
+    import torch
+    from nanokappa_b200.engine import _dp
+    from nanokappa_b200._lib import check
+    t = eng.t
+    slots, _ = eng.slot_count()
+    names8 = ("px", "py", "pz", "tc", "occ", "cx", "cy", "cz", "pid")
+    names4 = ("mode", "omode", "cfacet")
+    cap = eng.cap
+    host = {k: torch.empty(cap, dtype=t[k].dtype, pin_memory=True) for k in names8 + names4}
+    eng.flush_relaxation()
+    for k in host:
+        host[k][:slots].copy_(t[k][:slots])
+    torch.cuda.synchronize()
+    calls = max(1, min(a.steps, a.e2e_calls))
+    S = eng.S
+    Tsv = np.zeros(S); Esv = np.zeros(S); Nsv = np.zeros(S, dtype=np.int64)
+    per = 9 * 8 + 3 * 4
+    updates = 0
+    t0 = time.perf_counter()
+    n_cur = slots
+    for _ in range(calls):
+        if world == 1:
+            n_out = C.c_int64()
+            hp = lambda k: C.c_void_p(host[k].data_ptr())
+            check(eng.ctx, eng.L.nk_advance_host(eng.ctx, n_cur, 1, hp("px"), hp("py"), hp("pz"), hp("tc"), hp("occ"), hp("mode"),
+                                                 hp("omode"), hp("cfacet"), hp("cx"), hp("cy"), hp("cz"), hp("pid"), C.byref(n_out),
+                                                 Tsv.ctypes.data_as(C.c_void_p), Esv.ctypes.data_as(C.c_void_p),
+                                                 Nsv.ctypes.data_as(C.c_void_p)), "nk_advance_host")
+            n_cur = n_out.value
+            updates += int(Nsv.sum())
+        else:
+            for k in host:
+                t[k][:n_cur].copy_(host[k][:n_cur], non_blocking=True)
+            one_step()
+            eng.flush_relaxation()
+            n_cur, _ = eng.slot_count()
+            for k in host:
+                host[k][:n_cur].copy_(t[k][:n_cur], non_blocking=True)
+            res = eng.results()
+            updates += res["N_p"]
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    if world == 1:
+        updates_global = updates
+    else:
+        updates_global = updates      # results() already reports the global N_p
+    return {"seconds": sec, "updates_global": updates_global, "h2d": int(per * n_cur), "d2h": int(per * n_cur + 8 * 3 * S),
+            "calls": calls, "api": "nk_advance_host (C ABI, pinned host SoA)" if world == 1 else "Engine host-buffer step (torch pinned copies + step_local/all_reduce/finalize)"}
+
+
+def main():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", 1)))
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--particles", type=float, default=1e8, help="particles per GPU")
+    p.add_argument("--mesh", type=int, default=31, help="q-mesh of the synthetic mode table (31 -> 29791 x 6 modes)")
+    p.add_argument("--cpu-particles", type=float, default=2e5)
+    p.add_argument("--cpu-steps", type=int, default=20)
+    p.add_argument("--e2e-calls", type=int, default=3)
+    p.add_argument("--no-cpu", action="store_true")
+    a = p.parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -149,6 +149,13 @@ int nk_init_collisions(nk_ctx* ctx);
  * calculate_heat_flux / calculate_kappa / adjust_reservoir_balance.  Enqueued; no host sync. */
 int nk_step(nk_ctx* ctx, int n_steps);
 
+/* Per-kernel device timing of the timestep (CUDA events recorded on the ctx stream around every
+ * launch of nk_step / nk_step_local / nk_step_finalize between begin and end; used by bench.py for
+ * the roofline of the streaming kernel).  ms[4] = total milliseconds in k_step, k_emit, k_boundary,
+ * k_finalize; n_steps = timesteps covered.  nk_profile_end synchronises the stream. */
+int nk_profile_begin(nk_ctx* ctx);
+int nk_profile_end(nk_ctx* ctx, double* ms, int64_t* n_steps);
+
 /* Make `occ` hold the post-lifetime_scattering occupation (the step kernel defers the relaxation of
  * step k to the head of step k+1; outputs that read occupation call this first). */
 int nk_flush_relaxation(nk_ctx* ctx);

@@ -54,6 +54,8 @@ SIGNATURES = {
     "nk_init_collisions": (C.c_int, [VP]),
     "nk_step": (C.c_int, [VP, C.c_int]),
     "nk_flush_relaxation": (C.c_int, [VP]),
+    "nk_profile_begin": (C.c_int, [VP]),
+    "nk_profile_end": (C.c_int, [VP, VP, c_lp]),
     "nk_get_results": (C.c_int, [VP] + [VP] * 10),
     "nk_advance_host": (C.c_int, [VP, C.c_int64, C.c_int] + [VP] * 12 + [c_lp, VP, VP, VP]),
     "nk_set_rank": (C.c_int, [VP, C.c_int, C.c_int]),

@@ -255,12 +255,27 @@ class Mesh:
     def contains(self, x):
         """Point-in-solid by crossing parity along +x (with a generic direction to dodge edges)."""
         x = np.asarray(x, dtype=float).reshape(-1, 3)
-        d = np.array([0.8017837257372732, 0.5345224838248488, 0.2672612419124244])
+        d = np.array([0.8017837257372732, 0.5345224838248488, 0.2672612419124244])   # generic: misses edges
         out = np.zeros(x.shape[0], dtype=bool)
-        inb = np.all(x >= self.bounds[0] - self.tol, axis=1) & np.all(x <= self.bounds[1] + self.tol, axis=1)
-        for i in np.nonzero(inb)[0]:
-            _, t, _, pts = self._ray_all(x[i], d)
-            out[i] = (np.unique(np.around(pts, 8), axis=0).shape[0] % 2) == 1
+        inb = np.nonzero(np.all(x >= self.bounds[0] - self.tol, axis=1) & np.all(x <= self.bounds[1] + self.tol, axis=1))[0]
+        keep = np.ones(self.n_of_faces, dtype=bool)
+        if len(self.interfaces):
+            keep[self.interfaces] = False
+        n, k = self.face_normals[keep], self.face_k[keep]
+        inv = np.linalg.inv(self.face_basis_matrix[keep])                      # (F,3,3)
+        org = self.face_origins[keep]
+        den = n @ d
+        chunk = max(1, int(2e6 // max(1, n.shape[0])))
+        for s in range(0, inb.shape[0], chunk):
+            idx = inb[s:s + chunk]
+            p = x[idx]
+            with np.errstate(divide='ignore', invalid='ignore'):
+                t = -(p @ n.T + k) / den                                          # (P,F)
+            c = p[:, None, :] + t[..., None] * d - org[None]
+            bar = np.einsum('fij,pfj->pfi', inv, c)
+            a, b = bar[..., 0], bar[..., 1]
+            hit = np.isfinite(t) & (t > self.tol) & (a >= 0) & (b >= 0) & (a + b <= 1)
+            out[idx] = (hit.sum(axis=1) % 2) == 1
         return out
 
     contains_naive = contains

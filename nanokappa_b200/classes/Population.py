@@ -64,11 +64,15 @@ def build_tables(args, geometry, phonon, pop):
     return tb
 
 
-class Population(Constants):
-    '''Class comprising the particles to be simulated.'''
+class PopulationSetup(Constants):
+    '''Host-only part of the set-up: particle count, reservoir tables, rough-wall LUTs.  Needs no GPU;
+    bench.py's reference arm and the CPU tests use it to build the run tables for the oracle.'''
 
-    def __init__(self, arguments, geometry, phonon, device=None, seed=None, engine=None):
+    def __init__(self, arguments, geometry, phonon, seed=None):
         super().__init__()
+        self.setup_host(arguments, geometry, phonon, seed)
+
+    def setup_host(self, arguments, geometry, phonon, seed=None):
         self.args = arguments
         self.results_folder_name = self.args.results_folder
         self.n_dt_to_conv = 10
@@ -138,6 +142,41 @@ class Population(Constants):
             self.res_facet_temperature = np.zeros(0)
             self.res_counter = np.zeros((0,) + phonon.omega.shape)
 
+    def initialise_reservoirs(self, geometry, phonon):
+        """Reservoir temperatures and per-mode entry probabilities (Population.py:146-161, :323-354)."""
+        self.res_facet = geometry.res_facets
+        self.res_bound_values = geometry.res_values
+        self.res_bound_cond = geometry.res_bound_cond
+        mask_T = geometry.res_bound_cond == 'T'
+        mask_F = geometry.res_bound_cond == 'F'
+        self.res_facet_temperature = np.full(self.n_of_reservoirs, np.nan)
+        self.res_facet_temperature[mask_T] = geometry.res_values[mask_T]
+        if mask_F.any():
+            self.res_facet_temperature[mask_F] = geometry.res_values[mask_T].mean()
+        self.enter_prob = self.enter_probability(geometry, phonon)
+        self.res_counter = np.random.rand(*self.enter_prob.shape)
+        self.N_leaving = np.sum(self.enter_prob, axis=(1, 2)).round().astype(int)
+        self.res_energy_balance = np.zeros(self.n_of_reservoirs)
+        self.res_heat_flux = np.zeros((self.n_of_reservoirs, 3))
+
+    def enter_probability(self, geometry, phonon):
+        thickness = phonon.number_of_active_modes / (self.particle_density * geometry.facets_area[self.res_facet])
+        vel = np.transpose(phonon.group_vel, (0, 2, 1))
+        normals = -geometry.facets_normal[self.res_facet, :]
+        p = np.dot(normals, vel) * self.dt / thickness.reshape(-1, 1, 1)
+        return np.where(p < 0, 0, p)
+
+    def tables(self, geometry, phonon):
+        return build_tables(self.args, geometry, phonon, self)
+
+
+class Population(PopulationSetup):
+    '''Class comprising the particles to be simulated.'''
+
+    def __init__(self, arguments, geometry, phonon, device=None, seed=None, engine=None):
+        Constants.__init__(self)
+        self.setup_host(arguments, geometry, phonon, seed)
+
         # ---- device context
         if engine is None:
             if device is None:
@@ -165,30 +204,6 @@ class Population(Constants):
         print('Initialisation done!')
 
     # ---- set-up ------------------------------------------------------------------------------------
-    def initialise_reservoirs(self, geometry, phonon):
-        """Reservoir temperatures and per-mode entry probabilities (Population.py:146-161, :323-354)."""
-        self.res_facet = geometry.res_facets
-        self.res_bound_values = geometry.res_values
-        self.res_bound_cond = geometry.res_bound_cond
-        mask_T = geometry.res_bound_cond == 'T'
-        mask_F = geometry.res_bound_cond == 'F'
-        self.res_facet_temperature = np.full(self.n_of_reservoirs, np.nan)
-        self.res_facet_temperature[mask_T] = geometry.res_values[mask_T]
-        if mask_F.any():
-            self.res_facet_temperature[mask_F] = geometry.res_values[mask_T].mean()
-        self.enter_prob = self.enter_probability(geometry, phonon)
-        self.res_counter = np.random.rand(*self.enter_prob.shape)
-        self.N_leaving = np.sum(self.enter_prob, axis=(1, 2)).round().astype(int)
-        self.res_energy_balance = np.zeros(self.n_of_reservoirs)
-        self.res_heat_flux = np.zeros((self.n_of_reservoirs, 3))
-
-    def enter_probability(self, geometry, phonon):
-        thickness = phonon.number_of_active_modes / (self.particle_density * geometry.facets_area[self.res_facet])
-        vel = np.transpose(phonon.group_vel, (0, 2, 1))
-        normals = -geometry.facets_normal[self.res_facet, :]
-        p = np.dot(normals, vel) * self.dt / thickness.reshape(-1, 1, 1)
-        return np.where(p < 0, 0, p)
-
     def initialise_modes(self, phonon):
         """Tile the active modes when there is at least one particle per mode and subvolume, draw them
         at random otherwise (Population.py:127-144)."""

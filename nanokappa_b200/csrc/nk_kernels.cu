@@ -486,7 +486,18 @@ struct nk_ctx {
     std::vector<double> h_tau, h_Tg;
     double hot_lo = 0, hot_hi = 0;
     int step_blocks = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;   // 5 events per profiled step
+    size_t ev_used = 0;
 };
+
+static void nk_prof_mark(nk_ctx* ctx) {
+    if (!ctx->profiling) return;
+    if (ctx->ev_used == ctx->ev.size()) {
+        cudaEvent_t e; cudaEventCreate(&e); ctx->ev.push_back(e);
+    }
+    cudaEventRecord(ctx->ev[ctx->ev_used++], ctx->stream);
+}
 
 static std::string g_create_err;
 
@@ -551,6 +562,7 @@ void nk_destroy(nk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (void* p : ctx->owned) cudaFree(p);
+    for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -921,16 +933,20 @@ int nk_step_local(nk_ctx* ctx) {
         if (per_sm < 1) per_sm = 1;
         ctx->step_blocks = per_sm * ctx->n_sm;
     }
+    nk_prof_mark(ctx);
     if (ctx->has_rough) k_step<true><<<ctx->step_blocks, NK_STEP_THREADS, smem, ctx->stream>>>(P);
     else k_step<false><<<ctx->step_blocks, NK_STEP_THREADS, smem, ctx->stream>>>(P);
     NK_CK(cudaGetLastError());
+    nk_prof_mark(ctx);
     if (P.R > 0) {
         long long total = (long long)P.R * (P.emit_m_hi - P.emit_m_lo);
         k_emit<<<nk_grid(total, 128, ctx->n_sm * 16), 128, 0, ctx->stream>>>(P);
         NK_CK(cudaGetLastError());
     }
+    nk_prof_mark(ctx);
     k_boundary<<<ctx->n_sm * 4, 128, 0, ctx->stream>>>(P);
     NK_CK(cudaGetLastError());
+    nk_prof_mark(ctx);
     return 0;
 }
 
@@ -941,6 +957,29 @@ int nk_step_finalize(nk_ctx* ctx) {
     while (threads < P.S && threads < 1024) threads <<= 1;
     k_finalize<<<1, threads, 3 * (size_t)P.S * 8, ctx->stream>>>(P);
     NK_CK(cudaGetLastError());
+    nk_prof_mark(ctx);
+    return 0;
+}
+
+int nk_profile_begin(nk_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    ctx->profiling = true; ctx->ev_used = 0;
+    return 0;
+}
+int nk_profile_end(nk_ctx* ctx, double* ms, int64_t* n_steps) {
+    cudaSetDevice(ctx->device);
+    ctx->profiling = false;
+    NK_CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 4; ++k) ms[k] = 0.0;
+    size_t steps = ctx->ev_used / 5;
+    for (size_t s = 0; s < steps; ++s)
+        for (int k = 0; k < 4; ++k) {
+            float t = 0.f;
+            NK_CK(cudaEventElapsedTime(&t, ctx->ev[5 * s + k], ctx->ev[5 * s + k + 1]));
+            ms[k] += t;
+        }
+    if (n_steps) *n_steps = (int64_t)steps;
+    ctx->ev_used = 0;
     return 0;
 }
 

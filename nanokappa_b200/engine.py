@@ -187,6 +187,16 @@ class Engine:
     def flush_relaxation(self):
         check(self.ctx, self.L.nk_flush_relaxation(self.ctx), "nk_flush_relaxation")
 
+    def profile_begin(self):
+        check(self.ctx, self.L.nk_profile_begin(self.ctx), "nk_profile_begin")
+
+    def profile_end(self):
+        """-> (dict kernel -> total ms, n_steps) of the steps launched since profile_begin."""
+        ms = (C.c_double * 4)()
+        n = C.c_int64()
+        check(self.ctx, self.L.nk_profile_end(self.ctx, ms, C.byref(n)), "nk_profile_end")
+        return dict(k_step=ms[0], k_emit=ms[1], k_boundary=ms[2], k_finalize=ms[3]), n.value
+
     def synchronize(self):
         check(self.ctx, self.L.nk_synchronize(self.ctx), "nk_synchronize")
 

@@ -380,6 +380,22 @@ def _delete(st, mask):
         setattr(st, name, getattr(st, name)[keep])
 
 
+def bisect_left_fixed(arr, keys):
+    """Per-key left bisection with fixed initial bounds [0, len) -- NumPy's loop without the
+    previous-key shortcut (numpy/_core/src/npysort/binsearch.cpp)."""
+    keys = np.asarray(keys, dtype=float)
+    lo = np.zeros(keys.shape[0], dtype=np.int64)
+    hi = np.full(keys.shape[0], arr.shape[0], dtype=np.int64)
+    while np.any(lo < hi):
+        act = lo < hi
+        mid = (lo + hi) >> 1
+        less = np.zeros_like(act)
+        less[act] = arr[mid[act]] < keys[act]
+        lo = np.where(act & less, mid + 1, lo)
+        hi = np.where(act & ~less, mid, hi)
+    return lo
+
+
 def select_reflected_modes(tb, st_T_sv, in_modes, col_fac, col_pos, n_in, omega_in, ids, rng, step, event):
     """Specular / diffuse choice on rough facets.  Population.py:941-1015 ('velocity' model)."""
     J = tb["omega"].shape[1]
@@ -408,7 +424,14 @@ def select_reflected_modes(tb, st_T_sv, in_modes, col_fac, col_pos, n_in, omega_
             i_f = tb["facet_rough"][facet]
             ev = d_ev[i_p] if np.ndim(d_ev) else d_ev
             u = rng.diffuse_pick(i_p.shape[0], d_ids[i_p], step, ev) * tb["roulette"][i_f, -1]
-            flat_i = np.searchsorted(tb["roulette"][i_f, :], u)
+            if rng.keyed:
+                # creation rates can be negative (more specular inflow than outflow), so the cumulative
+                # table is not always monotonic and np.searchsorted's answer then depends on the previous
+                # key of the batch (it narrows its bounds from it).  The keyed contract is the plain
+                # per-key bisection the GPU does; on monotonic tables both are identical.
+                flat_i = bisect_left_fixed(tb["roulette"][i_f, :], u)
+            else:
+                flat_i = np.searchsorted(tb["roulette"][i_f, :], u)
             new_q = np.floor(flat_i / J).astype(int)
             new_modes[i_p, 0] = new_q
             new_modes[i_p, 1] = flat_i - new_q * J
@@ -432,11 +455,9 @@ def boundary_scattering(tb, st, rng, classifier=None):
     new_ts = copy.copy(st.n_timesteps)
     st.N_leaving = np.zeros(R, dtype=int)
     event = np.zeros(idx_all.shape, dtype=np.int64)   # rough events so far this step (keys the RNG)
-    is_res = np.isin(tb["facet_bc"], (BC_T, BC_F))
 
     while np.any(calc < 1):
         # I. absorption into reservoirs (:1565-1608)
-        cond_res = is_res[st.collision_facets] if st.collision_facets.shape[0] else np.zeros(0, dtype=bool)
         cond_res = np.isin(st.collision_cond, (BC_T, BC_F))
         idx_del = np.logical_and(calc < 1, cond_res)
         idx_del = np.logical_and(idx_del, (1 - calc) > new_ts)
@@ -564,9 +585,27 @@ def refresh_temperatures(tb, st, classifier=None):
     st.temperatures = particle_temperature(tb, st.subvol_temperature, st.positions)
 
 
-def lifetime_scattering(tb, st):
+class SciPyBackend:
+    """The third-party objects the reference itself evaluates on the hot path, for the CPU timing legs
+    of bench.py: cKDTree behind NearestNDInterpolator (Geometry.py:1210), RegularGridInterpolator for
+    tau (Phonon.py:336) and the per-step gc.collect() (Population.py:1769).  Results are identical to
+    the NumPy restatements above (tests/test_oracle_pin.py::test_restated_thirdparty_formulas)."""
+
+    def __init__(self, tb, collect_garbage=True):
+        from scipy.interpolate import RegularGridInterpolator
+        from scipy.spatial import cKDTree
+        Q, J = tb["omega"].shape
+        self.kdtree = cKDTree(tb["sv_centres"])
+        self.rgi = RegularGridInterpolator((tb["T_grid"], np.arange(Q), np.arange(J)), tb["tau"])
+        self.collect_garbage = collect_garbage
+
+
+def lifetime_scattering(tb, st, backend=None):
     """Deterministic relaxation toward Bose-Einstein.  Population.py:1701-1710."""
-    tau = lifetime_function(tb, st.temperatures, st.modes)
+    if backend is not None:
+        tau = backend.rgi(np.hstack((st.temperatures.reshape(-1, 1), st.modes)))
+    else:
+        tau = lifetime_function(tb, st.temperatures, st.modes)
     n0 = calculate_occupation(tb, st.temperatures, st.omega)
     with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
         st.occupation = np.where(tau > 0, n0 + (st.occupation - n0) * np.exp(-tb["dt"] / tau), n0)
@@ -630,15 +669,17 @@ def restart_reservoir_balance(tb, st):
     st.res_energy_balance = np.zeros(R)
 
 
-def run_timestep(tb, st, rng, classifier=None, on_convergence=None):
+def run_timestep(tb, st, rng, classifier=None, on_convergence=None, backend=None):
     """One timestep without the every-100-step output branch.  Population.py:1724-1769."""
+    if backend is not None:
+        classifier = backend.kdtree
     drift(tb, st)
     if tb["res_facet"].shape[0] > 0:
         new = fill_reservoirs(tb, st, rng)
         add_reservoir_particles(tb, st, new)
     boundary_scattering(tb, st, rng, classifier)
     refresh_temperatures(tb, st, classifier)
-    lifetime_scattering(tb, st)
+    lifetime_scattering(tb, st, backend)
     st.current_timestep += 1
     if st.current_timestep % tb["n_dt_to_conv"] == 0:
         st.subvol_heat_flux = calculate_heat_flux(tb, st)
@@ -647,9 +688,94 @@ def run_timestep(tb, st, rng, classifier=None, on_convergence=None):
         if on_convergence is not None:
             on_convergence(st)
         restart_reservoir_balance(tb, st)
+    if backend is not None and backend.collect_garbage:
+        import gc
+        gc.collect()                                                                  # Population.py:1769
+
+
+def make_state(tb, positions, modes, subvol_temperature, res_counter, ids=None):
+    """State of a freshly initialised population: occupation = Bose-Einstein at the subvolume
+    temperature, first collisions for everybody (Population.py:270-321)."""
+    positions = np.array(positions, dtype=float)
+    modes = np.array(modes, dtype=int)
+    J = tb["omega"].shape[1]
+    R = tb["res_facet"].shape[0]
+    n = positions.shape[0]
+    sv = classify(tb, positions)
+    T_sv = np.array(subvol_temperature, dtype=float)
+    omega = tb["omega"][modes[:, 0], modes[:, 1]]
+    st = State(positions=positions, modes=modes, omega=omega, group_vel=tb["group_vel"][modes[:, 0], modes[:, 1], :],
+               occupation=calculate_occupation(tb, T_sv[sv], omega), n_timesteps=None, collision_facets=None,
+               collision_positions=None, collision_cond=None, temperatures=T_sv[sv],
+               ids=np.arange(n, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64),
+               subvol_temperature=T_sv, res_counter=np.array(res_counter, dtype=float))
+    st.omega_modes = modes[:, 0] * J + modes[:, 1]
+    st.subvol_id = sv
+    st.res_energy_balance = np.zeros(R)
+    st.res_heat_flux = np.zeros((R, 3))
+    st.N_leaving = np.zeros(R, dtype=int)
+    with np.errstate(all="ignore"):
+        init_collisions(tb, st)
+    return st
 
 
 def init_collisions(tb, st):
     """First boundary hit of every particle + initial per-SV quantities.  Population.py:308-321."""
     st.n_timesteps, st.collision_facets, st.collision_positions = timesteps_to_boundary(tb, st.positions, st.group_vel)
     st.collision_cond = collision_condition(tb, st.collision_facets)
+
+
+# ------------------------------------------------------------------------------------------------
+# particle shards (SURVEY 8e): the same timestep with the population split over ranks.  Only the
+# per-subvolume / per-reservoir sums are exchanged (reduce_fn = all-reduce sum of one f64 vector).
+# ------------------------------------------------------------------------------------------------
+def run_timestep_sharded(tb, st, rng, reduce_fn, mode_lo, mode_hi):
+    """One timestep of one rank: emission restricted to flat modes [mode_lo, mode_hi), local boundary
+    loop, per-SV sums all-reduced before the temperatures are inverted.  With keyed random draws the
+    union of all ranks' particles equals the single-rank run."""
+    S = tb["sv_centres"].shape[0]
+    R = tb["res_facet"].shape[0]
+    Q, J = tb["omega"].shape
+    drift(tb, st)
+    if R > 0:
+        full = tb["enter_prob"]
+        mask = np.zeros(Q * J, dtype=bool)
+        mask[mode_lo:mode_hi] = True
+        tb_local = dict(tb)
+        tb_local["enter_prob"] = np.where(mask.reshape(1, Q, J), full, 0.0)
+        counter_before = st.res_counter.copy()
+        new = fill_reservoirs(tb_local, st, rng)
+        # entries outside the share keep evolving on their owner only
+        st.res_counter = np.where(mask.reshape(1, Q, J), st.res_counter, counter_before)
+        add_reservoir_particles(tb, st, new)
+    boundary_scattering(tb, st, rng)
+    sv = classify(tb, st.positions)
+    st.subvol_id = sv
+    dn = st.occupation - calculate_occupation(tb, st.subvol_temperature[sv], st.omega)
+    st.energies = tb["hbar"] * st.omega * dn
+    vec = np.concatenate([np.bincount(sv, weights=st.energies, minlength=S), np.bincount(sv, minlength=S).astype(float),
+                          st.N_leaving.astype(float)])
+    vec = reduce_fn(vec)
+    e, cnt = vec[:S], vec[S:2 * S]
+    st.N_leaving = vec[2 * S:].astype(int)
+    st.subvol_N_p = cnt.astype(int)
+    st.N_p = int(cnt.sum())
+    with np.errstate(divide="ignore", invalid="ignore"):
+        norm = tb["n_active"] / cnt if tb["norm_mean"] else tb["n_active"] / (tb["particle_density"] * tb["sv_volume"])
+        norm = np.where(np.isnan(norm), 0, norm)
+        st.subvol_energy = normalise_to_density(tb, e * norm) + crystal_energy_function(tb, st.subvol_temperature)
+    st.subvol_temperature = temperature_function(tb, st.subvol_energy)
+    st.temperatures = particle_temperature(tb, st.subvol_temperature, st.positions)
+    lifetime_scattering(tb, st)
+    st.current_timestep += 1
+
+
+def shard_state(st, lo, hi):
+    """Rows [lo, hi) of a state as an independent State (per-SV vectors are shared values)."""
+    out = st.copy()
+    for name in ("positions", "group_vel", "omega", "occupation", "temperatures", "n_timesteps", "modes", "collision_facets",
+                 "collision_positions", "collision_cond", "ids", "omega_modes", "subvol_id", "energies"):
+        v = getattr(out, name)
+        if v is not None:
+            setattr(out, name, v[lo:hi].copy())
+    return out

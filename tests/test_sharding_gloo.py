@@ -1,0 +1,82 @@
+"""world_size-2 check of the particle-shard protocol on CPU (gloo): two ranks, each owning half of the
+particles and half of every reservoir's mode table, exchanging only the per-SV sum vector per step,
+must reproduce the single-rank run (same keyed draws): identical particle census and integer state,
+temperatures equal up to the order of the floating-point sums."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STEPS = 12
+SEED = 5
+
+
+def _worker(rank, world, port, fixture, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    from oracle import gen_golden, nk_oracle as nko
+    from nanokappa_b200.parallel import mode_range, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tb, st, _ = gen_golden.load_fixture(fixture)
+    lo, hi = shard_bounds(rank, world, st.positions.shape[0])
+    mine = nko.shard_state(st, lo, hi)
+    Q, J = tb["omega"].shape
+    m_lo, m_hi = mode_range(rank, world, Q * J)
+
+    def reduce_fn(v):
+        t = torch.from_numpy(np.ascontiguousarray(v))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    rng = nko.KeyedRNG(SEED)
+    with np.errstate(all="ignore"):
+        for _ in range(STEPS):
+            nko.run_timestep_sharded(tb, mine, rng, reduce_fn, m_lo, m_hi)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ids=mine.ids, modes=mine.modes, positions=mine.positions,
+             occupation=mine.occupation, facets=mine.collision_facets, T=mine.subvol_temperature, N=mine.subvol_N_p)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["c2_crossplane", "c1_mixed"])
+def test_two_rank_shards_equal_single_rank(name, golden_dir, tmp_path):
+    from oracle import gen_golden, nk_oracle as nko
+    fixture = os.path.join(golden_dir, name + ".npz")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, fixture, str(tmp_path)), nprocs=2, join=True)
+    tb, st, _ = gen_golden.load_fixture(fixture)
+    rng = nko.KeyedRNG(SEED)
+    with np.errstate(all="ignore"):
+        for _ in range(STEPS):
+            nko.run_timestep(tb, st, rng)
+    r = [np.load(os.path.join(tmp_path, f"rank{k}.npz")) for k in range(2)]
+    ids = np.concatenate([r[0]["ids"], r[1]["ids"]])
+    assert np.unique(ids).shape[0] == ids.shape[0], "a particle lives on two ranks"
+    order = np.argsort(ids)
+    ref = np.argsort(st.ids)
+    assert np.array_equal(ids[order], st.ids[ref]), "union of the shards differs from the single-rank census"
+    cat = lambda k: np.concatenate([r[0][k], r[1][k]])[order]
+    assert np.array_equal(cat("modes"), st.modes[ref])
+    assert np.array_equal(cat("facets"), st.collision_facets[ref])
+    assert np.allclose(cat("positions"), st.positions[ref], rtol=1e-12, atol=1e-9, equal_nan=True)
+    assert np.allclose(cat("occupation"), st.occupation[ref], rtol=1e-9, atol=0)
+    for k in range(2):
+        assert np.array_equal(r[k]["N"], st.subvol_N_p)
+        assert np.allclose(r[k]["T"], st.subvol_temperature, rtol=1e-12, atol=0)
+    assert np.array_equal(r[0]["T"], r[1]["T"]), "ranks disagree on T_sv after the all-reduce"
+
+
+def test_mode_and_particle_partitions_cover_everything():
+    from nanokappa_b200.parallel import mode_range, shard_bounds
+    for world in (1, 2, 3, 4, 8):
+        for n in (0, 1, 7, 178746, 10 ** 8 + 3):
+            spans = [mode_range(r, world, n) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert [shard_bounds(r, world, n) for r in range(world)] == spans
