@@ -173,6 +173,7 @@ def config_dict(a, n_per_gpu, where):
     return {"workload": "si_thin_film_crossplane: box (2e4 A)^3, T 302/298 K on x faces, periodic sides, 20 slice SVs, nearest T, dt 1 ps "
                         "(BASELINE configs[1] geometry at configs[4] scale)",
             "particles_per_gpu": int(n_per_gpu), "mode_table": f"synthetic {a.mesh}^3 x 6", "subvolumes": 20,
+            "particle_order": "tiled modes (as initialised)" if getattr(a, "no_sort", False) else "sorted by mode at set-up",
             "l2_policy": "inputs larger than L2 (no flush)" if n_per_gpu * 44 > 2.6e8 else "state fits L2; L2 flushed between timed steps",
             "parallelism": f"particle shards x{a.gpus}, per-step all-reduce of the per-SV vectors" if a.gpus > 1 else "single GPU"}
 
@@ -225,6 +226,8 @@ def gpu_arm(a):
     eng.set_timestep(0)
     eng.init_collisions()
     eng.synchronize()
+    if not a.no_sort:
+        eng.sort_by_mode()          # set-up-time layout choice: neighbours share mode records
 
     acc_t = None
     if world > 1:
@@ -391,6 +394,7 @@ def main():
     p.add_argument("--cpu-steps", type=int, default=20)
     p.add_argument("--e2e-calls", type=int, default=3)
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-sort", action="store_true", help="keep the tiled mode order of Population.initialise_modes")
     a = p.parse_args()
     if a.impl == "reference":
         reference_arm(a)

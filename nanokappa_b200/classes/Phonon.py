@@ -221,9 +221,27 @@ class Phonon(Constants):
         T_min, T_max = self.temperature_array.min(), self.temperature_array.max()
         dT = 0.1
         self.T_array = np.arange(T_min, T_max + dT, dT)
+        # optional on-disk cache of the (slow: nT x modes exponentials) table, keyed by its inputs
+        cache = os.environ.get('NK_TABLE_CACHE')
+        path = None
+        if cache:
+            import hashlib
+            h = hashlib.sha1()
+            for arr in (self.omega, self.inactive_modes_mask, self.T_array, np.array([self.volume_unitcell, self.hbar, self.kb])):
+                h.update(np.ascontiguousarray(arr).tobytes())
+            path = os.path.join(cache, 'nk_energy_table_{}.npy'.format(h.hexdigest()[:16]))
+            if os.path.isfile(path):
+                self.energy_array = np.load(path)
+                return
         chunk = max(1, int(4e6 // max(1, self.number_of_modes)))
         parts = [self.calculate_crystal_energy(self.T_array[i:i + chunk]) for i in range(0, self.T_array.shape[0], chunk)]
         self.energy_array = np.concatenate(parts).reshape(-1)
+        if path:
+            try:
+                os.makedirs(cache, exist_ok=True)
+                np.save(path, self.energy_array)
+            except OSError:
+                pass
 
     def temperature_function(self, E):
         if self.engine is not None:

@@ -141,15 +141,109 @@ __device__ __forceinline__ double nk_relax(const NkP& P, double T, int mode, dou
 }
 
 // ---- the streaming kernel ----------------------------------------------------------------------------
+//
+// One pass over the particle SoA per timestep: 5 x 16 B + 8 B vector loads, 5 x 16 B vector stores per
+// particle PAIR, one 64 B gather of the mode record {omega, v_g, tau slabs}.  Everything that depends only
+// on the subvolume (1/(k_B T_sv), tau interpolation weight and slab) is hoisted into a per-block
+// shared-memory table, so the per-particle arithmetic is: one Bose-Einstein evaluation shared by the
+// relaxation of the previous step and the energy of this one (the particle usually stays in its
+// subvolume), one decay exponential, the drift and a 1-D slice lookup.
+//
+// FAST = slice subvolumes + nearest temperature rule (the Si/Ge thin-film configurations).  The general
+// variant (linear interpolation along the slices, or grid/voronoi subvolumes) evaluates the per-particle
+// temperature and tau explicitly.
+//
+// Occupation / energy arithmetic uses a Newton-refined reciprocal instead of IEEE division (<= 2 ulp);
+// positions, collision times and every integer result keep the reference's exact operation order.
 #define NK_STEP_THREADS 256
-template <bool HAS_ROUGH>
+
+__device__ __forceinline__ double nk_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    if (!(fabs(x) > 1e-300 && fabs(x) < 1e300)) r = 1.0 / x;      // 0, inf, nan, denormal: exact path
+    return r;
+}
+
+struct NkSvHot {            // per-subvolume values hoisted out of the particle loop (shared memory)
+    double* invb;           // 1 / (k_B T_sv)   (0 when T_sv <= 0 -> occupation 0)
+    double* tw;             // tau interpolation weight w
+    int* tr;                // slab offset into the mode record (0..2) or -1 -> full table
+    int* ti;                // absolute slab index
+};
+__host__ __device__ static inline size_t nk_hot_smem_bytes(int S) { return (size_t)S * (2 * 8 + 2 * 4); }
+// carve + fill the table; caller syncs
+__device__ __forceinline__ NkSvHot nk_load_hot(const NkP& P, void* mem) {
+    NkSvHot h;
+    const int S = P.S;
+    h.invb = reinterpret_cast<double*>(mem); h.tw = h.invb + S;
+    h.tr = reinterpret_cast<int*>(h.tw + S); h.ti = h.tr + S;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        double T = P.T_sv[i];
+        h.invb[i] = T > 0.0 ? nk_div(1.0, nk_mul(T, P.kb)) : 0.0;
+        int it = nk_T_index(P, T);
+        double t0 = P.Tg[it], t1 = P.Tg[it + 1];
+        h.tw[i] = nk_div(nk_sub(T, t0), nk_sub(t1, t0));
+        int r = it - P.tau_i0;
+        h.tr[i] = (r >= 0 && r <= 2) ? r : -1;
+        h.ti[i] = it;
+    }
+    return h;
+}
+
+// 64 B mode record as two 256-bit non-coherent loads (LDG.E.256): {omega, v} and the tau slabs
+__device__ __forceinline__ void nk_ld256(const double* p, double4& v) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+}
+
+// Bose-Einstein with the hoisted 1/(k_B T): a = hbar*omega
+__device__ __forceinline__ double nk_bose_fast(double a, double omega, double invb) {
+    return (invb > 0.0 && omega > 0.0) ? nk_rcp(exp(a * invb) - 1.0) : 0.0;
+}
+
+// lifetime_scattering of one particle (Population.py:1701-1710) at its position BEFORE the drift of the
+// next step.  Returns the relaxed occupation; be0 / g0 = equilibrium occupation and slice used (FAST).
+template <bool FAST>
+__device__ __forceinline__ double nk_relax_particle(const NkP& P, const NkSvSmem& s, const NkSvHot& h, double x, double y, double z,
+                                                    int mode, double omega, double a, const double4& mt, double occ,
+                                                    double& be0, int& g0) {
+    const double dt = P.dt;
+    double tau;
+    if (FAST) {
+        const double xa = P.axis == 0 ? x : (P.axis == 1 ? y : z);
+        g0 = P.S > 1 ? nk_searchsorted_left(s.sv_mid, P.S - 1, xa, P.sv_inv_dx) : 0;     // interp1d 'nearest'
+        be0 = nk_bose_fast(a, omega, h.invb[g0]);
+        const int r = h.tr[g0];
+        const double w = h.tw[g0];
+        double lo, hi;
+        if (r >= 0) {
+            lo = r == 0 ? mt.x : (r == 1 ? mt.y : mt.z);
+            hi = r == 0 ? mt.y : (r == 1 ? mt.z : mt.w);
+        } else {
+            const int it = h.ti[g0];
+            lo = __ldg(P.tau + (size_t)it * P.M + mode);
+            hi = __ldg(P.tau + (size_t)(it + 1) * P.M + mode);
+        }
+        tau = nk_add(nk_mul(lo, nk_sub(1.0, w)), nk_mul(hi, w));
+    } else {
+        const double Ti = nk_particle_T(P, s.svc, s.sv_axis, s.sv_mid, s.T_sv, x, y, z, -1);
+        tau = nk_tau(P, Ti, mode);
+        be0 = (Ti > 0.0 && omega > 0.0) ? nk_rcp(exp(a * nk_rcp(nk_mul(Ti, P.kb))) - 1.0) : 0.0;
+        g0 = -1;
+    }
+    return tau > 0.0 ? be0 + (occ - be0) * exp(-dt * nk_rcp(tau)) : be0;
+}
+
+template <bool HAS_ROUGH, bool FAST>
 __global__ void __launch_bounds__(NK_STEP_THREADS, 3) k_step(NkP P) {
     extern __shared__ double sm[];
     NkSvSmem s = nk_load_sv(P, sm);
     const int S = P.S;
     double* binE = sm + nk_sv_smem_doubles(S);             // S
     double* binF = binE + S;                               // 3S
-    unsigned int* binC = reinterpret_cast<unsigned int*>(binF + 3 * S);   // S
+    unsigned int* binC = reinterpret_cast<unsigned int*>(binF + 3 * S);   // S (+ pad to 8 B)
+    NkSvHot h = nk_load_hot(P, binC + S + (S & 1));
     for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0.0; binC[i] = 0u; binF[3 * i] = 0.0; binF[3 * i + 1] = 0.0; binF[3 * i + 2] = 0.0; }
     __syncthreads();
 
@@ -157,8 +251,10 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, 3) k_step(NkP P) {
     const long long step = P.dyn->step;
     const bool relax = P.dyn->relax_pending != 0;
     const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
-    const double dt = P.dt;
+    const double dt = P.dt, hbar = P.hbar;
     const unsigned int lane = threadIdx.x & 31u;
+    const int axis = P.axis;
+    const NkModeHot* __restrict__ mhot = P.mhot;
 
     // the loop bound is WARP-uniform (lane 0's index) because the hit-list append below uses
     // full-mask warp votes; lanes past the end carry dead slots
@@ -180,42 +276,62 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, 3) k_step(NkP P) {
         }
         double xs[2] = {X.x, X.y}, ys[2] = {Y.x, Y.y}, zs[2] = {Z.x, Z.y}, tcs[2] = {TC.x, TC.y}, ocs[2] = {OC.x, OC.y};
         int mds[2] = {MD.x, MD.y}, oms[2] = {OM.x, OM.y};
+        bool hits[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            bool live = (base + k < n) && mds[k] >= 0;
+            const bool live = (base + k < n) && mds[k] >= 0;
             bool hit = false;
             if (live) {
-                NkMode mp = P.mprop[mds[k]];
-                double omega = mp.omega;
-                if (HAS_ROUGH && oms[k] != mds[k]) omega = P.mprop[oms[k]].omega;
+                double4 ma, mt;
+                nk_ld256(&mhot[mds[k]].omega, ma);        // omega, v_g
+                nk_ld256(&mhot[mds[k]].t[0], mt);         // tau slabs
+                double omega = ma.x;
+                if (HAS_ROUGH && oms[k] != mds[k]) omega = mhot[oms[k]].omega;
+                const double a = nk_mul(hbar, omega);
                 double x = xs[k], y = ys[k], z = zs[k], occ = ocs[k];
-                if (relax) {
-                    double Ti = nk_particle_T(P, s.svc, s.sv_axis, s.sv_mid, s.T_sv, x, y, z, -1);
-                    occ = nk_relax(P, Ti, mds[k], omega, occ);
-                }
-                x = nk_add(x, nk_mul(mp.vx, dt)); y = nk_add(y, nk_mul(mp.vy, dt)); z = nk_add(z, nk_mul(mp.vz, dt));
-                double tcn = nk_sub(tcs[k], 1.0);
+                double be0 = 0.0; int g0 = -1;
+                if (relax) occ = nk_relax_particle<FAST>(P, s, h, x, y, z, mds[k], omega, a, mt, occ, be0, g0);
+                x = nk_add(x, nk_mul(ma.y, dt)); y = nk_add(y, nk_mul(ma.z, dt)); z = nk_add(z, nk_mul(ma.w, dt));
+                const double tcn = nk_sub(tcs[k], 1.0);
                 xs[k] = x; ys[k] = y; zs[k] = z; tcs[k] = tcn; ocs[k] = occ;
                 hit = tcn < 0.0;
                 if (!hit) {
-                    int sv = nk_classify(P, s.svc, s.sv_mid, x, y, z);
-                    double e = nk_mul(nk_mul(P.hbar, omega), nk_sub(occ, nk_bose(P, s.T_sv[sv], omega)));
+                    int sv;
+                    if (FAST) {
+                        // nearest centre of a slice stack = 1-D lookup; inside 1e-6 A of a slice boundary the
+                        // full squared-distance comparison decides, so the index equals the reference's
+                        const double xa = axis == 0 ? x : (axis == 1 ? y : z);
+                        sv = S > 1 ? nk_searchsorted_left(s.sv_mid, S - 1, xa, P.sv_inv_dx) : 0;
+                        const bool edge = (sv > 0 && xa - s.sv_mid[sv - 1] < 1e-6) || (sv < S - 1 && s.sv_mid[sv] - xa < 1e-6);
+                        if (edge) sv = nk_classify(P, s.svc, s.sv_mid, x, y, z);
+                    } else {
+                        sv = nk_classify(P, s.svc, s.sv_mid, x, y, z);
+                    }
+                    double be1 = be0;
+                    if (!(FAST && relax && sv == g0)) be1 = nk_bose_fast(a, omega, h.invb[sv]);
+                    const double e = a * (occ - be1);
                     atomicAdd(binE + sv, e);
                     atomicAdd(binC + sv, 1u);
                     if (with_flux) {
-                        atomicAdd(binF + 3 * sv, nk_mul(mp.vx, e));
-                        atomicAdd(binF + 3 * sv + 1, nk_mul(mp.vy, e));
-                        atomicAdd(binF + 3 * sv + 2, nk_mul(mp.vz, e));
+                        atomicAdd(binF + 3 * sv, ma.y * e);
+                        atomicAdd(binF + 3 * sv + 1, ma.z * e);
+                        atomicAdd(binF + 3 * sv + 2, ma.w * e);
                     }
                 }
             }
-            // warp-aggregated append to the hit list
-            unsigned int m = __ballot_sync(0xffffffffu, hit);
-            if (m) {
-                unsigned int leader = __ffs(m) - 1u, pos = 0;
-                if (lane == leader) pos = atomicAdd(&P.dyn->n_hits, __popc(m));
-                pos = __shfl_sync(0xffffffffu, pos, leader);
-                if (hit) P.hitlist[pos + __popc(m & ((1u << lane) - 1u))] = (int)(base + k);
+            hits[k] = hit;
+        }
+        // warp-aggregated append to the hit list (both particles of every lane in one vote)
+        {
+            const unsigned int m0 = __ballot_sync(0xffffffffu, hits[0]);
+            const unsigned int m1 = __ballot_sync(0xffffffffu, hits[1]);
+            if (m0 | m1) {
+                unsigned int pos = 0;
+                if (lane == 0) pos = atomicAdd(&P.dyn->n_hits, __popc(m0) + __popc(m1));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                const unsigned int below = (1u << lane) - 1u;
+                if (hits[0]) P.hitlist[pos + __popc(m0 & below)] = (int)base;
+                if (hits[1]) P.hitlist[pos + __popc(m0) + __popc(m1 & below)] = (int)(base + 1);
             }
         }
         if (inb) {
@@ -453,9 +569,12 @@ __global__ void __launch_bounds__(1024) k_finalize(NkP P) {
 }
 
 // apply the deferred lifetime_scattering so that `occ` is what the reference holds after run_timestep
+// (same arithmetic as the head of k_step, so flushing between steps is bit-neutral)
+template <bool FAST>
 __global__ void __launch_bounds__(256) k_flush_relax(NkP P) {
     extern __shared__ double sm[];
     NkSvSmem s = nk_load_sv(P, sm);
+    NkSvHot h = nk_load_hot(P, sm + nk_sv_smem_doubles(P.S));
     __syncthreads();
     if (!P.dyn->relax_pending) return;
     const long long n = P.dyn->n_slots;
@@ -463,9 +582,12 @@ __global__ void __launch_bounds__(256) k_flush_relax(NkP P) {
         int md = P.mode[i];
         if (md < 0) continue;
         int om = P.omode[i];
-        double omega = P.mprop[om].omega;
-        double Ti = nk_particle_T(P, s.svc, s.sv_axis, s.sv_mid, s.T_sv, P.px[i], P.py[i], P.pz[i], -1);
-        P.occ[i] = nk_relax(P, Ti, md, omega, P.occ[i]);
+        double4 ma, mt;
+        nk_ld256(&P.mhot[md].omega, ma);
+        nk_ld256(&P.mhot[md].t[0], mt);
+        double omega = om == md ? ma.x : P.mhot[om].omega;
+        double be0; int g0;
+        P.occ[i] = nk_relax_particle<FAST>(P, s, h, P.px[i], P.py[i], P.pz[i], md, omega, nk_mul(P.hbar, omega), mt, P.occ[i], be0, g0);
     }
 }
 __global__ void k_clear_relax(NkP P) { P.dyn->relax_pending = 0; }
@@ -483,7 +605,7 @@ struct nk_ctx {
     int has_rough = 0;
     bool particles_bound = false;
     // host mirrors needed to rebuild derived tables
-    std::vector<double> h_tau, h_Tg;
+    std::vector<double> h_tau, h_Tg, h_mode;
     double hot_lo = 0, hot_hi = 0;
     int step_blocks = 0;
     bool profiling = false;
@@ -665,6 +787,16 @@ static int nk_build_tau4(nk_ctx* ctx) {
         for (int k = 0; k < 4; ++k) t4[m].t[k] = (i0 + k < NT) ? ctx->h_tau[(size_t)(i0 + k) * M + m] : 0.0;
     NkTau4* d; NK_UP(d, NkTau4, t4.data(), (size_t)M);
     P.tau4 = d; P.tau_i0 = (NT >= 4) ? i0 : -1000000;
+    // 64 B hot record per mode for the streaming kernel: {omega, v_g} + the same four tau slabs
+    std::vector<NkModeHot> hot(M);
+    for (int m = 0; m < M; ++m) {
+        hot[m].omega = ctx->h_mode[4 * (size_t)m]; hot[m].vx = ctx->h_mode[4 * (size_t)m + 1];
+        hot[m].vy = ctx->h_mode[4 * (size_t)m + 2]; hot[m].vz = ctx->h_mode[4 * (size_t)m + 3];
+        for (int k = 0; k < 4; ++k) hot[m].t[k] = t4[m].t[k];
+    }
+    NkModeHot* dh; NK_UP(dh, NkModeHot, hot.data(), (size_t)M);
+    P.mhot = dh;
+    ctx->step_blocks = 0;
     return 0;
 }
 
@@ -687,6 +819,8 @@ int nk_set_phonon(nk_ctx* ctx, int Q, int J, int NT, const double* Tg, const dou
     P.nE = nE; P.hbar = hbar; P.kb = kb; P.V_uc = V_uc; P.n_active = (double)n_active;
     P.dens_norm = (double)Q * V_uc;
     P.Tg_inv_d = 1.0 / (Tg[1] - Tg[0]);
+    ctx->h_mode.resize(4 * (size_t)M);
+    for (int m = 0; m < M; ++m) { ctx->h_mode[4 * (size_t)m] = mp[m].omega; ctx->h_mode[4 * (size_t)m + 1] = mp[m].vx; ctx->h_mode[4 * (size_t)m + 2] = mp[m].vy; ctx->h_mode[4 * (size_t)m + 3] = mp[m].vz; }
     ctx->h_tau.assign(tau, tau + (size_t)NT * M);
     ctx->h_Tg.assign(Tg, Tg + NT);
     if (ctx->hot_hi == 0) { ctx->hot_lo = 295.0; ctx->hot_hi = 305.0; }
@@ -906,7 +1040,7 @@ int nk_particle_temperature(nk_ctx* ctx, int64_t n, const double* x, double* T) 
 static int nk_check_ready(nk_ctx* ctx) {
     const NkP& P = ctx->P;
     if (!ctx->particles_bound) { ctx->err = "particles not bound"; return -1; }
-    if (!P.faces || !P.svc || !P.mprop || !P.acc) { ctx->err = "tables missing: call nk_set_mesh, nk_set_subvols, nk_set_phonon, nk_set_population, nk_set_reservoirs first"; return -1; }
+    if (!P.faces || !P.svc || !P.mprop || !P.mhot || !P.acc) { ctx->err = "tables missing: call nk_set_mesh, nk_set_subvols, nk_set_phonon, nk_set_population, nk_set_reservoirs first"; return -1; }
     if (P.dt <= 0) { ctx->err = "nk_set_population not called"; return -1; }
     return 0;
 }
@@ -919,23 +1053,24 @@ int nk_init_collisions(nk_ctx* ctx) {
     return 0;
 }
 
-static size_t nk_step_smem(const NkP& P) { return (nk_sv_smem_doubles(P.S) + 4 * (size_t)P.S) * 8 + (size_t)P.S * 4 + 8; }
+static size_t nk_step_smem(const NkP& P) { return (nk_sv_smem_doubles(P.S) + 4 * (size_t)P.S) * 8 + ((size_t)P.S + 2) * 4 + nk_hot_smem_bytes(P.S) + 16; }
 
 int nk_step_local(nk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (nk_check_ready(ctx)) return -1;
     const NkP& P = ctx->P;
     size_t smem = nk_step_smem(P);
+    const bool fast = P.is_slice && P.interp == NK_INTERP_NEAREST;
+    void (*kern)(NkP) = ctx->has_rough ? (fast ? k_step<true, true> : k_step<true, false>)
+                                       : (fast ? k_step<false, true> : k_step<false, false>);
     if (!ctx->step_blocks) {
         int per_sm = 0;
-        if (ctx->has_rough) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step<true>, NK_STEP_THREADS, smem);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step<false>, NK_STEP_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NK_STEP_THREADS, smem);
         if (per_sm < 1) per_sm = 1;
         ctx->step_blocks = per_sm * ctx->n_sm;
     }
     nk_prof_mark(ctx);
-    if (ctx->has_rough) k_step<true><<<ctx->step_blocks, NK_STEP_THREADS, smem, ctx->stream>>>(P);
-    else k_step<false><<<ctx->step_blocks, NK_STEP_THREADS, smem, ctx->stream>>>(P);
+    kern<<<ctx->step_blocks, NK_STEP_THREADS, smem, ctx->stream>>>(P);
     NK_CK(cudaGetLastError());
     nk_prof_mark(ctx);
     if (P.R > 0) {
@@ -994,8 +1129,9 @@ int nk_step(nk_ctx* ctx, int n_steps) {
 int nk_flush_relaxation(nk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (nk_check_ready(ctx)) return -1;
-    size_t smem = nk_sv_smem_doubles(ctx->P.S) * 8;
-    k_flush_relax<<<ctx->n_sm * 8, 256, smem, ctx->stream>>>(ctx->P);
+    size_t smem = nk_sv_smem_doubles(ctx->P.S) * 8 + nk_hot_smem_bytes(ctx->P.S);
+    if (ctx->P.is_slice && ctx->P.interp == NK_INTERP_NEAREST) k_flush_relax<true><<<ctx->n_sm * 8, 256, smem, ctx->stream>>>(ctx->P);
+    else k_flush_relax<false><<<ctx->n_sm * 8, 256, smem, ctx->stream>>>(ctx->P);
     NK_CK(cudaGetLastError());
     k_clear_relax<<<1, 1, 0, ctx->stream>>>(ctx->P);
     NK_CK(cudaGetLastError());

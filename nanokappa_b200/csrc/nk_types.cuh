@@ -31,6 +31,12 @@ struct __align__(32) NkTau4 {
     double t[4];
 };
 
+// streaming-kernel record: one 64 B line segment per mode = {omega, v_g} + tau slabs tau_i0..tau_i0+3
+struct __align__(64) NkModeHot {
+    double omega, vx, vy, vz;
+    double t[4];
+};
+
 struct NkDyn {                   // device-resident, mutated by kernels
     long long n_slots;           // slots [0, n_slots) are live or on the free list
     long long n_free;            // free-list height (may dip below 0 inside nk_emit_kernel)
@@ -71,6 +77,7 @@ struct NkP {
     const NkMode* mprop;              // (M)
     const double* tau;                // (NT, M)
     const NkTau4* tau4;               // (M) slabs tau_i0 .. tau_i0+3
+    const NkModeHot* mhot;            // (M) hot record of the streaming kernel
     int tau_i0;
     double Tg_inv_d;                  // 1 / (Tg[1]-Tg[0]) guess
     int nE; const double* Ea; const double* Ta;

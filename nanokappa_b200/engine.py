@@ -165,6 +165,25 @@ class Engine:
         if n_timesteps is None:
             self.init_collisions()
 
+    def sort_by_mode(self):
+        """Maintenance pass (not part of a timestep): compact the slots and order the live particles by
+        mode index, so that the 64-byte mode-record gathers of neighbouring lanes hit the same cache line.
+        Sums are order independent; particle identity is carried by `pid`.  Drops the free list."""
+        n, _ = self.slot_count()
+        if n == 0:
+            return
+        t = self.t
+        mode = t["mode"][:n]
+        key = torch.where(mode >= 0, mode, torch.full_like(mode, 2 ** 31 - 1))
+        perm = torch.argsort(key, stable=True)
+        n_live = int((mode >= 0).sum().item())
+        for k in ("px", "py", "pz", "tc", "occ", "mode", "omode", "cfacet", "cx", "cy", "cz", "pid"):
+            t[k][:n] = t[k][:n][perm]
+        del perm, key
+        t["mode"][n_live:n] = -1
+        torch.cuda.synchronize(self.device)
+        check(self.ctx, self.L.nk_set_slot_count(self.ctx, n_live), "nk_set_slot_count")
+
     def set_sv_temperature(self, T):
         T = _f64(T)
         check(self.ctx, self.L.nk_set_sv_temperature(self.ctx, _p(T)), "nk_set_sv_temperature")
