@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnk_b200.so")
+LIB_PATH = os.environ.get("NK_LIB", os.path.join(_HERE, "libnk_b200.so"))   # NK_LIB: experiment builds
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)

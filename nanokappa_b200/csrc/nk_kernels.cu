@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 #include <cmath>
+#include <cstdlib>
 
 #include "../../include/nk_b200.h"
 #include "nk_device.cuh"
@@ -156,29 +157,82 @@ __device__ __forceinline__ double nk_relax(const NkP& P, double T, int mode, dou
 // Occupation / energy arithmetic uses a Newton-refined reciprocal instead of IEEE division (<= 2 ulp);
 // positions, collision times and every integer result keep the reference's exact operation order.
 #define NK_STEP_THREADS 256
+#ifndef NK_STEP_MIN_BLOCKS
+#define NK_STEP_MIN_BLOCKS 4
+#endif
 
+// Newton-refined reciprocal of a positive normal double (<= 2 ulp): MUFU.RCP64H + 4 DFMA, no branch
 __device__ __forceinline__ double nk_rcp(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     r = fma(fma(-x, r, 1.0), r, r);
     r = fma(fma(-x, r, 1.0), r, r);
-    if (!(fabs(x) > 1e-300 && fabs(x) < 1e300)) r = 1.0 / x;      // 0, inf, nan, denormal: exact path
     return r;
+}
+
+// Branch-free exp for the occupation arithmetic: argument clamped to [-708, 709] (results there are
+// ~1e-308 / ~1e308, i.e. 0 / inf for every use below), Cody-Waite reduction, degree-13 Taylor polynomial on
+// |r| <= ln2/2 (truncation 4e-18), exponent added with integer arithmetic.  Coefficients live in constant
+// memory so that they are DFMA operands instead of 64-bit immediates.
+__constant__ double NK_EXP_C[12] = {
+    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+    1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+__device__ __forceinline__ double nk_exp(double x) {
+    x = fmin(fmax(x, -708.0), 709.0);
+    const double magic = 6755399441055744.0;                      // 2^52 + 2^51: rounds to nearest integer
+    const double t = fma(x, 1.4426950408889634, magic);
+    const int k = __double2loint(t);
+    const double kf = t - magic;
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double p = NK_EXP_C[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) p = fma(p, r, NK_EXP_C[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// Bose-Einstein with the hoisted 1/(k_B T): a = hbar*omega.  exp(x)-1 == 0 only for x == 0 -> inf like 1/0.
+__device__ __forceinline__ double nk_bose_fast(double a, double omega, double invb) {
+    const double d = nk_exp(a * invb) - 1.0;
+    const double v = d > 0.0 ? nk_rcp(d) : CUDART_INF;
+    return (invb > 0.0 && omega > 0.0) ? v : 0.0;
+}
+__device__ __forceinline__ double nk_decay(double dt, double tau) {       // exp(-dt/tau), tau > 0
+    return nk_exp(-dt * nk_rcp(tau));
+}
+
+// slice index of a coordinate = searchsorted(mid, xa, 'left') for uniformly spaced slices: arithmetic guess
+// verified against the padded boundary table midp[0..S] (midp[0] = -inf, midp[S] = +inf); the exact
+// bisection runs only when the guess is off (never for in-range coordinates, kept for safety).
+__device__ __forceinline__ int nk_slice_lookup(const NkP& P, const double* midp, const double* mid, double xa, double& lo, double& hi) {
+    int g = __double2int_rd((xa - P.sv_x0) * P.sv_inv_dx);
+    g = max(0, min(g, P.S - 1));
+    lo = midp[g]; hi = midp[g + 1];
+    if (!((lo < xa) && (xa <= hi))) {
+        g = P.S > 1 ? nk_searchsorted_left(mid, P.S - 1, xa, P.sv_inv_dx) : 0;
+        lo = midp[g]; hi = midp[g + 1];
+    }
+    return g;
 }
 
 struct NkSvHot {            // per-subvolume values hoisted out of the particle loop (shared memory)
     double* invb;           // 1 / (k_B T_sv)   (0 when T_sv <= 0 -> occupation 0)
     double* tw;             // tau interpolation weight w
+    double* midp;           // (S+1) slice boundaries padded with -inf / +inf
     int* tr;                // slab offset into the mode record (0..2) or -1 -> full table
     int* ti;                // absolute slab index
 };
-__host__ __device__ static inline size_t nk_hot_smem_bytes(int S) { return (size_t)S * (2 * 8 + 2 * 4); }
+__host__ __device__ static inline size_t nk_hot_smem_bytes(int S) { return (size_t)S * (3 * 8 + 2 * 4) + 16; }
 // carve + fill the table; caller syncs
 __device__ __forceinline__ NkSvHot nk_load_hot(const NkP& P, void* mem) {
     NkSvHot h;
     const int S = P.S;
-    h.invb = reinterpret_cast<double*>(mem); h.tw = h.invb + S;
-    h.tr = reinterpret_cast<int*>(h.tw + S); h.ti = h.tr + S;
+    h.invb = reinterpret_cast<double*>(mem); h.tw = h.invb + S; h.midp = h.tw + S;
+    h.tr = reinterpret_cast<int*>(h.midp + S + 1); h.ti = h.tr + S;
+    for (int i = threadIdx.x; i <= S; i += blockDim.x)
+        h.midp[i] = i == 0 ? -CUDART_INF : (i == S ? CUDART_INF : P.sv_mid[i - 1]);
     for (int i = threadIdx.x; i < S; i += blockDim.x) {
         double T = P.T_sv[i];
         h.invb[i] = T > 0.0 ? nk_div(1.0, nk_mul(T, P.kb)) : 0.0;
@@ -197,10 +251,6 @@ __device__ __forceinline__ void nk_ld256(const double* p, double4& v) {
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
 }
 
-// Bose-Einstein with the hoisted 1/(k_B T): a = hbar*omega
-__device__ __forceinline__ double nk_bose_fast(double a, double omega, double invb) {
-    return (invb > 0.0 && omega > 0.0) ? nk_rcp(exp(a * invb) - 1.0) : 0.0;
-}
 
 // lifetime_scattering of one particle (Population.py:1701-1710) at its position BEFORE the drift of the
 // next step.  Returns the relaxed occupation; be0 / g0 = equilibrium occupation and slice used (FAST).
@@ -208,19 +258,17 @@ template <bool FAST>
 __device__ __forceinline__ double nk_relax_particle(const NkP& P, const NkSvSmem& s, const NkSvHot& h, double x, double y, double z,
                                                     int mode, double omega, double a, const double4& mt, double occ,
                                                     double& be0, int& g0) {
-    const double dt = P.dt;
     double tau;
     if (FAST) {
         const double xa = P.axis == 0 ? x : (P.axis == 1 ? y : z);
-        g0 = P.S > 1 ? nk_searchsorted_left(s.sv_mid, P.S - 1, xa, P.sv_inv_dx) : 0;     // interp1d 'nearest'
+        double lo_b, hi_b;
+        g0 = nk_slice_lookup(P, h.midp, s.sv_mid, xa, lo_b, hi_b);                        // interp1d 'nearest'
         be0 = nk_bose_fast(a, omega, h.invb[g0]);
         const int r = h.tr[g0];
         const double w = h.tw[g0];
-        double lo, hi;
-        if (r >= 0) {
-            lo = r == 0 ? mt.x : (r == 1 ? mt.y : mt.z);
-            hi = r == 0 ? mt.y : (r == 1 ? mt.z : mt.w);
-        } else {
+        double lo = r == 0 ? mt.x : (r == 1 ? mt.y : mt.z);
+        double hi = r == 0 ? mt.y : (r == 1 ? mt.z : mt.w);
+        if (r < 0) {                                                                       // temperature outside the packed slabs
             const int it = h.ti[g0];
             lo = __ldg(P.tau + (size_t)it * P.M + mode);
             hi = __ldg(P.tau + (size_t)(it + 1) * P.M + mode);
@@ -229,14 +277,90 @@ __device__ __forceinline__ double nk_relax_particle(const NkP& P, const NkSvSmem
     } else {
         const double Ti = nk_particle_T(P, s.svc, s.sv_axis, s.sv_mid, s.T_sv, x, y, z, -1);
         tau = nk_tau(P, Ti, mode);
-        be0 = (Ti > 0.0 && omega > 0.0) ? nk_rcp(exp(a * nk_rcp(nk_mul(Ti, P.kb))) - 1.0) : 0.0;
+        be0 = nk_bose_fast(a, omega, Ti > 0.0 ? nk_rcp(nk_mul(Ti, P.kb)) : 0.0);
         g0 = -1;
     }
-    return tau > 0.0 ? be0 + (occ - be0) * exp(-dt * nk_rcp(tau)) : be0;
+    const double relaxed = be0 + (occ - be0) * nk_decay(P.dt, tau > 0.0 ? tau : 1.0);
+    return tau > 0.0 ? relaxed : be0;
 }
 
-template <bool HAS_ROUGH, bool FAST>
-__global__ void __launch_bounds__(NK_STEP_THREADS, 3) k_step(NkP P) {
+// one live particle: deferred relaxation -> drift -> (if no collision this step) subvolume + energy bins.
+// Returns true when the particle's collision falls inside this step (it then goes to the hit list).
+template <bool HAS_ROUGH, bool FAST, bool RELAX, bool FLUX>
+__device__ __forceinline__ bool nk_step_particle(const NkP& P, const NkSvSmem& s, const NkSvHot& h, double* binE, double* binF,
+                                                 unsigned int* binC, int md, int om, double& x, double& y, double& z,
+                                                 double& tc, double& occ) {
+    const NkModeHot* __restrict__ mhot = P.mhot;
+    double4 ma, mt;
+    nk_ld256(&mhot[md].omega, ma);        // omega, v_g
+    nk_ld256(&mhot[md].t[0], mt);         // tau slabs
+    double omega = ma.x;
+    if (HAS_ROUGH && om != md) omega = mhot[om].omega;
+    const double a = nk_mul(P.hbar, omega);
+    const double dt = P.dt;
+    double be0 = 0.0; int g0 = -1;
+    if (RELAX) occ = nk_relax_particle<FAST>(P, s, h, x, y, z, md, omega, a, mt, occ, be0, g0);
+    x = nk_add(x, nk_mul(ma.y, dt)); y = nk_add(y, nk_mul(ma.z, dt)); z = nk_add(z, nk_mul(ma.w, dt));
+    tc = nk_sub(tc, 1.0);
+    if (tc < 0.0) return true;
+    int sv;
+    if (FAST) {
+        // nearest centre of a slice stack = 1-D lookup; inside 1e-6 A of a slice boundary the full
+        // squared-distance comparison decides, so the index equals the reference's
+        const double xa = P.axis == 0 ? x : (P.axis == 1 ? y : z);
+        double lo_b, hi_b;
+        sv = nk_slice_lookup(P, h.midp, s.sv_mid, xa, lo_b, hi_b);
+        if ((xa - lo_b < 1e-6) || (hi_b - xa < 1e-6)) sv = nk_classify(P, s.svc, s.sv_mid, x, y, z);
+    } else {
+        sv = nk_classify(P, s.svc, s.sv_mid, x, y, z);
+    }
+    double be1 = be0;
+    if (!(FAST && RELAX && sv == g0)) be1 = nk_bose_fast(a, omega, h.invb[sv]);
+    const double e = a * (occ - be1);
+    atomicAdd(binE + sv, e);
+    atomicAdd(binC + sv, 1u);
+    if (FLUX) {
+        atomicAdd(binF + 3 * sv, ma.y * e);
+        atomicAdd(binF + 3 * sv + 1, ma.z * e);
+        atomicAdd(binF + 3 * sv + 2, ma.w * e);
+    }
+    return false;
+}
+
+// warp-aggregated append of up to two slots per lane to the hit list (full-mask votes: call converged)
+__device__ __forceinline__ void nk_push_hits(const NkP& P, unsigned int lane, bool h0, bool h1, long long base) {
+    const unsigned int m0 = __ballot_sync(0xffffffffu, h0);
+    const unsigned int m1 = __ballot_sync(0xffffffffu, h1);
+    if (m0 | m1) {
+        unsigned int pos = 0;
+        if (lane == 0) pos = atomicAdd(&P.dyn->n_hits, __popc(m0) + __popc(m1));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        const unsigned int below = (1u << lane) - 1u;
+        if (h0) P.hitlist[pos + __popc(m0 & below)] = (int)base;
+        if (h1) P.hitlist[pos + __popc(m0) + __popc(m1 & below)] = (int)(base + 1);
+    }
+}
+
+template <bool FLUX>
+__device__ __forceinline__ void nk_flush_bins(const NkP& P, const double* binE, const double* binF, const unsigned int* binC) {
+    const int S = P.S;
+    double* acc = P.acc;
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        if (binC[i]) {
+            atomicAdd(acc + NK_ACC_E(S, P.R) + i, binE[i]);
+            atomicAdd(acc + NK_ACC_CNT(S, P.R) + i, (double)binC[i]);
+            if (FLUX) {
+                atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i, binF[3 * i]);
+                atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i + 1, binF[3 * i + 1]);
+                atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i + 2, binF[3 * i + 2]);
+            }
+        }
+    }
+}
+
+// ---- variant A: direct 128-bit global loads/stores (any capacity) ------------------------------------------
+template <bool HAS_ROUGH, bool FAST, bool RELAX, bool FLUX>
+__global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step(NkP P) {
     extern __shared__ double sm[];
     NkSvSmem s = nk_load_sv(P, sm);
     const int S = P.S;
@@ -248,16 +372,10 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, 3) k_step(NkP P) {
     __syncthreads();
 
     const long long n = P.dyn->n_slots;
-    const long long step = P.dyn->step;
-    const bool relax = P.dyn->relax_pending != 0;
-    const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
-    const double dt = P.dt, hbar = P.hbar;
     const unsigned int lane = threadIdx.x & 31u;
-    const int axis = P.axis;
-    const NkModeHot* __restrict__ mhot = P.mhot;
 
-    // the loop bound is WARP-uniform (lane 0's index) because the hit-list append below uses
-    // full-mask warp votes; lanes past the end carry dead slots
+    // the loop bound is WARP-uniform (lane 0's index) because the hit-list append uses full-mask warp
+    // votes; lanes past the end carry dead slots
     for (long long wbase = 2 * ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); wbase < n;
          wbase += 2 * (long long)gridDim.x * blockDim.x) {
         const long long base = wbase + 2 * lane;
@@ -274,87 +392,201 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, 3) k_step(NkP P) {
             OM = MD;
             if (HAS_ROUGH) OM = *reinterpret_cast<const int2*>(P.omode + base);
         }
-        double xs[2] = {X.x, X.y}, ys[2] = {Y.x, Y.y}, zs[2] = {Z.x, Z.y}, tcs[2] = {TC.x, TC.y}, ocs[2] = {OC.x, OC.y};
-        int mds[2] = {MD.x, MD.y}, oms[2] = {OM.x, OM.y};
-        bool hits[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const bool live = (base + k < n) && mds[k] >= 0;
-            bool hit = false;
-            if (live) {
-                double4 ma, mt;
-                nk_ld256(&mhot[mds[k]].omega, ma);        // omega, v_g
-                nk_ld256(&mhot[mds[k]].t[0], mt);         // tau slabs
-                double omega = ma.x;
-                if (HAS_ROUGH && oms[k] != mds[k]) omega = mhot[oms[k]].omega;
-                const double a = nk_mul(hbar, omega);
-                double x = xs[k], y = ys[k], z = zs[k], occ = ocs[k];
-                double be0 = 0.0; int g0 = -1;
-                if (relax) occ = nk_relax_particle<FAST>(P, s, h, x, y, z, mds[k], omega, a, mt, occ, be0, g0);
-                x = nk_add(x, nk_mul(ma.y, dt)); y = nk_add(y, nk_mul(ma.z, dt)); z = nk_add(z, nk_mul(ma.w, dt));
-                const double tcn = nk_sub(tcs[k], 1.0);
-                xs[k] = x; ys[k] = y; zs[k] = z; tcs[k] = tcn; ocs[k] = occ;
-                hit = tcn < 0.0;
-                if (!hit) {
-                    int sv;
-                    if (FAST) {
-                        // nearest centre of a slice stack = 1-D lookup; inside 1e-6 A of a slice boundary the
-                        // full squared-distance comparison decides, so the index equals the reference's
-                        const double xa = axis == 0 ? x : (axis == 1 ? y : z);
-                        sv = S > 1 ? nk_searchsorted_left(s.sv_mid, S - 1, xa, P.sv_inv_dx) : 0;
-                        const bool edge = (sv > 0 && xa - s.sv_mid[sv - 1] < 1e-6) || (sv < S - 1 && s.sv_mid[sv] - xa < 1e-6);
-                        if (edge) sv = nk_classify(P, s.svc, s.sv_mid, x, y, z);
-                    } else {
-                        sv = nk_classify(P, s.svc, s.sv_mid, x, y, z);
-                    }
-                    double be1 = be0;
-                    if (!(FAST && relax && sv == g0)) be1 = nk_bose_fast(a, omega, h.invb[sv]);
-                    const double e = a * (occ - be1);
-                    atomicAdd(binE + sv, e);
-                    atomicAdd(binC + sv, 1u);
-                    if (with_flux) {
-                        atomicAdd(binF + 3 * sv, ma.y * e);
-                        atomicAdd(binF + 3 * sv + 1, ma.z * e);
-                        atomicAdd(binF + 3 * sv + 2, ma.w * e);
-                    }
-                }
-            }
-            hits[k] = hit;
-        }
-        // warp-aggregated append to the hit list (both particles of every lane in one vote)
-        {
-            const unsigned int m0 = __ballot_sync(0xffffffffu, hits[0]);
-            const unsigned int m1 = __ballot_sync(0xffffffffu, hits[1]);
-            if (m0 | m1) {
-                unsigned int pos = 0;
-                if (lane == 0) pos = atomicAdd(&P.dyn->n_hits, __popc(m0) + __popc(m1));
-                pos = __shfl_sync(0xffffffffu, pos, 0);
-                const unsigned int below = (1u << lane) - 1u;
-                if (hits[0]) P.hitlist[pos + __popc(m0 & below)] = (int)base;
-                if (hits[1]) P.hitlist[pos + __popc(m0) + __popc(m1 & below)] = (int)(base + 1);
-            }
-        }
+        bool h0 = false, h1 = false;
+        if (base < n && MD.x >= 0) h0 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binC, MD.x, OM.x, X.x, Y.x, Z.x, TC.x, OC.x);
+        if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binC, MD.y, OM.y, X.y, Y.y, Z.y, TC.y, OC.y);
+        nk_push_hits(P, lane, h0, h1, base);
         if (inb) {
-            *reinterpret_cast<double2*>(P.px + base) = make_double2(xs[0], xs[1]);
-            *reinterpret_cast<double2*>(P.py + base) = make_double2(ys[0], ys[1]);
-            *reinterpret_cast<double2*>(P.pz + base) = make_double2(zs[0], zs[1]);
-            *reinterpret_cast<double2*>(P.tc + base) = make_double2(tcs[0], tcs[1]);
-            *reinterpret_cast<double2*>(P.occ + base) = make_double2(ocs[0], ocs[1]);
+            *reinterpret_cast<double2*>(P.px + base) = X;
+            *reinterpret_cast<double2*>(P.py + base) = Y;
+            *reinterpret_cast<double2*>(P.pz + base) = Z;
+            *reinterpret_cast<double2*>(P.tc + base) = TC;
+            *reinterpret_cast<double2*>(P.occ + base) = OC;
         }
     }
     __syncthreads();
-    double* acc = P.acc;
-    for (int i = threadIdx.x; i < S; i += blockDim.x) {
-        if (binC[i]) {
-            atomicAdd(acc + NK_ACC_E(S, P.R) + i, binE[i]);
-            atomicAdd(acc + NK_ACC_CNT(S, P.R) + i, (double)binC[i]);
-            if (with_flux) {
-                atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i, binF[3 * i]);
-                atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i + 1, binF[3 * i + 1]);
-                atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i + 2, binF[3 * i + 2]);
+    nk_flush_bins<FLUX>(P, binE, binF, binC);
+}
+
+// ---- variant A1: one particle per thread, 64-bit accesses (fewer live registers -> more resident warps) ------
+#ifndef NK_STEP1_MIN_BLOCKS
+#define NK_STEP1_MIN_BLOCKS 5
+#endif
+template <bool HAS_ROUGH, bool FAST, bool RELAX, bool FLUX>
+__global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP1_MIN_BLOCKS) k_step1(NkP P) {
+    extern __shared__ double sm[];
+    NkSvSmem s = nk_load_sv(P, sm);
+    const int S = P.S;
+    double* binE = sm + nk_sv_smem_doubles(S);
+    double* binF = binE + S;
+    unsigned int* binC = reinterpret_cast<unsigned int*>(binF + 3 * S);
+    NkSvHot h = nk_load_hot(P, binC + S + (S & 1));
+    for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0.0; binC[i] = 0u; binF[3 * i] = 0.0; binF[3 * i + 1] = 0.0; binF[3 * i + 2] = 0.0; }
+    __syncthreads();
+    const long long n = P.dyn->n_slots;
+    const unsigned int lane = threadIdx.x & 31u;
+    for (long long wbase = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < n;
+         wbase += (long long)gridDim.x * blockDim.x) {
+        const long long i = wbase + lane;
+        bool hit = false;
+        if (i < n) {
+            const int md = P.mode[i];
+            if (md >= 0) {
+                const int om = HAS_ROUGH ? P.omode[i] : md;
+                double x = P.px[i], y = P.py[i], z = P.pz[i], tc = P.tc[i], occ = P.occ[i];
+                hit = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binC, md, om, x, y, z, tc, occ);
+                P.px[i] = x; P.py[i] = y; P.pz[i] = z; P.tc[i] = tc; P.occ[i] = occ;
+            }
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            unsigned int pos = 0;
+            if (lane == 0) pos = atomicAdd(&P.dyn->n_hits, __popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (hit) P.hitlist[pos + __popc(m & ((1u << lane) - 1u))] = (int)i;
+        }
+    }
+    __syncthreads();
+    nk_flush_bins<FLUX>(P, binE, binF, binC);
+}
+
+// ---- variant B: TMA bulk-copy pipeline -------------------------------------------------------------------------
+// The particle SoA is streamed through shared memory in tiles of NK_TILE slots by the bulk async-copy engine
+// (cp.async.bulk, SASS UBLKCP) with an mbarrier per stage: NK_STAGES tiles are in flight per block regardless
+// of register pressure, consumer warps read/write the tile in shared memory, and the updated tile goes back
+// with a bulk store.  Needs capacity % NK_TILE == 0 (slots past n_slots are dead: mode = -1).
+#define NK_TILE 512
+#define NK_STAGES 3
+__device__ __forceinline__ unsigned int nk_smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void nk_mbar_init(void* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nk_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void nk_mbar_expect_tx(void* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nk_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void nk_mbar_wait(void* bar, unsigned int parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "NK_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra NK_DONE_%=;\n\t"
+        "bra NK_WAIT_%=;\n\t"
+        "NK_DONE_%=:\n\t}" ::"r"(nk_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void nk_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned int bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(nk_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(nk_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void nk_bulk_s2g(void* dst_gmem, const void* src_smem, unsigned int bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(nk_smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+
+struct NkTileSmem {                         // one pipeline stage (24.5 KB)
+    double x[NK_TILE], y[NK_TILE], z[NK_TILE], tc[NK_TILE], occ[NK_TILE];
+    int mode[NK_TILE], omode[NK_TILE];
+};
+
+template <bool HAS_ROUGH, bool FAST, bool RELAX, bool FLUX>
+__global__ void __launch_bounds__(NK_STEP_THREADS, 2) k_step_tma(NkP P) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    NkTileSmem* stage = reinterpret_cast<NkTileSmem*>(smraw);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smraw + NK_STAGES * sizeof(NkTileSmem));
+    double* sm = reinterpret_cast<double*>(full + NK_STAGES + 1);
+    NkSvSmem s = nk_load_sv(P, sm);
+    const int S = P.S;
+    double* binE = sm + nk_sv_smem_doubles(S);
+    double* binF = binE + S;
+    unsigned int* binC = reinterpret_cast<unsigned int*>(binF + 3 * S);
+    NkSvHot h = nk_load_hot(P, binC + S + (S & 1));
+    for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0.0; binC[i] = 0u; binF[3 * i] = 0.0; binF[3 * i + 1] = 0.0; binF[3 * i + 2] = 0.0; }
+
+    const long long n = P.dyn->n_slots;
+    const long long n_tiles = (n + NK_TILE - 1) / NK_TILE;
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int tile_bytes = NK_TILE * (5 * 8 + (HAS_ROUGH ? 8 : 4));
+
+    auto issue_load = [&](int st, long long tile) {
+        NkTileSmem& T = stage[st];
+        const long long o = tile * NK_TILE;
+        nk_mbar_expect_tx(&full[st], tile_bytes);
+        nk_bulk_g2s(T.x, P.px + o, NK_TILE * 8, &full[st]);
+        nk_bulk_g2s(T.y, P.py + o, NK_TILE * 8, &full[st]);
+        nk_bulk_g2s(T.z, P.pz + o, NK_TILE * 8, &full[st]);
+        nk_bulk_g2s(T.tc, P.tc + o, NK_TILE * 8, &full[st]);
+        nk_bulk_g2s(T.occ, P.occ + o, NK_TILE * 8, &full[st]);
+        nk_bulk_g2s(T.mode, P.mode + o, NK_TILE * 4, &full[st]);
+        if (HAS_ROUGH) nk_bulk_g2s(T.omode, P.omode + o, NK_TILE * 4, &full[st]);
+    };
+
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < NK_STAGES; ++st) nk_mbar_init(&full[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < NK_STAGES; ++st) {
+            const long long tile = (long long)blockIdx.x + (long long)st * gridDim.x;
+            if (tile < n_tiles) issue_load(st, tile);
+        }
+    }
+
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int st = (int)(it % NK_STAGES);
+        const unsigned int parity = (unsigned int)((it / NK_STAGES) & 1);
+        nk_mbar_wait(&full[st], parity);
+        NkTileSmem& T = stage[st];
+        const int j = 2 * threadIdx.x;
+        double2 X = *reinterpret_cast<double2*>(T.x + j), Y = *reinterpret_cast<double2*>(T.y + j), Z = *reinterpret_cast<double2*>(T.z + j);
+        double2 TC = *reinterpret_cast<double2*>(T.tc + j), OC = *reinterpret_cast<double2*>(T.occ + j);
+        int2 MD = *reinterpret_cast<int2*>(T.mode + j), OM = MD;
+        if (HAS_ROUGH) OM = *reinterpret_cast<int2*>(T.omode + j);
+        const long long base = tile * NK_TILE + j;
+        bool h0 = false, h1 = false;
+        if (base < n && MD.x >= 0) h0 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binC, MD.x, OM.x, X.x, Y.x, Z.x, TC.x, OC.x);
+        if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binC, MD.y, OM.y, X.y, Y.y, Z.y, TC.y, OC.y);
+        nk_push_hits(P, lane, h0, h1, base);
+        *reinterpret_cast<double2*>(T.x + j) = X; *reinterpret_cast<double2*>(T.y + j) = Y; *reinterpret_cast<double2*>(T.z + j) = Z;
+        *reinterpret_cast<double2*>(T.tc + j) = TC; *reinterpret_cast<double2*>(T.occ + j) = OC;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the bulk store
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const long long o = tile * NK_TILE;
+            nk_bulk_s2g(P.px + o, T.x, NK_TILE * 8);
+            nk_bulk_s2g(P.py + o, T.y, NK_TILE * 8);
+            nk_bulk_s2g(P.pz + o, T.z, NK_TILE * 8);
+            nk_bulk_s2g(P.tc + o, T.tc, NK_TILE * 8);
+            nk_bulk_s2g(P.occ + o, T.occ, NK_TILE * 8);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the stage written back one iteration ago has been read by now: refill it
+            if (it >= 1) {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                const long long nt = tile + (long long)(NK_STAGES - 1) * gridDim.x;
+                if (nt < n_tiles) issue_load((int)((it - 1) % NK_STAGES), nt);
             }
         }
     }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncthreads();
+    nk_flush_bins<FLUX>(P, binE, binF, binC);
+}
+
+typedef void (*nk_step_fn)(NkP);
+template <int V, bool A, bool B, bool C, bool D>
+static nk_step_fn nk_pick5() {
+    return V == 1 ? (nk_step_fn)k_step_tma<A, B, C, D> : (V == 2 ? (nk_step_fn)k_step1<A, B, C, D> : (nk_step_fn)k_step<A, B, C, D>);
+}
+template <int V, bool A, bool B, bool C>
+static nk_step_fn nk_pick4(bool d) { return d ? nk_pick5<V, A, B, C, true>() : nk_pick5<V, A, B, C, false>(); }
+template <int V, bool A, bool B>
+static nk_step_fn nk_pick3(bool c, bool d) { return c ? nk_pick4<V, A, B, true>(d) : nk_pick4<V, A, B, false>(d); }
+template <int V, bool A>
+static nk_step_fn nk_pick2(bool b, bool c, bool d) { return b ? nk_pick3<V, A, true>(c, d) : nk_pick3<V, A, false>(c, d); }
+template <int V>
+static nk_step_fn nk_pick1(bool a, bool b, bool c, bool d) { return a ? nk_pick2<V, true>(b, c, d) : nk_pick2<V, false>(b, c, d); }
+static nk_step_fn nk_pick_step(int variant, bool rough, bool fast, bool relax, bool flux) {
+    return variant == 1 ? nk_pick1<1>(rough, fast, relax, flux) : (variant == 2 ? nk_pick1<2>(rough, fast, relax, flux) : nk_pick1<0>(rough, fast, relax, flux));
 }
 
 // ---- helpers shared by the rare-path kernels ------------------------------------------------------------
@@ -608,7 +840,11 @@ struct nk_ctx {
     std::vector<double> h_tau, h_Tg, h_mode;
     double hot_lo = 0, hot_hi = 0;
     int step_blocks = 0;
+    int step_blocks_variant = -1;
+    int step_variant = 0;
     bool profiling = false;
+    long long h_step = 0;          // host mirror of NkDyn::step
+    bool h_relax_pending = false;  // host mirror of NkDyn::relax_pending
     std::vector<cudaEvent_t> ev;   // 5 events per profiled step
     size_t ev_used = 0;
 };
@@ -673,6 +909,7 @@ int nk_create(int device, nk_ctx** out) {
     cudaGetDeviceProperties(&prop, device);
     ctx->n_sm = prop.multiProcessorCount;
     ctx->P.world = 1;
+    if (const char* e = getenv("NK_STEP_IMPL")) ctx->step_variant = !strcmp(e, "tma") ? 1 : (!strcmp(e, "ldg1") ? 2 : 0);
     NkDyn z; memset(&z, 0, sizeof(z));
     ctx->P.dyn = nk_upload<NkDyn>(ctx, &z, 1);
     *out = ctx;
@@ -765,6 +1002,7 @@ int nk_set_subvols(nk_ctx* ctx, int S, const double* centres, const double* volu
     NK_UP(dd, double, ax.data(), S); P.sv_axis = dd;
     NK_UP(dd, double, mid.data(), mid.size()); P.sv_mid = dd;
     P.sv_inv_dx = (S > 1 && ax[S - 1] != ax[0]) ? (S - 1) / (ax[S - 1] - ax[0]) : 0.0;
+    P.sv_x0 = (S > 1 && P.sv_inv_dx > 0) ? ax[0] - 0.5 / P.sv_inv_dx : 0.0;
     std::vector<double> T0(S, 0.0);
     NK_UP(P.T_sv, double, T0.data(), S);
     return 0;
@@ -968,6 +1206,7 @@ int nk_set_timestep(nk_ctx* ctx, int64_t k) {
     cudaSetDevice(ctx->device);
     NkDyn d; if (nk_read_dyn(ctx, &d)) return -1;
     d.step = k; d.relax_pending = 0;
+    ctx->h_step = k; ctx->h_relax_pending = false;
     return nk_write_dyn(ctx, &d);
 }
 int nk_get_timestep(nk_ctx* ctx, int64_t* k) {
@@ -1053,7 +1292,7 @@ int nk_init_collisions(nk_ctx* ctx) {
     return 0;
 }
 
-static size_t nk_step_smem(const NkP& P) { return (nk_sv_smem_doubles(P.S) + 4 * (size_t)P.S) * 8 + ((size_t)P.S + 2) * 4 + nk_hot_smem_bytes(P.S) + 16; }
+static size_t nk_step_smem(const NkP& P) { return (nk_sv_smem_doubles(P.S) + 4 * (size_t)P.S) * 8 + ((size_t)P.S + 2) * 4 + nk_hot_smem_bytes(P.S) + 32; }
 
 int nk_step_local(nk_ctx* ctx) {
     cudaSetDevice(ctx->device);
@@ -1061,13 +1300,24 @@ int nk_step_local(nk_ctx* ctx) {
     const NkP& P = ctx->P;
     size_t smem = nk_step_smem(P);
     const bool fast = P.is_slice && P.interp == NK_INTERP_NEAREST;
-    void (*kern)(NkP) = ctx->has_rough ? (fast ? k_step<true, true> : k_step<true, false>)
-                                       : (fast ? k_step<false, true> : k_step<false, false>);
-    if (!ctx->step_blocks) {
+    // the step counter and the relaxation flag are mirrored on the host (every mutation goes through this
+    // library), so the launch-uniform RELAX / FLUX variants can be chosen without a device read-back
+    const bool relax = ctx->h_relax_pending;
+    const bool flux = ((ctx->h_step + 1) % P.n_dt_to_conv) == 0;
+    int variant = ctx->step_variant;                          // 0: 2 particles/thread LDG.128, 1: TMA pipeline, 2: 1 particle/thread
+    if (variant == 1 && (P.cap % NK_TILE) != 0) variant = 0;
+    if (variant == 1) smem = NK_STAGES * sizeof(NkTileSmem) + (NK_STAGES + 1) * 8 + nk_step_smem(P);
+    nk_step_fn kern = nk_pick_step(variant, ctx->has_rough, fast, relax, flux);
+    if (!ctx->step_blocks || ctx->step_blocks_variant != variant) {
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NK_STEP_THREADS, smem);
+        for (int r = 0; r < 2; ++r) for (int f = 0; f < 2; ++f) {       // every variant may need the opt-in shared memory size
+            nk_step_fn k = nk_pick_step(variant, ctx->has_rough, fast, r, f);
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nk_pick_step(variant, ctx->has_rough, fast, true, true), NK_STEP_THREADS, smem);
         if (per_sm < 1) per_sm = 1;
         ctx->step_blocks = per_sm * ctx->n_sm;
+        ctx->step_blocks_variant = variant;
     }
     nk_prof_mark(ctx);
     kern<<<ctx->step_blocks, NK_STEP_THREADS, smem, ctx->stream>>>(P);
@@ -1092,6 +1342,7 @@ int nk_step_finalize(nk_ctx* ctx) {
     while (threads < P.S && threads < 1024) threads <<= 1;
     k_finalize<<<1, threads, 3 * (size_t)P.S * 8, ctx->stream>>>(P);
     NK_CK(cudaGetLastError());
+    ctx->h_step += 1; ctx->h_relax_pending = true;
     nk_prof_mark(ctx);
     return 0;
 }
@@ -1135,6 +1386,7 @@ int nk_flush_relaxation(nk_ctx* ctx) {
     NK_CK(cudaGetLastError());
     k_clear_relax<<<1, 1, 0, ctx->stream>>>(ctx->P);
     NK_CK(cudaGetLastError());
+    ctx->h_relax_pending = false;
     return 0;
 }
 

@@ -71,6 +71,7 @@ struct NkP {
     const double* sv_mid;             // (S-1) x/2+x/2 midpoints (scipy interp1d 'nearest')
     const double* sv_volume;
     double sv_inv_dx;                 // 1 / slice spacing (guess only; exactness comes from fix-up)
+    double sv_x0;                     // lower end of slice 0 on the slice axis (guess only)
     // ---- modes
     int Q, J, M, NT;
     const double* Tg;                 // (NT)

@@ -128,8 +128,8 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------
     def allocate(self, capacity):
-        cap = int(capacity) + (int(capacity) & 1)
-        cap = max(cap, 2)
+        cap = max(int(capacity), 2)
+        cap = (cap + 511) // 512 * 512          # whole 512-slot tiles: enables the TMA bulk-copy step kernel
         dev = self.device
         f = lambda: torch.zeros(cap, dtype=torch.float64, device=dev)
         i = lambda fill: torch.full((cap,), fill, dtype=torch.int32, device=dev)

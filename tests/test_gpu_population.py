@@ -1,0 +1,99 @@
+"""GPU tests of the reference-shaped Python surface: Geometry / Phonon / Population built from a
+parameters file, stepped with run_timestep, output files in the reference's formats, and a statistical
+comparison with the oracle (different random streams, so within stated error bars only)."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+import argument_parser as ap
+from oracle import gen_golden, nk_oracle as nko
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(text, folder):
+    text = text.replace("kappa-m313131.hdf5", "synthetic:5").replace("--mat_folder test_material/Si/", "--mat_folder /nonexistent/")
+    args = ap.initialise_parser(False).parse_args(text.split())
+    args.results_folder = str(folder)
+    return args
+
+
+def _population(text, folder, seed=3):
+    from nanokappa_b200.classes.Geometry import Geometry
+    from nanokappa_b200.classes.Phonon import Phonon
+    from nanokappa_b200.classes.Population import Population
+    args = _args(text, folder)
+    with contextlib.redirect_stdout(io.StringIO()):
+        geo = Geometry(args)
+        ph = Phonon(args, 0)
+        np.random.seed(seed)
+        pop = Population(args, geo, ph, device=0, seed=seed)
+    return args, geo, ph, pop
+
+
+def test_population_surface_and_files(tmp_path):
+    text = gen_golden.PARAMS_C1.format(eta=2, n=20000)
+    args, geo, ph, pop = _population(text, tmp_path)
+    n0 = pop.N_p
+    assert pop.positions.shape == (n0, 3) and pop.modes.shape == (n0, 2) and pop.occupation.shape == (n0,)
+    assert pop.group_vel.shape == (n0, 3) and pop.omega.shape == (n0,) and pop.n_timesteps.shape == (n0,)
+    assert set(np.unique(pop.collision_cond)) <= {"T", "P", "R"}
+    assert np.array_equal(np.bincount(pop.subvol_id, minlength=10), pop.subvol_N_p)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(120):
+            pop.run_timestep(geo, ph)
+        pop.write_final_state(geo)
+    assert pop.current_timestep == 120 and abs(pop.N_p - n0) < 0.05 * n0
+    # convergence.txt: header + row 0 + one row per 10 steps, parsed positionally like the reference does
+    pop.view.read_convergence()
+    v = pop.view
+    assert v.timestep.tolist() == list(range(0, 121, 10))
+    assert v.T.shape == (13, 10) and v.sv_phi.shape == (13, 30) and v.sv_k.shape == (13, 10) and v.en_res.shape == (13, 2)
+    assert np.allclose(v.T[0], 298.0) and v.T[-1, 0] > v.T[-1, -1] > 297.9            # hot side warms up first
+    assert (v.N_p > 0).all() and np.isfinite(v.k[1:]).all()
+    # particle_data.txt round trip (--part_dist restart file format)
+    data = np.loadtxt(os.path.join(tmp_path, "particle_data.txt"), delimiter=",", comments="#")
+    assert data.shape == (pop.N_p, 6)
+    assert np.allclose(data[:, 2:5], pop.positions, atol=1e-3) and np.array_equal(data[:, :2].astype(int), pop.modes)
+    assert os.path.isfile(os.path.join(tmp_path, "residue.txt")) and os.path.isfile(os.path.join(tmp_path, "subvolumes.txt"))
+
+
+def test_restart_from_particle_file(tmp_path):
+    text = gen_golden.PARAMS_C2.format(n=8000)
+    a = tmp_path / "a"; b = tmp_path / "b"; a.mkdir(); b.mkdir()
+    args, geo, ph, pop = _population(text, a)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(30):
+            pop.run_timestep(geo, ph)
+        pop.write_final_state(geo)
+    T_before = pop.subvol_temperature.copy()
+    text2 = text.replace("--part_dist random_subvol", "--part_dist " + os.path.join(a, "particle_data.txt"))
+    args2, geo2, ph2, pop2 = _population(text2, b)
+    assert pop2.N_p == pop.N_p
+    assert np.allclose(pop2.subvol_temperature, T_before, atol=0.05)      # positions are stored to 1e-3 A, occupation to 7 digits
+
+
+def test_statistical_agreement_with_oracle(tmp_path):
+    """Same physical case, independent random streams: after 150 steps the subvolume temperature
+    profiles must agree within the Monte-Carlo noise (sigma_T ~ 0.02 K for 3e4 particles in 10 slices;
+    band = 0.12 K), the particle count within 1 %, and the mean heat flux within 25 %."""
+    text = gen_golden.PARAMS_C1.format(eta=5, n=30000)
+    args, geo, ph, pop = _population(text, tmp_path, seed=11)
+    tb = pop.tables
+    p = pop._particles()
+    st = nko.make_state(tb, p["positions"], p["modes"], np.full(10, 298.0), pop.res_counter, ids=p["ids"])
+    rng = nko.KeyedRNG(987)
+    flux_o, flux_g = [], []
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+        for k in range(150):
+            nko.run_timestep(tb, st, rng, on_convergence=lambda s: flux_o.append(s.subvol_heat_flux[:, 0].copy()))
+            pop.run_timestep(geo, ph)
+            if pop.current_timestep % 10 == 0:
+                flux_g.append(pop.subvol_heat_flux[:, 0].copy())
+    assert abs(pop.N_p - st.N_p) < 0.01 * st.N_p
+    assert np.abs(pop.subvol_temperature - st.subvol_temperature).max() < 0.12
+    fo, fg = np.mean(flux_o[5:], axis=0)[:3].mean(), np.mean(flux_g[5:], axis=0)[:3].mean()
+    assert fo > 0 and abs(fg - fo) < 0.25 * fo
