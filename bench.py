@@ -72,29 +72,78 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons DURING the timed region, polled every few ms through NVML
+    (nvidia-ml-py); falls back to `nvidia-smi -lms` when NVML is not importable."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index = index
+        self.samples = []          # (sm_mhz, power_w, reasons_bitmask)
+        self.sm_max = None
+        self.stop_flag = False
+        self.thread = None
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.nv = None
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                              "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=self._read, daemon=True)
+                self.thread.start()
+            except Exception:
+                self.proc = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(sm), pw, int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self):
+        self.stop_flag = True
+        if self.nv is not None:
+            if self.thread is not None:
+                self.thread.join(timeout=1)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"]}
+            nv = self.nv
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            mask = 0
+            for _, _, r in self.samples:
+                mask |= r
+            return {"sm_mhz": float(np.median([x[0] for x in self.samples])), "sm_max_mhz": self.sm_max,
+                    "power_w_max": float(max(x[1] for x in self.samples)), "samples": len(self.samples),
+                    "reasons": sorted(k for k, v in names.items() if mask & v)}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -289,8 +338,14 @@ def gpu_arm(a):
     peak, peak_src = load_peaks()
     step_ms = prof["k_step"] / max(nprof, 1)
     achieved = BYTES_PER_UPDATE * alive_local / (step_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "kstep_traffic.json")
+    if os.path.isfile(tpath):
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_per_update"] * alive_local          # ncu-measured DRAM bytes per update x this launch's updates
+        traffic_src = tj["source"]
     roofline = {"bound": "hbm", "kernel": "k_step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "bytes_per_update": BYTES_PER_UPDATE, "updates_per_launch": int(alive_local),
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": BYTES_PER_UPDATE * alive_local, "peak_source": peak_src, "bytes_per_update": BYTES_PER_UPDATE, "updates_per_launch": int(alive_local),
                 "avg_launch_ms": step_ms,
                 "kernel_share_of_step": {k: v / max(sum(prof.values()), 1e-12) for k, v in prof.items()}}
 
@@ -316,7 +371,7 @@ def gpu_arm(a):
             "metric": "particle-timestep updates/s", "value": value, "unit": "updates/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(a, n, "gpu"),
-            "clocks": clocks, "gpu_launches": int(4 * a.steps),
+            "clocks": clocks, "gpu_launches": int((2 if world == 1 else 3) * a.steps),
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                     "timesteps_per_call": 1, "calls": e2e["calls"], "api": e2e["api"]},
             "roofline": roofline, "cpu_baseline": cpu,

@@ -208,23 +208,30 @@ struct NkParticle {
 // roughness_boundary_condition :1491-1544 / select_reflected_modes :941-988 /
 // pick_diffuse_modes :990-1015), executed as a sequence of events.  `acc` receives the reservoir
 // statistics (:1585-1602).  Returns with p.alive == false when the particle was absorbed.
-__device__ __noinline__ void nk_boundary_events(const NkP& P, NkParticle& p, long long step, double* acc) {
-    const NkFace* faces = P.faces;
+// geometry tables the event loop reads; the pointers go to shared-memory copies when the mesh is small
+struct NkGeo {
+    const NkFace* faces;
+    const int* bc; const int* partner; const int* res; const int* rough;
+    const double* normal; const double* centroid;
+};
+
+__device__ __forceinline__ void nk_boundary_events(const NkP& P, const NkGeo& G, NkParticle& p, long long step, double* acc) {
+    const NkFace* faces = G.faces;
     double done = 0.0;
     double ts = p.tc;
     unsigned int ev = 0;
     const double dt = P.dt;
     for (int it = 0; it < 4096; ++it) {
         int cfi = p.cf < 0 ? P.nf - 1 : p.cf;                    // bound_cond[-1] for escaped rays (:667, :1487)
-        int cond = P.facet_bc[cfi];
+        int cond = G.bc[cfi];
         double rem = nk_sub(1.0, done);
         if (rem > ts) {
             if (cond == NK_BC_T || cond == NK_BC_F) {
                 // I. absorbed by a reservoir (:1565-1608)
-                int r = P.facet_res[cfi];
+                int r = G.res[cfi];
                 if (r >= 0) {
                     double e = nk_mul(nk_mul(P.hbar, p.omega), nk_sub(p.occ, nk_bose(P, P.res_T[r], p.omega)));
-                    const double* n = P.facet_normal + 3 * cfi;
+                    const double* n = G.normal + 3 * cfi;
                     double vn = dot3(p.vx, p.vy, p.vz, n[0], n[1], n[2]);
                     atomicAdd(acc + NK_ACC_NLEAVE(P.S, P.R) + r, 1.0);
                     atomicAdd(acc + NK_ACC_EBAL(P.S, P.R) + r, -e);
@@ -241,9 +248,9 @@ __device__ __noinline__ void nk_boundary_events(const NkP& P, NkParticle& p, lon
             double dist = norm3(nk_sub(p.cx, qx), nk_sub(p.cy, qy), nk_sub(p.cz, qz));
             if (cond == NK_BC_P) {
                 // II. periodic wrap (:1463-1489)
-                int g = p.cf >= 0 ? P.facet_partner[p.cf] : -1;
+                int g = p.cf >= 0 ? G.partner[p.cf] : -1;
                 if (g < 0) { P.dyn->error |= NK_ERR_EVENTS; break; }
-                const double* cg = P.facet_centroid + 3 * g; const double* ch = P.facet_centroid + 3 * p.cf;
+                const double* cg = G.centroid + 3 * g; const double* ch = G.centroid + 3 * p.cf;
                 double nx = nk_add(p.cx, nk_sub(cg[0], ch[0])), ny = nk_add(p.cy, nk_sub(cg[1], ch[1])), nz = nk_add(p.cz, nk_sub(cg[2], ch[2]));
                 done = nk_add(done, nk_div(dist, norm3(nk_mul(p.vx, dt), nk_mul(p.vy, dt), nk_mul(p.vz, dt))));
                 p.x = nx; p.y = ny; p.z = nz;
@@ -254,7 +261,7 @@ __device__ __noinline__ void nk_boundary_events(const NkP& P, NkParticle& p, lon
                 // III. rough facet: specular or diffuse (:1491-1544, :941-1015)
                 done = nk_add(done, nk_div(dist, nk_mul(norm3(p.vx, p.vy, p.vz), dt)));
                 p.x = p.cx; p.y = p.cy; p.z = p.cz;
-                int fr = P.facet_rough[cfi];
+                int fr = G.rough[cfi];
                 double u_dice, u_pick;
                 nk_uniforms(P, p.id, step, NK_STREAM_ROUGH0 + ev, u_dice, u_pick);
                 ++ev;

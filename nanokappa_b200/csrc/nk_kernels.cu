@@ -284,11 +284,60 @@ __device__ __forceinline__ double nk_relax_particle(const NkP& P, const NkSvSmem
     return tau > 0.0 ? relaxed : be0;
 }
 
+// Reservoir counters (Population.fill_reservoirs 'constant', Population.py:358-370): every entry of the
+// (R, Q*J) table advances its fractional counter; entries that emit this step are appended to the
+// emission list that k_rare consumes.  Runs as the prologue of the streaming kernel (grid-stride over all
+// its blocks): it does not depend on the particles at all.
+__device__ __forceinline__ void nk_emit_scan(const NkP& P) {
+    const int mspan = P.emit_m_hi - P.emit_m_lo;
+    const long long total = (long long)P.R * mspan;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / mspan);
+        const int m = P.emit_m_lo + (int)(e % mspan);
+        const size_t idx = (size_t)r * P.M + m;
+        const double prob = P.enter_prob[idx];
+        const double fixed = floor(prob);
+        double cnt = nk_add(P.res_counter[idx], nk_sub(prob, fixed));
+        const int extra = cnt >= 1.0 ? 1 : 0;
+        cnt = nk_sub(cnt, (double)extra);
+        P.res_counter[idx] = cnt;
+        int n_new = (int)fixed + extra;
+        if (n_new == 0) continue;
+        if (n_new > NK_EMIT_CMAX) { atomicOr(&P.dyn->error, NK_ERR_CMAX); n_new = NK_EMIT_CMAX; }
+        const unsigned int k = atomicAdd(&P.dyn->n_emit, 1u);
+        P.emitlist[k] = make_int2((r << 8) | n_new, m);
+    }
+}
+
+// Block-private per-subvolume sums.  On sm_100 shared-memory atomicAdd is native only for 32-bit integers
+// (ATOMS.ADD / ATOMS.POPC.INC); the f64 and the 64-bit integer versions are compare-and-swap loops
+// (ATOMS.CAST.SPIN.64) and were a quarter of the kernel's stall samples.  Terms are therefore accumulated
+// in 64-bit FIXED POINT built from two native 32-bit adds: the low word's returned old value tells this
+// add whether it wrapped, and the carry rides on the high word's add (two's complement, so signed terms
+// just work, and the result does not depend on the order of the adds).  Quantum: 2^-46 eV for energies
+// (1.4e-14 eV, the size of the f64 rounding noise of the reference's own sum), 2^-30 for flux terms.  A
+// term outside the fixed-point range (|q| >= 2^40; never for physical occupations) or non-finite goes to
+// an f64 side bin.  A block adds at most a few million terms: |sum| < 2^62.
+#define NK_QE 70368744177664.0          // 2^46
+#define NK_QF 1073741824.0              // 2^30
+__device__ __forceinline__ void nk_bin_add(long long* q, double* side, double v, double scale) {
+    const double t = v * scale;
+    if (fabs(t) < 1099511627776.0) {
+        const long long i = __double2ll_rn(t);
+        const unsigned int lo = (unsigned int)i, hi = (unsigned int)(i >> 32);
+        unsigned int* w = reinterpret_cast<unsigned int*>(q);            // little endian: w[0] low, w[1] high
+        const unsigned int old = atomicAdd(w, lo);
+        atomicAdd(w + 1, hi + ((old + lo) < old ? 1u : 0u));
+    } else {
+        atomicAdd(side, v);
+    }
+}
+
 // one live particle: deferred relaxation -> drift -> (if no collision this step) subvolume + energy bins.
 // Returns true when the particle's collision falls inside this step (it then goes to the hit list).
 template <bool HAS_ROUGH, bool FAST, bool RELAX, bool FLUX>
-__device__ __forceinline__ bool nk_step_particle(const NkP& P, const NkSvSmem& s, const NkSvHot& h, double* binE, double* binF,
-                                                 unsigned int* binC, int md, int om, double& x, double& y, double& z,
+__device__ __forceinline__ bool nk_step_particle(const NkP& P, const NkSvSmem& s, const NkSvHot& h, long long* binE, long long* binF,
+                                                 double* binX, unsigned int* binC, int md, int om, double& x, double& y, double& z,
                                                  double& tc, double& occ) {
     const NkModeHot* __restrict__ mhot = P.mhot;
     double4 ma, mt;
@@ -317,12 +366,12 @@ __device__ __forceinline__ bool nk_step_particle(const NkP& P, const NkSvSmem& s
     double be1 = be0;
     if (!(FAST && RELAX && sv == g0)) be1 = nk_bose_fast(a, omega, h.invb[sv]);
     const double e = a * (occ - be1);
-    atomicAdd(binE + sv, e);
+    nk_bin_add(binE + sv, binX + sv, e, NK_QE);
     atomicAdd(binC + sv, 1u);
     if (FLUX) {
-        atomicAdd(binF + 3 * sv, ma.y * e);
-        atomicAdd(binF + 3 * sv + 1, ma.z * e);
-        atomicAdd(binF + 3 * sv + 2, ma.w * e);
+        nk_bin_add(binF + 3 * sv, binX + P.S + 3 * sv, ma.y * e, NK_QF);
+        nk_bin_add(binF + 3 * sv + 1, binX + P.S + 3 * sv + 1, ma.z * e, NK_QF);
+        nk_bin_add(binF + 3 * sv + 2, binX + P.S + 3 * sv + 2, ma.w * e, NK_QF);
     }
     return false;
 }
@@ -342,17 +391,17 @@ __device__ __forceinline__ void nk_push_hits(const NkP& P, unsigned int lane, bo
 }
 
 template <bool FLUX>
-__device__ __forceinline__ void nk_flush_bins(const NkP& P, const double* binE, const double* binF, const unsigned int* binC) {
+__device__ __forceinline__ void nk_flush_bins(const NkP& P, const long long* binE, const long long* binF, const double* binX,
+                                              const unsigned int* binC) {
     const int S = P.S;
     double* acc = P.acc;
     for (int i = threadIdx.x; i < S; i += blockDim.x) {
         if (binC[i]) {
-            atomicAdd(acc + NK_ACC_E(S, P.R) + i, binE[i]);
+            atomicAdd(acc + NK_ACC_E(S, P.R) + i, (double)binE[i] * (1.0 / NK_QE) + binX[i]);
             atomicAdd(acc + NK_ACC_CNT(S, P.R) + i, (double)binC[i]);
             if (FLUX) {
-                atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i, binF[3 * i]);
-                atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i + 1, binF[3 * i + 1]);
-                atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i + 2, binF[3 * i + 2]);
+                for (int k = 0; k < 3; ++k)
+                    atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i + k, (double)binF[3 * i + k] * (1.0 / NK_QF) + binX[S + 3 * i + k]);
             }
         }
     }
@@ -364,13 +413,15 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step(Nk
     extern __shared__ double sm[];
     NkSvSmem s = nk_load_sv(P, sm);
     const int S = P.S;
-    double* binE = sm + nk_sv_smem_doubles(S);             // S
-    double* binF = binE + S;                               // 3S
-    unsigned int* binC = reinterpret_cast<unsigned int*>(binF + 3 * S);   // S (+ pad to 8 B)
+    long long* binE = reinterpret_cast<long long*>(sm + nk_sv_smem_doubles(S));   // S   fixed-point energy sums
+    long long* binF = binE + S;                                                      // 3S  fixed-point flux sums
+    double* binX = reinterpret_cast<double*>(binF + 3 * S);                         // 4S  f64 side bins
+    unsigned int* binC = reinterpret_cast<unsigned int*>(binX + 4 * S);             // S (+ pad to 8 B)
     NkSvHot h = nk_load_hot(P, binC + S + (S & 1));
-    for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0.0; binC[i] = 0u; binF[3 * i] = 0.0; binF[3 * i + 1] = 0.0; binF[3 * i + 2] = 0.0; }
+    for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0; binC[i] = 0u; for (int k = 0; k < 3; ++k) binF[3 * i + k] = 0; for (int k = 0; k < 4; ++k) binX[4 * i + k] = 0.0; }
     __syncthreads();
 
+    nk_emit_scan(P);
     const long long n = P.dyn->n_slots;
     const unsigned int lane = threadIdx.x & 31u;
 
@@ -393,8 +444,8 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step(Nk
             if (HAS_ROUGH) OM = *reinterpret_cast<const int2*>(P.omode + base);
         }
         bool h0 = false, h1 = false;
-        if (base < n && MD.x >= 0) h0 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binC, MD.x, OM.x, X.x, Y.x, Z.x, TC.x, OC.x);
-        if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binC, MD.y, OM.y, X.y, Y.y, Z.y, TC.y, OC.y);
+        if (base < n && MD.x >= 0) h0 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.x, OM.x, X.x, Y.x, Z.x, TC.x, OC.x);
+        if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.y, OM.y, X.y, Y.y, Z.y, TC.y, OC.y);
         nk_push_hits(P, lane, h0, h1, base);
         if (inb) {
             *reinterpret_cast<double2*>(P.px + base) = X;
@@ -405,7 +456,7 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step(Nk
         }
     }
     __syncthreads();
-    nk_flush_bins<FLUX>(P, binE, binF, binC);
+    nk_flush_bins<FLUX>(P, binE, binF, binX, binC);
 }
 
 // ---- variant A1: one particle per thread, 64-bit accesses (fewer live registers -> more resident warps) ------
@@ -417,12 +468,14 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP1_MIN_BLOCKS) k_step1(
     extern __shared__ double sm[];
     NkSvSmem s = nk_load_sv(P, sm);
     const int S = P.S;
-    double* binE = sm + nk_sv_smem_doubles(S);
-    double* binF = binE + S;
-    unsigned int* binC = reinterpret_cast<unsigned int*>(binF + 3 * S);
+    long long* binE = reinterpret_cast<long long*>(sm + nk_sv_smem_doubles(S));
+    long long* binF = binE + S;
+    double* binX = reinterpret_cast<double*>(binF + 3 * S);
+    unsigned int* binC = reinterpret_cast<unsigned int*>(binX + 4 * S);
     NkSvHot h = nk_load_hot(P, binC + S + (S & 1));
-    for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0.0; binC[i] = 0u; binF[3 * i] = 0.0; binF[3 * i + 1] = 0.0; binF[3 * i + 2] = 0.0; }
+    for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0; binC[i] = 0u; for (int k = 0; k < 3; ++k) binF[3 * i + k] = 0; for (int k = 0; k < 4; ++k) binX[4 * i + k] = 0.0; }
     __syncthreads();
+    nk_emit_scan(P);
     const long long n = P.dyn->n_slots;
     const unsigned int lane = threadIdx.x & 31u;
     for (long long wbase = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < n;
@@ -434,7 +487,7 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP1_MIN_BLOCKS) k_step1(
             if (md >= 0) {
                 const int om = HAS_ROUGH ? P.omode[i] : md;
                 double x = P.px[i], y = P.py[i], z = P.pz[i], tc = P.tc[i], occ = P.occ[i];
-                hit = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binC, md, om, x, y, z, tc, occ);
+                hit = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, md, om, x, y, z, tc, occ);
                 P.px[i] = x; P.py[i] = y; P.pz[i] = z; P.tc[i] = tc; P.occ[i] = occ;
             }
         }
@@ -447,7 +500,7 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP1_MIN_BLOCKS) k_step1(
         }
     }
     __syncthreads();
-    nk_flush_bins<FLUX>(P, binE, binF, binC);
+    nk_flush_bins<FLUX>(P, binE, binF, binX, binC);
 }
 
 // ---- variant B: TMA bulk-copy pipeline -------------------------------------------------------------------------
@@ -494,12 +547,14 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, 2) k_step_tma(NkP P) {
     double* sm = reinterpret_cast<double*>(full + NK_STAGES + 1);
     NkSvSmem s = nk_load_sv(P, sm);
     const int S = P.S;
-    double* binE = sm + nk_sv_smem_doubles(S);
-    double* binF = binE + S;
-    unsigned int* binC = reinterpret_cast<unsigned int*>(binF + 3 * S);
+    long long* binE = reinterpret_cast<long long*>(sm + nk_sv_smem_doubles(S));
+    long long* binF = binE + S;
+    double* binX = reinterpret_cast<double*>(binF + 3 * S);
+    unsigned int* binC = reinterpret_cast<unsigned int*>(binX + 4 * S);
     NkSvHot h = nk_load_hot(P, binC + S + (S & 1));
-    for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0.0; binC[i] = 0u; binF[3 * i] = 0.0; binF[3 * i + 1] = 0.0; binF[3 * i + 2] = 0.0; }
+    for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0; binC[i] = 0u; for (int k = 0; k < 3; ++k) binF[3 * i + k] = 0; for (int k = 0; k < 4; ++k) binX[4 * i + k] = 0.0; }
 
+    nk_emit_scan(P);
     const long long n = P.dyn->n_slots;
     const long long n_tiles = (n + NK_TILE - 1) / NK_TILE;
     const unsigned int lane = threadIdx.x & 31u;
@@ -544,8 +599,8 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, 2) k_step_tma(NkP P) {
         if (HAS_ROUGH) OM = *reinterpret_cast<int2*>(T.omode + j);
         const long long base = tile * NK_TILE + j;
         bool h0 = false, h1 = false;
-        if (base < n && MD.x >= 0) h0 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binC, MD.x, OM.x, X.x, Y.x, Z.x, TC.x, OC.x);
-        if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binC, MD.y, OM.y, X.y, Y.y, Z.y, TC.y, OC.y);
+        if (base < n && MD.x >= 0) h0 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.x, OM.x, X.x, Y.x, Z.x, TC.x, OC.x);
+        if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.y, OM.y, X.y, Y.y, Z.y, TC.y, OC.y);
         nk_push_hits(P, lane, h0, h1, base);
         *reinterpret_cast<double2*>(T.x + j) = X; *reinterpret_cast<double2*>(T.y + j) = Y; *reinterpret_cast<double2*>(T.z + j) = Z;
         *reinterpret_cast<double2*>(T.tc + j) = TC; *reinterpret_cast<double2*>(T.occ + j) = OC;
@@ -569,7 +624,7 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, 2) k_step_tma(NkP P) {
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncthreads();
-    nk_flush_bins<FLUX>(P, binE, binF, binC);
+    nk_flush_bins<FLUX>(P, binE, binF, binX, binC);
 }
 
 typedef void (*nk_step_fn)(NkP);
@@ -589,133 +644,115 @@ static nk_step_fn nk_pick_step(int variant, bool rough, bool fast, bool relax, b
     return variant == 1 ? nk_pick1<1>(rough, fast, relax, flux) : (variant == 2 ? nk_pick1<2>(rough, fast, relax, flux) : nk_pick1<0>(rough, fast, relax, flux));
 }
 
-// ---- helpers shared by the rare-path kernels ------------------------------------------------------------
+// ---- helpers shared by the rare-path code ------------------------------------------------------------------
 __device__ __forceinline__ void nk_store_particle(const NkP& P, long long i, const NkParticle& p) {
     P.px[i] = p.x; P.py[i] = p.y; P.pz[i] = p.z; P.tc[i] = p.tc; P.occ[i] = p.occ;
     P.mode[i] = p.mode; P.omode[i] = p.omode; P.cfacet[i] = p.cf; P.cx[i] = p.cx; P.cy[i] = p.cy; P.cz[i] = p.cz;
 }
-// refresh_temperatures contribution of one particle handled outside k_step
-__device__ __forceinline__ void nk_accumulate_global(const NkP& P, const NkParticle& p, bool with_flux) {
+// refresh_temperatures contribution of one particle handled outside k_step; `acc` is the block-private
+// (shared memory) copy of the accumulator vector
+__device__ __forceinline__ void nk_accumulate(const NkP& P, double* acc, const NkParticle& p, bool with_flux) {
     int sv = nk_classify(P, P.svc, P.sv_mid, p.x, p.y, p.z);
     double e = nk_mul(nk_mul(P.hbar, p.omega), nk_sub(p.occ, nk_bose(P, P.T_sv[sv], p.omega)));
-    atomicAdd(P.acc + NK_ACC_E(P.S, P.R) + sv, e);
-    atomicAdd(P.acc + NK_ACC_CNT(P.S, P.R) + sv, 1.0);
+    atomicAdd(acc + NK_ACC_E(P.S, P.R) + sv, e);
+    atomicAdd(acc + NK_ACC_CNT(P.S, P.R) + sv, 1.0);
     if (with_flux) {
-        atomicAdd(P.acc + NK_ACC_FLUX(P.S, P.R) + 3 * sv, nk_mul(p.vx, e));
-        atomicAdd(P.acc + NK_ACC_FLUX(P.S, P.R) + 3 * sv + 1, nk_mul(p.vy, e));
-        atomicAdd(P.acc + NK_ACC_FLUX(P.S, P.R) + 3 * sv + 2, nk_mul(p.vz, e));
+        atomicAdd(acc + NK_ACC_FLUX(P.S, P.R) + 3 * sv, nk_mul(p.vx, e));
+        atomicAdd(acc + NK_ACC_FLUX(P.S, P.R) + 3 * sv + 1, nk_mul(p.vy, e));
+        atomicAdd(acc + NK_ACC_FLUX(P.S, P.R) + 3 * sv + 2, nk_mul(p.vz, e));
     }
 }
-__device__ __forceinline__ void nk_kill(const NkP& P, long long i) {
+
+// Free slots live in a ring: absorbed particles push at `fr_tail`, emission pops at `fr_head` but only
+// entries pushed in EARLIER steps (below `fr_snap`, advanced by the finalize), so that pushes and pops
+// of the same launch never touch the same entry.
+__device__ __forceinline__ void nk_kill(const NkP& P, double* acc, long long i) {
     P.mode[i] = -1;
-    long long k = atomicAdd((unsigned long long*)&P.dyn->n_free, 1ull);
-    P.freelist[k] = (int)i;
-    atomicAdd((unsigned long long*)&P.dyn->n_alive, (unsigned long long)(-1LL));
-    atomicAdd(P.acc + NK_ACC_NABS(P.S, P.R), 1.0);
+    unsigned long long k = atomicAdd((unsigned long long*)&P.dyn->fr_tail, 1ull);
+    P.freelist[k % (unsigned long long)P.cap] = (int)i;
+    atomicAdd(acc + NK_ACC_NABS(P.S, P.R), 1.0);
+}
+__device__ __forceinline__ long long nk_take_slot(const NkP& P) {
+    long long old = (long long)atomicAdd((unsigned long long*)&P.dyn->fr_head, 1ull);
+    if (old < P.dyn->fr_snap) return P.freelist[old % P.cap];
+    atomicAdd((unsigned long long*)&P.dyn->fr_head, (unsigned long long)(-1LL));       // nothing recyclable: append
+    long long slot = (long long)atomicAdd((unsigned long long*)&P.dyn->n_slots, 1ull);
+    if (slot >= P.cap) {
+        atomicAdd((unsigned long long*)&P.dyn->n_slots, (unsigned long long)(-1LL));
+        atomicOr(&P.dyn->error, NK_ERR_CAPACITY);
+        return -1;
+    }
+    return slot;
 }
 
-// ---- boundary events of the hit list ----------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_boundary(NkP P) {
-    const unsigned int nh = P.dyn->n_hits;
-    const long long step = P.dyn->step;
-    const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
-    for (unsigned int h = blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += gridDim.x * blockDim.x) {
-        long long i = P.hitlist[h];
+// One emission-list entry: n_new copies of mode m entering through reservoir r (Population.py:385-406,
+// :491-508, add_reservoir_particles :525-552, Mesh.sample_surface Mesh.py:923-951).
+__device__ __forceinline__ void nk_emit_entry(const NkP& P, const NkGeo& G, double* acc, int r, int m, int n_new, long long step, bool with_flux) {
+    const NkFace* faces = G.faces;
+    const double dt = P.dt;
+    const size_t idx = (size_t)r * P.M + m;
+    const double prob = P.enter_prob[idx];
+    const double cnt = P.res_counter[idx];                 // value after this step's update
+    const NkMode mp = P.mprop[m];
+    for (int c = n_new; c >= 1; --c) {
         NkParticle p;
-        p.x = P.px[i]; p.y = P.py[i]; p.z = P.pz[i]; p.tc = P.tc[i]; p.occ = P.occ[i];
-        p.mode = P.mode[i]; p.omode = P.omode[i];
-        NkMode m = P.mprop[p.mode];
-        p.vx = m.vx; p.vy = m.vy; p.vz = m.vz;
-        p.omega = (p.omode == p.mode) ? m.omega : P.mprop[p.omode].omega;
-        p.cf = P.cfacet[i]; p.cx = P.cx[i]; p.cy = P.cy[i]; p.cz = P.cz[i];
-        p.id = P.pid[i]; p.alive = true;
-        nk_boundary_events(P, p, step, P.acc);
-        if (p.alive) {
-            nk_store_particle(P, i, p);
-            nk_accumulate_global(P, p, with_flux);
-        } else {
-            nk_kill(P, i);
-        }
+        p.id = NK_EMIT_ID_BASE + (((step * P.R + r) * (long long)P.M + m) * NK_EMIT_CMAX + (c - 1));
+        double ua, uface, us, ur;
+        nk_uniforms(P, p.id, step, NK_STREAM_EMIT_A, ua, uface);
+        nk_uniforms(P, p.id, step, NK_STREAM_EMIT_B, us, ur);
+        const double dt_in = (c == 1) ? nk_mul(dt, nk_sub(1.0, nk_div(cnt, prob)))
+                                      : nk_mul(dt, nk_sub(1.0, nk_div(nk_add((double)(c - 1), ua), prob)));
+        // face ~ area: searchsorted(cdf, u, side='right') as np.random.choice does
+        const int f0 = P.res_face_ptr[r], f1 = P.res_face_ptr[r + 1];
+        int lo = f0, hi = f1;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (P.res_face_cdf[mid] <= uface) lo = mid + 1; else hi = mid; }
+        const int face = P.res_faces[min(lo, f1 - 1)];
+        const double* V = P.face_vertices + 9 * (size_t)face;
+        const double rs = sqrt(us);
+        const double a0 = nk_sub(1.0, rs), a1 = nk_mul(nk_sub(1.0, ur), rs), a2 = nk_mul(ur, rs);
+        const double x0 = nk_add(nk_add(nk_mul(a0, V[0]), nk_mul(a1, V[3])), nk_mul(a2, V[6]));
+        const double y0 = nk_add(nk_add(nk_mul(a0, V[1]), nk_mul(a1, V[4])), nk_mul(a2, V[7]));
+        const double z0 = nk_add(nk_add(nk_mul(a0, V[2]), nk_mul(a1, V[5])), nk_mul(a2, V[8]));
+        p.mode = m; p.omode = m; p.omega = mp.omega; p.vx = mp.vx; p.vy = mp.vy; p.vz = mp.vz;
+        double t;
+        nk_find_boundary_1(P, faces, x0, y0, z0, p.vx, p.vy, p.vz, p.cx, p.cy, p.cz, t, p.cf);
+        p.tc = nk_sub(nk_div(t, dt), nk_div(dt_in, dt));
+        p.x = nk_add(x0, nk_mul(p.vx, dt_in)); p.y = nk_add(y0, nk_mul(p.vy, dt_in)); p.z = nk_add(z0, nk_mul(p.vz, dt_in));
+        p.occ = nk_bose(P, P.res_T[r], p.omega);
+        p.alive = true;
+        atomicAdd(acc + NK_ACC_NEMIT(P.S, P.R), 1.0);
+        if (p.tc < 0.0) nk_boundary_events(P, G, p, step, acc);
+        if (!p.alive) { atomicAdd(acc + NK_ACC_NABS(P.S, P.R), 1.0); continue; }   // crossed the whole domain within the step
+        const long long slot = nk_take_slot(P);
+        if (slot < 0) continue;
+        nk_store_particle(P, slot, p);
+        P.pid[slot] = p.id;
+        nk_accumulate(P, acc, p, with_flux);
     }
 }
 
-// ---- reservoir emission (Population.fill_reservoirs 'constant' :356-406, :491-508 and
-//      add_reservoir_particles :525-552; Mesh.sample_surface Mesh.py:923-951) ---------------------------------
-__global__ void __launch_bounds__(128) k_emit(NkP P) {
-    const long long step = P.dyn->step;
-    const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
-    const int mspan = P.emit_m_hi - P.emit_m_lo;
-    const long long total = (long long)P.R * mspan;
-    const double dt = P.dt;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        int r = (int)(e / mspan);
-        int m = P.emit_m_lo + (int)(e % mspan);
-        size_t idx = (size_t)r * P.M + m;
-        double prob = P.enter_prob[idx];
-        double fixed = floor(prob);
-        double cnt = nk_add(P.res_counter[idx], nk_sub(prob, fixed));
-        int extra = cnt >= 1.0 ? 1 : 0;
-        cnt = nk_sub(cnt, (double)extra);
-        P.res_counter[idx] = cnt;
-        int n_new = (int)fixed + extra;
-        if (n_new == 0) continue;
-        if (n_new > NK_EMIT_CMAX) { P.dyn->error |= NK_ERR_CMAX; n_new = NK_EMIT_CMAX; }
-        NkMode mp = P.mprop[m];
-        for (int c = n_new; c >= 1; --c) {
-            NkParticle p;
-            p.id = NK_EMIT_ID_BASE + (((step * P.R + r) * (long long)P.M + m) * NK_EMIT_CMAX + (c - 1));
-            double ua, uface, us, ur;
-            nk_uniforms(P, p.id, step, NK_STREAM_EMIT_A, ua, uface);
-            nk_uniforms(P, p.id, step, NK_STREAM_EMIT_B, us, ur);
-            double dt_in = (c == 1) ? nk_mul(dt, nk_sub(1.0, nk_div(cnt, prob)))
-                                    : nk_mul(dt, nk_sub(1.0, nk_div(nk_add((double)(c - 1), ua), prob)));
-            // face ~ area: searchsorted(cdf, u, side='right') as np.random.choice does
-            int f0 = P.res_face_ptr[r], f1 = P.res_face_ptr[r + 1];
-            int lo = f0, hi = f1;
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (P.res_face_cdf[mid] <= uface) lo = mid + 1; else hi = mid; }
-            int face = P.res_faces[min(lo, f1 - 1)];
-            const double* V = P.face_vertices + 9 * (size_t)face;
-            double rs = sqrt(us);
-            double a0 = nk_sub(1.0, rs), a1 = nk_mul(nk_sub(1.0, ur), rs), a2 = nk_mul(ur, rs);
-            double x0 = nk_add(nk_add(nk_mul(a0, V[0]), nk_mul(a1, V[3])), nk_mul(a2, V[6]));
-            double y0 = nk_add(nk_add(nk_mul(a0, V[1]), nk_mul(a1, V[4])), nk_mul(a2, V[7]));
-            double z0 = nk_add(nk_add(nk_mul(a0, V[2]), nk_mul(a1, V[5])), nk_mul(a2, V[8]));
-            p.mode = m; p.omode = m; p.omega = mp.omega; p.vx = mp.vx; p.vy = mp.vy; p.vz = mp.vz;
-            double t;
-            nk_find_boundary_1(P, P.faces, x0, y0, z0, p.vx, p.vy, p.vz, p.cx, p.cy, p.cz, t, p.cf);
-            p.tc = nk_sub(nk_div(t, dt), nk_div(dt_in, dt));
-            p.x = nk_add(x0, nk_mul(p.vx, dt_in)); p.y = nk_add(y0, nk_mul(p.vy, dt_in)); p.z = nk_add(z0, nk_mul(p.vz, dt_in));
-            p.occ = nk_bose(P, P.res_T[r], p.omega);
-            p.alive = true;
-            atomicAdd(P.acc + NK_ACC_NEMIT(P.S, P.R), 1.0);
-            if (p.tc < 0.0) nk_boundary_events(P, p, step, P.acc);
-            if (!p.alive) { atomicAdd(P.acc + NK_ACC_NABS(P.S, P.R), 1.0); continue; }   // crossed the whole domain within the step
-            // slot: recycle a free one, else append
-            long long slot;
-            long long old = (long long)atomicAdd((unsigned long long*)&P.dyn->n_free, (unsigned long long)(-1LL));
-            if (old > 0) slot = P.freelist[old - 1];
-            else {
-                // empty: undo the pop (keeps n_free >= 0 once the kernel has drained) and append
-                atomicAdd((unsigned long long*)&P.dyn->n_free, 1ull);
-                slot = (long long)atomicAdd((unsigned long long*)&P.dyn->n_slots, 1ull);
-            }
-            if (slot >= P.cap) {
-                atomicAdd((unsigned long long*)&P.dyn->n_slots, (unsigned long long)(-1LL));
-                atomicOr(&P.dyn->error, NK_ERR_CAPACITY);
-                continue;
-            }
-            nk_store_particle(P, slot, p);
-            P.pid[slot] = p.id;
-            atomicAdd((unsigned long long*)&P.dyn->n_alive, 1ull);
-            nk_accumulate_global(P, p, with_flux);
-        }
+// One hit-list entry: the boundary event loop of an existing particle.
+__device__ __forceinline__ void nk_hit_entry(const NkP& P, const NkGeo& G, double* acc, long long i, long long step, bool with_flux) {
+    NkParticle p;
+    p.x = P.px[i]; p.y = P.py[i]; p.z = P.pz[i]; p.tc = P.tc[i]; p.occ = P.occ[i];
+    p.mode = P.mode[i]; p.omode = P.omode[i];
+    const NkMode m = P.mprop[p.mode];
+    p.vx = m.vx; p.vy = m.vy; p.vz = m.vz;
+    p.omega = (p.omode == p.mode) ? m.omega : P.mprop[p.omode].omega;
+    p.cf = P.cfacet[i]; p.cx = P.cx[i]; p.cy = P.cy[i]; p.cz = P.cz[i];
+    p.id = P.pid[i]; p.alive = true;
+    nk_boundary_events(P, G, p, step, acc);
+    if (p.alive) {
+        nk_store_particle(P, i, p);
+        nk_accumulate(P, acc, p, with_flux);
+    } else {
+        nk_kill(P, acc, i);
     }
 }
 
 // ---- close the step: calculate_energy normalisation, temperature_function, heat flux, kappa,
-//      reservoir balances (Population.py:704-728, :692, :730-788, :1685-1699) ------------------------------------
-__global__ void __launch_bounds__(1024) k_finalize(NkP P) {
-    extern __shared__ double sm[];
+//      reservoir balances (Population.py:704-728, :692, :730-788, :1685-1699).  One block. -----------------------
+__device__ void nk_finalize_block(const NkP& P, double* sm) {
     const int S = P.S, R = P.R;
     double* sT = sm;             // new T_sv
     double* sPhi = sm + S;       // flux along the slice axis
@@ -724,8 +761,8 @@ __global__ void __launch_bounds__(1024) k_finalize(NkP P) {
     const long long step_done = P.dyn->step + 1;
     const bool conv = (step_done % P.n_dt_to_conv) == 0;
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
-        double cnt = acc[NK_ACC_CNT(S, R) + s];
-        double esum = acc[NK_ACC_E(S, R) + s];
+        double cnt = __ldcg(acc + NK_ACC_CNT(S, R) + s);
+        double esum = __ldcg(acc + NK_ACC_E(S, R) + s);
         double norm;
         if (P.norm_mean) { norm = nk_div(P.n_active, cnt); if (norm != norm) norm = 0.0; }
         else norm = nk_div(P.n_active, nk_mul(P.particle_density, P.sv_volume[s]));
@@ -740,7 +777,7 @@ __global__ void __launch_bounds__(1024) k_finalize(NkP P) {
         if (conv) {
             double f[3];
             for (int k = 0; k < 3; ++k) {
-                f[k] = nk_mul(nk_div(nk_mul(acc[NK_ACC_FLUX(S, R) + 3 * s + k], norm), P.dens_norm), P.eVpsa2_in_Wm2);
+                f[k] = nk_mul(nk_div(nk_mul(__ldcg(acc + NK_ACC_FLUX(S, R) + 3 * s + k), norm), P.dens_norm), P.eVpsa2_in_Wm2);
                 out[NK_OUT_FLUX(S, R) + 3 * s + k] = f[k];
             }
             sPhi[s] = f[P.axis];
@@ -749,10 +786,10 @@ __global__ void __launch_bounds__(1024) k_finalize(NkP P) {
     __syncthreads();
     // reservoirs: accumulate this step, normalise on convergence steps
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
-        out[NK_OUT_NLEAVE(S, R) + r] = acc[NK_ACC_NLEAVE(S, R) + r];
-        double eb = nk_add(P.res_acc[r], acc[NK_ACC_EBAL(S, R) + r]);
+        out[NK_OUT_NLEAVE(S, R) + r] = __ldcg(acc + NK_ACC_NLEAVE(S, R) + r);
+        double eb = nk_add(P.res_acc[r], __ldcg(acc + NK_ACC_EBAL(S, R) + r));
         double fx[3];
-        for (int k = 0; k < 3; ++k) fx[k] = nk_add(P.res_acc[R + 3 * r + k], acc[NK_ACC_RFLUX(S, R) + 3 * r + k]);
+        for (int k = 0; k < 3; ++k) fx[k] = nk_add(P.res_acc[R + 3 * r + k], __ldcg(acc + NK_ACC_RFLUX(S, R) + 3 * r + k));
         if (conv) {
             double area = P.facet_area[P.res_facet[r]];
             double den = nk_mul(nk_mul(nk_mul(P.particle_density, P.dt), (double)P.n_dt_to_conv), area);
@@ -767,7 +804,7 @@ __global__ void __launch_bounds__(1024) k_finalize(NkP P) {
     }
     if (threadIdx.x == 0) {
         double np = 0.0, et = 0.0;
-        for (int s = 0; s < S; ++s) { np += sN[s]; et += acc[NK_ACC_E(S, R) + s]; }
+        for (int s = 0; s < S; ++s) { np += sN[s]; et += __ldcg(acc + NK_ACC_E(S, R) + s); }
         out[NK_OUT_NP(S, R)] = np;
         out[NK_OUT_ETOT(S, R)] = et;
         if (conv && P.is_slice && R == 2) {
@@ -796,7 +833,85 @@ __global__ void __launch_bounds__(1024) k_finalize(NkP P) {
         d->step = step_done;
         d->relax_pending = 1;
         d->n_hits = 0;
-        if (d->n_free < 0) d->n_free = 0;
+        d->n_emit = 0;
+        d->fr_snap = d->fr_tail;           // slots freed in this step become recyclable from the next one
+        d->blocks_done = 0;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_finalize(NkP P) {
+    extern __shared__ double sm[];
+    nk_finalize_block(P, sm);
+}
+
+// ---- the rare path of a step: boundary events of the hit list + reservoir emission -----------------------------
+// Work items [0, n_hits) are existing particles whose collision falls inside the step, [n_hits, n_hits + n_emit)
+// are emission-list entries.  One thread per item; triangles staged in shared memory when they fit.  With
+// FUSE the last block to finish closes the step (single-GPU path: no collective between the two halves).
+#define NK_RARE_THREADS 128
+#define NK_RARE_FACES 128
+#define NK_RARE_FACETS 64
+template <bool FUSE>
+__global__ void __launch_bounds__(NK_RARE_THREADS) k_rare(NkP P) {
+    __shared__ NkFace sfaces[NK_RARE_FACES];
+    __shared__ int sfi[4 * NK_RARE_FACETS];
+    __shared__ double sfd[6 * NK_RARE_FACETS];
+    extern __shared__ double sm_fin[];
+    __shared__ int s_last;
+    NkGeo G;
+    G.faces = P.faces; G.bc = P.facet_bc; G.partner = P.facet_partner; G.res = P.facet_res; G.rough = P.facet_rough;
+    G.normal = P.facet_normal; G.centroid = P.facet_centroid;
+    if (P.F <= NK_RARE_FACES) {
+        const double* src = reinterpret_cast<const double*>(P.faces);
+        double* dst = reinterpret_cast<double*>(sfaces);
+        for (int k = threadIdx.x; k < P.F * (int)(sizeof(NkFace) / 8); k += blockDim.x) dst[k] = src[k];
+        G.faces = sfaces;
+    }
+    if (P.nf <= NK_RARE_FACETS) {
+        for (int k = threadIdx.x; k < P.nf; k += blockDim.x) {
+            sfi[k] = P.facet_bc[k]; sfi[NK_RARE_FACETS + k] = P.facet_partner[k];
+            sfi[2 * NK_RARE_FACETS + k] = P.facet_res[k]; sfi[3 * NK_RARE_FACETS + k] = P.facet_rough[k];
+        }
+        for (int k = threadIdx.x; k < 3 * P.nf; k += blockDim.x) { sfd[k] = P.facet_normal[k]; sfd[3 * NK_RARE_FACETS + k] = P.facet_centroid[k]; }
+        G.bc = sfi; G.partner = sfi + NK_RARE_FACETS; G.res = sfi + 2 * NK_RARE_FACETS; G.rough = sfi + 3 * NK_RARE_FACETS;
+        G.normal = sfd; G.centroid = sfd + 3 * NK_RARE_FACETS;
+    }
+    // block-private accumulators: thousands of items would otherwise hammer the same ~40 global addresses
+    double* racc = sm_fin + 3 * P.S;
+    const int nacc = nk_acc_len(P.S, P.R);
+    for (int k = threadIdx.x; k < nacc; k += blockDim.x) racc[k] = 0.0;
+    __syncthreads();
+    const unsigned int nh = P.dyn->n_hits, ne = P.dyn->n_emit;
+    const long long step = P.dyn->step;
+    const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
+    for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < nh + ne; w += gridDim.x * blockDim.x) {
+        if (w < nh) {
+            nk_hit_entry(P, G, racc, P.hitlist[w], step, with_flux);
+        } else {
+            const int2 e = P.emitlist[w - nh];
+            nk_emit_entry(P, G, racc, e.x >> 8, e.y, e.x & 0xff, step, with_flux);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nacc; k += blockDim.x)
+        if (racc[k] != 0.0) atomicAdd(P.acc + k, racc[k]);
+    if (threadIdx.x == 0) {
+        // live count: + particles that got a slot (emitted - absorbed on arrival) - absorbed
+        const double d = racc[NK_ACC_NEMIT(P.S, P.R)] - racc[NK_ACC_NABS(P.S, P.R)];
+        if (d != 0.0) atomicAdd((unsigned long long*)&P.dyn->n_alive, (unsigned long long)(long long)d);
+    }
+    if (FUSE) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int t = atomicAdd(&P.dyn->blocks_done, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            nk_finalize_block(P, sm_fin);
+        }
     }
 }
 
@@ -1097,6 +1212,7 @@ int nk_set_reservoirs(nk_ctx* ctx, int R, const int32_t* res_facet, const double
     NK_UP(dd, double, res_T, R); P.res_T = dd;
     NK_UP(dd, double, enter_prob, (size_t)R * P.M); P.enter_prob = dd;
     NK_UP(dd, double, res_counter, (size_t)R * P.M); P.res_counter = dd;
+    int2* de; NK_UP(de, int2, (const int2*)nullptr, (size_t)std::max(R, 1) * P.M); P.emitlist = de;
     return nk_alloc_scratch(ctx);
 }
 
@@ -1163,7 +1279,7 @@ int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots) {
     if (!ctx->particles_bound) { ctx->err = "nk_bind_particles first"; return -1; }
     if (n_slots < 0 || n_slots > ctx->P.cap) { ctx->err = "n_slots out of range"; return -1; }
     NkDyn d; if (nk_read_dyn(ctx, &d)) return -1;
-    d.n_slots = n_slots; d.n_free = 0; d.n_hits = 0;
+    d.n_slots = n_slots; d.fr_head = d.fr_tail = d.fr_snap = 0; d.n_hits = 0; d.n_emit = 0; d.blocks_done = 0;
     if (nk_write_dyn(ctx, &d)) return -1;
     unsigned long long* dc; NK_CK(cudaMalloc(&dc, 8)); NK_CK(cudaMemset(dc, 0, 8));
     k_count_alive<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->P, dc);
@@ -1292,9 +1408,10 @@ int nk_init_collisions(nk_ctx* ctx) {
     return 0;
 }
 
-static size_t nk_step_smem(const NkP& P) { return (nk_sv_smem_doubles(P.S) + 4 * (size_t)P.S) * 8 + ((size_t)P.S + 2) * 4 + nk_hot_smem_bytes(P.S) + 32; }
+static size_t nk_step_smem(const NkP& P) { return (nk_sv_smem_doubles(P.S) + 8 * (size_t)P.S) * 8 + ((size_t)P.S + 2) * 4 + nk_hot_smem_bytes(P.S) + 32; }
 
-int nk_step_local(nk_ctx* ctx) {
+// kernels of one step; fuse_finalize: the last block of k_rare closes the step (no collective in between)
+static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize) {
     cudaSetDevice(ctx->device);
     if (nk_check_ready(ctx)) return -1;
     const NkP& P = ctx->P;
@@ -1323,17 +1440,16 @@ int nk_step_local(nk_ctx* ctx) {
     kern<<<ctx->step_blocks, NK_STEP_THREADS, smem, ctx->stream>>>(P);
     NK_CK(cudaGetLastError());
     nk_prof_mark(ctx);
-    if (P.R > 0) {
-        long long total = (long long)P.R * (P.emit_m_hi - P.emit_m_lo);
-        k_emit<<<nk_grid(total, 128, ctx->n_sm * 16), 128, 0, ctx->stream>>>(P);
-        NK_CK(cudaGetLastError());
-    }
-    nk_prof_mark(ctx);
-    k_boundary<<<ctx->n_sm * 4, 128, 0, ctx->stream>>>(P);
+    const size_t fin_smem = (3 * (size_t)P.S + nk_acc_len(P.S, P.R)) * 8;
+    if (fuse_finalize) k_rare<true><<<ctx->n_sm * 16, NK_RARE_THREADS, fin_smem, ctx->stream>>>(P);
+    else k_rare<false><<<ctx->n_sm * 16, NK_RARE_THREADS, fin_smem, ctx->stream>>>(P);
     NK_CK(cudaGetLastError());
     nk_prof_mark(ctx);
+    if (fuse_finalize) { ctx->h_step += 1; ctx->h_relax_pending = true; nk_prof_mark(ctx); }
     return 0;
 }
+
+int nk_step_local(nk_ctx* ctx) { return nk_step_kernels(ctx, false); }
 
 int nk_step_finalize(nk_ctx* ctx) {
     cudaSetDevice(ctx->device);
@@ -1357,11 +1473,11 @@ int nk_profile_end(nk_ctx* ctx, double* ms, int64_t* n_steps) {
     ctx->profiling = false;
     NK_CK(cudaStreamSynchronize(ctx->stream));
     for (int k = 0; k < 4; ++k) ms[k] = 0.0;
-    size_t steps = ctx->ev_used / 5;
+    size_t steps = ctx->ev_used / 4;                 // marks: | k_step | k_rare | finalize (0 when fused) |
     for (size_t s = 0; s < steps; ++s)
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 3; ++k) {
             float t = 0.f;
-            NK_CK(cudaEventElapsedTime(&t, ctx->ev[5 * s + k], ctx->ev[5 * s + k + 1]));
+            NK_CK(cudaEventElapsedTime(&t, ctx->ev[4 * s + k], ctx->ev[4 * s + k + 1]));
             ms[k] += t;
         }
     if (n_steps) *n_steps = (int64_t)steps;
@@ -1370,10 +1486,9 @@ int nk_profile_end(nk_ctx* ctx, double* ms, int64_t* n_steps) {
 }
 
 int nk_step(nk_ctx* ctx, int n_steps) {
-    for (int k = 0; k < n_steps; ++k) {
-        if (nk_step_local(ctx)) return -1;
-        if (nk_step_finalize(ctx)) return -1;
-    }
+    for (int k = 0; k < n_steps; ++k)
+        if (nk_step_kernels(ctx, ctx->P.world == 1)) return -1;
+        else if (ctx->P.world != 1 && nk_step_finalize(ctx)) return -1;
     return 0;
 }
 

@@ -39,11 +39,13 @@ struct __align__(64) NkModeHot {
 
 struct NkDyn {                   // device-resident, mutated by kernels
     long long n_slots;           // slots [0, n_slots) are live or on the free list
-    long long n_free;            // free-list height (may dip below 0 inside nk_emit_kernel)
+    long long fr_head;           // free-slot ring: next entry to recycle
+    long long fr_tail;           //                 next entry to write (slots freed by absorption)
+    long long fr_snap;           //                 fr_tail at the end of the previous step (pop limit)
     long long n_alive;
     long long step;              // Population.current_timestep
     unsigned int n_hits;         // particles whose collision falls inside this step
-    unsigned int n_hits_done;
+    unsigned int n_emit;         // emission-list entries of this step
     int relax_pending;           // lifetime_scattering of step-1 still to be applied to `occ`
     int error;                   // sticky device-side error bits
     unsigned int blocks_done;    // last-block detection
@@ -100,6 +102,7 @@ struct NkP {
     long long* pid;
     // ---- scratch owned by the ctx
     int* hitlist; int* freelist;
+    int2* emitlist;                   // (R*M) {reservoir << 8 | copies, mode} of the entries emitting this step
     double* T_sv;                     // (S) current subvolume temperatures
     double* acc;                      // per-step accumulators, see layout below
     double* res_acc;                  // (R*4) E_bal + flux accumulated over the convergence window

@@ -214,7 +214,7 @@ class Engine:
         ms = (C.c_double * 4)()
         n = C.c_int64()
         check(self.ctx, self.L.nk_profile_end(self.ctx, ms, C.byref(n)), "nk_profile_end")
-        return dict(k_step=ms[0], k_emit=ms[1], k_boundary=ms[2], k_finalize=ms[3]), n.value
+        return dict(k_step=ms[0], k_rare=ms[1], k_finalize=ms[2]), n.value
 
     def synchronize(self):
         check(self.ctx, self.L.nk_synchronize(self.ctx), "nk_synchronize")
