@@ -12,6 +12,8 @@ pairs validated by comparing the facets' boundary vertices).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 from scipy.spatial import cKDTree, Delaunay
 from scipy.spatial.transform import Rotation as rot
@@ -268,7 +270,7 @@ class Geometry:
                 err[np.isnan(err)] = 1
             cover = new_cover
             ns = min(ns * 2, 2 ** 18)
-            if nt > 2 ** 24:
+            if nt > int(float(os.environ.get('NK_VOLUME_MAX_SAMPLES', 2 ** 24))):
                 break
         return cover * self.volume
 

@@ -55,12 +55,26 @@ PARAMS_C2 = """
 --n_mean 10 --results_folder x --conv_crit 0 10 --colormap jet --output screen --max_sim_time 0-00:00:00
 """
 
+# C4-like: faceted cylinder (40 triangles), voronoi subvolumes (nearest T), rough side walls, reservoirs on the caps
+PARAMS_C4 = """
+--mat_folder test_material/Si/ --hdf_file kappa-m313131.hdf5 --poscar_file POSCAR
+--geometry cylinder --dimensions 3000 600 10 --scale 1 1 1 --geo_rotation 0 0 0 xyz
+--subvolumes voronoi 6
+--bound_pos relative 0.5 0.5 -0.1 0.5 0.5 1.1
+--bound_cond T T R
+--bound_values 305 295 {eta}
+--reference_temp local --temp_dist cold --temp_interp nearest
+--particles total {n} --part_dist random_subvol --timestep 1 --iterations 1000
+--n_mean 10 --results_folder x --conv_crit 0 10 --colormap jet --output screen --max_sim_time 0-00:00:00
+"""
+
 CONFIGS = {
     # name: (parameter text, table mesh n, lattice)
     "c1_specular": (PARAMS_C1.format(eta=0, n=4000), 5),
     "c1_diffuse": (PARAMS_C1.format(eta=10, n=4000), 5),
     "c1_mixed": (PARAMS_C1.format(eta=0.5, n=4000), 5),
     "c2_crossplane": (PARAMS_C2.format(n=6000), 5),
+    "c4_cylinder_voronoi": (PARAMS_C4.format(eta=3, n=3000), 5),
 }
 
 STATE_FIELDS = ("positions", "modes", "omega", "group_vel", "occupation", "n_timesteps", "collision_facets",

@@ -1,0 +1,79 @@
+"""Particle shards on the real kernels: two contexts (ranks 0 and 1 of 2, emulated on one GPU) own half of
+the particles and half of every reservoir's mode table; their accumulator vectors are summed between
+nk_step_local and nk_step_finalize exactly as the NCCL all-reduce does in nanokappa_b200.parallel.  The union of
+the shards must equal the single-context run: identical census / modes / facets, temperatures to 1e-12."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gen_golden
+
+pytestmark = pytest.mark.gpu
+SEED = 77
+
+
+def _engine(tb, st, rows, rank=None, world=None):
+    from nanokappa_b200.engine import Engine
+    from nanokappa_b200._lib import check
+    J = tb["omega"].shape[1]
+    eng = Engine(0, seed=SEED)
+    eng.set_tables(tb, res_counter=st.res_counter)
+    eng.allocate(2 * st.positions.shape[0] + 64)
+    eng.load_particles(st.positions[rows], (st.modes[:, 0] * J + st.modes[:, 1])[rows], st.occupation[rows], ids=st.ids[rows],
+                       omodes=st.omega_modes[rows], n_timesteps=st.n_timesteps[rows], collision_facets=st.collision_facets[rows],
+                       collision_positions=st.collision_positions[rows])
+    eng.set_sv_temperature(st.subvol_temperature)
+    eng.set_timestep(0)
+    if world is not None:
+        check(eng.ctx, eng.L.nk_set_rank(eng.ctx, rank, world), "nk_set_rank")
+    return eng
+
+
+def _acc(eng):
+    from nanokappa_b200._lib import check
+    ptr, ln = C.c_void_p(), C.c_int64()
+    check(eng.ctx, eng.L.nk_acc_buffer(eng.ctx, C.byref(ptr), C.byref(ln)), "nk_acc_buffer")
+
+    class _A:
+        __cuda_array_interface__ = {"shape": (ln.value,), "typestr": "<f8", "data": (ptr.value, False), "version": 3}
+    return torch.as_tensor(_A(), device=eng.device)
+
+
+@pytest.mark.parametrize("name", ["c2_crossplane", "c1_mixed"])
+def test_two_shards_equal_one_context(name, golden_dir):
+    tb, st, _ = gen_golden.load_fixture(os.path.join(golden_dir, name + ".npz"))
+    n = st.positions.shape[0]
+    single = _engine(tb, st, slice(0, n))
+    shards = [_engine(tb, st, slice(0, n // 2), 0, 2), _engine(tb, st, slice(n // 2, n), 1, 2)]
+    accs = [_acc(e) for e in shards]
+    steps = 25
+    single.step(steps)
+    for _ in range(steps):
+        for e in shards:
+            e.step_local()
+        torch.cuda.synchronize()
+        total = accs[0] + accs[1]
+        for a in accs:
+            a.copy_(total)
+        for e in shards:
+            e.step_finalize()
+    ps = single.particles()
+    parts = [e.particles() for e in shards]
+    ids = np.concatenate([p["ids"] for p in parts])
+    assert np.unique(ids).shape[0] == ids.shape[0]
+    order = np.argsort(ids)
+    assert np.array_equal(ids[order], ps["ids"])
+    cat = lambda k: np.concatenate([p[k] for p in parts])[order]
+    assert np.array_equal(cat("modes"), ps["modes"])
+    assert np.array_equal(cat("collision_facets"), ps["collision_facets"])
+    assert np.allclose(cat("positions"), ps["positions"], rtol=1e-13, atol=1e-9, equal_nan=True)
+    assert np.allclose(cat("occupation"), ps["occupation"], rtol=1e-9, atol=0)
+    rs = single.results()
+    for e in shards:
+        r = e.results()
+        assert np.array_equal(r["subvol_N_p"], rs["subvol_N_p"]) and np.array_equal(r["N_leaving"], rs["N_leaving"])
+        assert np.allclose(r["subvol_temperature"], rs["subvol_temperature"], rtol=1e-12, atol=0)
+    assert sum(e.slot_count()[1] for e in shards) == single.slot_count()[1]
