@@ -459,6 +459,211 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step(Nk
     nk_flush_bins<FLUX>(P, binE, binF, binX, binC);
 }
 
+__device__ __forceinline__ unsigned int nk_smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+// ---- variant A2: variant A + per-thread software prefetch through shared memory (cp.async / LDGSTS) -----------
+// Every thread copies the 88 bytes of ITS next two particles into a private shared-memory slot with cp.async
+// while it works on the current pair, so two tiles of loads are in flight per warp without holding them in
+// registers (occupancy stays at 4 blocks / SM).  A thread only reads back what it copied itself: no barrier.
+struct NkPfStage {
+    double2 x[NK_STEP_THREADS], y[NK_STEP_THREADS], z[NK_STEP_THREADS], tc[NK_STEP_THREADS], oc[NK_STEP_THREADS];
+    int2 md[NK_STEP_THREADS], om[NK_STEP_THREADS];
+};
+__device__ __forceinline__ void nk_cp16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(nk_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void nk_cp8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(nk_smem_u32(dst)), "l"(src) : "memory");
+}
+template <bool HAS_ROUGH, bool FAST, bool RELAX, bool FLUX>
+__global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step_pf(NkP P) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    NkPfStage* stage = reinterpret_cast<NkPfStage*>(smraw);
+    double* sm = reinterpret_cast<double*>(smraw + 2 * sizeof(NkPfStage));
+    NkSvSmem s = nk_load_sv(P, sm);
+    const int S = P.S;
+    long long* binE = reinterpret_cast<long long*>(sm + nk_sv_smem_doubles(S));
+    long long* binF = binE + S;
+    double* binX = reinterpret_cast<double*>(binF + 3 * S);
+    unsigned int* binC = reinterpret_cast<unsigned int*>(binX + 4 * S);
+    NkSvHot h = nk_load_hot(P, binC + S + (S & 1));
+    for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0; binC[i] = 0u; for (int k = 0; k < 3; ++k) binF[3 * i + k] = 0; for (int k = 0; k < 4; ++k) binX[4 * i + k] = 0.0; }
+    __syncthreads();
+
+    nk_emit_scan(P);
+    const long long n = P.dyn->n_slots;
+    const unsigned int lane = threadIdx.x & 31u;
+    const int t = threadIdx.x;
+    const long long stride = 2 * (long long)gridDim.x * blockDim.x;
+
+    auto prefetch = [&](int st, long long base) {
+        if (base < n) {
+            NkPfStage& T = stage[st];
+            nk_cp16(&T.x[t], P.px + base); nk_cp16(&T.y[t], P.py + base); nk_cp16(&T.z[t], P.pz + base);
+            nk_cp16(&T.tc[t], P.tc + base); nk_cp16(&T.oc[t], P.occ + base);
+            nk_cp8(&T.md[t], P.mode + base);
+            if (HAS_ROUGH) nk_cp8(&T.om[t], P.omode + base);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    long long wbase = 2 * ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u));
+    int st = 0;
+    if (wbase < n) prefetch(0, wbase + 2 * lane);
+    for (; wbase < n; wbase += stride, st ^= 1) {
+        const long long base = wbase + 2 * lane;
+        prefetch(st ^ 1, base + stride);                        // next pair (an empty group past the end)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");    // everything but the newest group has landed
+        const bool inb = base < n;
+        double2 X = make_double2(0, 0), Y = X, Z = X, TC = X, OC = X;
+        int2 MD = make_int2(-1, -1), OM = MD;
+        if (inb) {
+            const NkPfStage& T = stage[st];
+            X = T.x[t]; Y = T.y[t]; Z = T.z[t]; TC = T.tc[t]; OC = T.oc[t]; MD = T.md[t];
+            OM = MD;
+            if (HAS_ROUGH) OM = T.om[t];
+        }
+        bool h0 = false, h1 = false;
+        if (base < n && MD.x >= 0) h0 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.x, OM.x, X.x, Y.x, Z.x, TC.x, OC.x);
+        if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.y, OM.y, X.y, Y.y, Z.y, TC.y, OC.y);
+        nk_push_hits(P, lane, h0, h1, base);
+        if (inb) {
+            *reinterpret_cast<double2*>(P.px + base) = X;
+            *reinterpret_cast<double2*>(P.py + base) = Y;
+            *reinterpret_cast<double2*>(P.pz + base) = Z;
+            *reinterpret_cast<double2*>(P.tc + base) = TC;
+            *reinterpret_cast<double2*>(P.occ + base) = OC;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    nk_flush_bins<FLUX>(P, binE, binF, binX, binC);
+}
+
+// ---- variant T: per-(mode, subvolume) tables ------------------------------------------------------------------
+// With the nearest-temperature rule both the equilibrium occupation and the relaxation factor of a particle are
+// functions of (mode, subvolume) only.  When there are many particles per (mode, subvolume) pair it is cheaper
+// to tabulate {n0, exp(-dt/tau)} once per step (k_mode_tables, M x S entries, the arithmetic of nk_bose_fast /
+// nk_decay, so results are bit-identical to the direct variants) than to evaluate two exponentials and three
+// reciprocals per particle.  Particles are ordered by mode, so a warp gathers from a handful of table rows.
+__global__ void __launch_bounds__(256) k_mode_tables(NkP P) {
+    extern __shared__ double sm[];
+    NkSvHot h = nk_load_hot(P, sm);
+    __syncthreads();
+    const int S = P.S;
+    const long long total = (long long)P.M * S;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / S), sv = (int)(i % S);
+        double4 ma, mt;
+        nk_ld256(&P.mhot[m].omega, ma);
+        nk_ld256(&P.mhot[m].t[0], mt);
+        const double a = nk_mul(P.hbar, ma.x);
+        const double be = nk_bose_fast(a, ma.x, h.invb[sv]);
+        const int r = h.tr[sv];
+        const double w = h.tw[sv];
+        double lo = r == 0 ? mt.x : (r == 1 ? mt.y : mt.z);
+        double hi = r == 0 ? mt.y : (r == 1 ? mt.z : mt.w);
+        if (r < 0) {
+            const int it = h.ti[sv];
+            lo = __ldg(P.tau + (size_t)it * P.M + m);
+            hi = __ldg(P.tau + (size_t)(it + 1) * P.M + m);
+        }
+        const double tau = nk_add(nk_mul(lo, nk_sub(1.0, w)), nk_mul(hi, w));
+        const double dec = tau > 0.0 ? nk_decay(P.dt, tau) : 0.0;       // tau <= 0: relax straight to n0
+        P.hot_tab[i] = make_double2(be, dec);
+    }
+}
+
+template <bool HAS_ROUGH, bool RELAX, bool FLUX>
+__device__ __forceinline__ bool nk_step_particle_tab(const NkP& P, const NkSvSmem& s, const NkSvHot& h, long long* binE, long long* binF,
+                                                     double* binX, unsigned int* binC, int md, int om, double& x, double& y, double& z,
+                                                     double& tc, double& occ) {
+    double4 ma;
+    nk_ld256(&P.mhot[md].omega, ma);        // omega, v_g
+    double omega = ma.x;
+    if (HAS_ROUGH && om != md) omega = P.mhot[om].omega;
+    const double a = nk_mul(P.hbar, omega);
+    const double dt = P.dt;
+    const int S = P.S;
+    const double2* __restrict__ row = P.hot_tab + (size_t)md * S;
+    const double2* __restrict__ orow = (HAS_ROUGH && om != md) ? P.hot_tab + (size_t)om * S : row;
+    double be0 = 0.0; int g0 = -1;
+    if (RELAX) {
+        const double xa = P.axis == 0 ? x : (P.axis == 1 ? y : z);
+        double lo_b, hi_b;
+        g0 = nk_slice_lookup(P, h.midp, s.sv_mid, xa, lo_b, hi_b);          // interp1d 'nearest'
+        const double2 t0 = __ldg(row + g0);
+        be0 = (HAS_ROUGH && om != md) ? __ldg(orow + g0).x : t0.x;
+        const double relaxed = be0 + (occ - be0) * t0.y;
+        occ = t0.y > 0.0 ? relaxed : be0;
+    }
+    x = nk_add(x, nk_mul(ma.y, dt)); y = nk_add(y, nk_mul(ma.z, dt)); z = nk_add(z, nk_mul(ma.w, dt));
+    tc = nk_sub(tc, 1.0);
+    if (tc < 0.0) return true;
+    const double xa = P.axis == 0 ? x : (P.axis == 1 ? y : z);
+    double lo_b, hi_b;
+    int sv = nk_slice_lookup(P, h.midp, s.sv_mid, xa, lo_b, hi_b);
+    if ((xa - lo_b < 1e-6) || (hi_b - xa < 1e-6)) sv = nk_classify(P, s.svc, s.sv_mid, x, y, z);
+    double be1 = be0;
+    if (!(RELAX && sv == g0)) be1 = __ldg(orow + sv).x;
+    const double e = a * (occ - be1);
+    nk_bin_add(binE + sv, binX + sv, e, NK_QE);
+    atomicAdd(binC + sv, 1u);
+    if (FLUX) {
+        nk_bin_add(binF + 3 * sv, binX + P.S + 3 * sv, ma.y * e, NK_QF);
+        nk_bin_add(binF + 3 * sv + 1, binX + P.S + 3 * sv + 1, ma.z * e, NK_QF);
+        nk_bin_add(binF + 3 * sv + 2, binX + P.S + 3 * sv + 2, ma.w * e, NK_QF);
+    }
+    return false;
+}
+
+template <bool HAS_ROUGH, bool FAST, bool RELAX, bool FLUX>
+__global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step_tab(NkP P) {
+    extern __shared__ double sm[];
+    NkSvSmem s = nk_load_sv(P, sm);
+    const int S = P.S;
+    long long* binE = reinterpret_cast<long long*>(sm + nk_sv_smem_doubles(S));
+    long long* binF = binE + S;
+    double* binX = reinterpret_cast<double*>(binF + 3 * S);
+    unsigned int* binC = reinterpret_cast<unsigned int*>(binX + 4 * S);
+    NkSvHot h = nk_load_hot(P, binC + S + (S & 1));
+    for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0; binC[i] = 0u; for (int k = 0; k < 3; ++k) binF[3 * i + k] = 0; for (int k = 0; k < 4; ++k) binX[4 * i + k] = 0.0; }
+    __syncthreads();
+
+    nk_emit_scan(P);
+    const long long n = P.dyn->n_slots;
+    const unsigned int lane = threadIdx.x & 31u;
+    for (long long wbase = 2 * ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); wbase < n;
+         wbase += 2 * (long long)gridDim.x * blockDim.x) {
+        const long long base = wbase + 2 * lane;
+        const bool inb = base < n;
+        double2 X = make_double2(0, 0), Y = X, Z = X, TC = X, OC = X;
+        int2 MD = make_int2(-1, -1), OM = MD;
+        if (inb) {
+            X = *reinterpret_cast<const double2*>(P.px + base);
+            Y = *reinterpret_cast<const double2*>(P.py + base);
+            Z = *reinterpret_cast<const double2*>(P.pz + base);
+            TC = *reinterpret_cast<const double2*>(P.tc + base);
+            OC = *reinterpret_cast<const double2*>(P.occ + base);
+            MD = *reinterpret_cast<const int2*>(P.mode + base);
+            OM = MD;
+            if (HAS_ROUGH) OM = *reinterpret_cast<const int2*>(P.omode + base);
+        }
+        bool h0 = false, h1 = false;
+        if (base < n && MD.x >= 0) h0 = nk_step_particle_tab<HAS_ROUGH, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.x, OM.x, X.x, Y.x, Z.x, TC.x, OC.x);
+        if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle_tab<HAS_ROUGH, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.y, OM.y, X.y, Y.y, Z.y, TC.y, OC.y);
+        nk_push_hits(P, lane, h0, h1, base);
+        if (inb) {
+            *reinterpret_cast<double2*>(P.px + base) = X;
+            *reinterpret_cast<double2*>(P.py + base) = Y;
+            *reinterpret_cast<double2*>(P.pz + base) = Z;
+            *reinterpret_cast<double2*>(P.tc + base) = TC;
+            *reinterpret_cast<double2*>(P.occ + base) = OC;
+        }
+    }
+    __syncthreads();
+    nk_flush_bins<FLUX>(P, binE, binF, binX, binC);
+}
+
 // ---- variant A1: one particle per thread, 64-bit accesses (fewer live registers -> more resident warps) ------
 #ifndef NK_STEP1_MIN_BLOCKS
 #define NK_STEP1_MIN_BLOCKS 5
@@ -510,7 +715,6 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP1_MIN_BLOCKS) k_step1(
 // with a bulk store.  Needs capacity % NK_TILE == 0 (slots past n_slots are dead: mode = -1).
 #define NK_TILE 512
 #define NK_STAGES 3
-__device__ __forceinline__ unsigned int nk_smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void nk_mbar_init(void* bar, unsigned int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nk_smem_u32(bar)), "r"(count));
 }
@@ -630,7 +834,7 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, 2) k_step_tma(NkP P) {
 typedef void (*nk_step_fn)(NkP);
 template <int V, bool A, bool B, bool C, bool D>
 static nk_step_fn nk_pick5() {
-    return V == 1 ? (nk_step_fn)k_step_tma<A, B, C, D> : (V == 2 ? (nk_step_fn)k_step1<A, B, C, D> : (nk_step_fn)k_step<A, B, C, D>);
+    return V == 1 ? (nk_step_fn)k_step_tma<A, B, C, D> : (V == 2 ? (nk_step_fn)k_step1<A, B, C, D> : (V == 3 ? (nk_step_fn)k_step_pf<A, B, C, D> : (V == 4 ? (nk_step_fn)k_step_tab<A, B, C, D> : (nk_step_fn)k_step<A, B, C, D>)));
 }
 template <int V, bool A, bool B, bool C>
 static nk_step_fn nk_pick4(bool d) { return d ? nk_pick5<V, A, B, C, true>() : nk_pick5<V, A, B, C, false>(); }
@@ -641,7 +845,7 @@ static nk_step_fn nk_pick2(bool b, bool c, bool d) { return b ? nk_pick3<V, A, t
 template <int V>
 static nk_step_fn nk_pick1(bool a, bool b, bool c, bool d) { return a ? nk_pick2<V, true>(b, c, d) : nk_pick2<V, false>(b, c, d); }
 static nk_step_fn nk_pick_step(int variant, bool rough, bool fast, bool relax, bool flux) {
-    return variant == 1 ? nk_pick1<1>(rough, fast, relax, flux) : (variant == 2 ? nk_pick1<2>(rough, fast, relax, flux) : nk_pick1<0>(rough, fast, relax, flux));
+    return variant == 1 ? nk_pick1<1>(rough, fast, relax, flux) : (variant == 2 ? nk_pick1<2>(rough, fast, relax, flux) : (variant == 3 ? nk_pick1<3>(rough, fast, relax, flux) : (variant == 4 ? nk_pick1<4>(rough, fast, relax, flux) : nk_pick1<0>(rough, fast, relax, flux))));
 }
 
 // ---- helpers shared by the rare-path code ------------------------------------------------------------------
@@ -957,6 +1161,11 @@ struct nk_ctx {
     int step_blocks = 0;
     int step_blocks_variant = -1;
     int step_variant = 0;
+    bool use_tab = true;           // NK_STEP_TAB=0 disables the per-(mode, subvolume) table variant
+    bool force_tab = false;        // NK_STEP_TAB=force: use it regardless of the particle count (tests)
+    bool tab_dirty = true;         // T_sv changed since k_mode_tables last ran
+    long long h_slots_hint = 0;
+    int last_variant = 0;    // slot count at the last nk_set_slot_count
     bool profiling = false;
     long long h_step = 0;          // host mirror of NkDyn::step
     bool h_relax_pending = false;  // host mirror of NkDyn::relax_pending
@@ -1024,7 +1233,8 @@ int nk_create(int device, nk_ctx** out) {
     cudaGetDeviceProperties(&prop, device);
     ctx->n_sm = prop.multiProcessorCount;
     ctx->P.world = 1;
-    if (const char* e = getenv("NK_STEP_IMPL")) ctx->step_variant = !strcmp(e, "tma") ? 1 : (!strcmp(e, "ldg1") ? 2 : 0);
+    if (const char* e = getenv("NK_STEP_TAB")) { ctx->use_tab = strcmp(e, "0") != 0; ctx->force_tab = !strcmp(e, "force"); }
+    if (const char* e = getenv("NK_STEP_IMPL")) ctx->step_variant = !strcmp(e, "tma") ? 1 : (!strcmp(e, "ldg1") ? 2 : (!strcmp(e, "pf") ? 3 : 0));
     NkDyn z; memset(&z, 0, sizeof(z));
     ctx->P.dyn = nk_upload<NkDyn>(ctx, &z, 1);
     *out = ctx;
@@ -1149,7 +1359,7 @@ static int nk_build_tau4(nk_ctx* ctx) {
     }
     NkModeHot* dh; NK_UP(dh, NkModeHot, hot.data(), (size_t)M);
     P.mhot = dh;
-    ctx->step_blocks = 0;
+    ctx->step_blocks = 0; ctx->tab_dirty = true;
     return 0;
 }
 
@@ -1198,6 +1408,13 @@ static int nk_alloc_scratch(nk_ctx* ctx) {
     NK_UP(dd, double, (const double*)nullptr, (size_t)nk_acc_len(P.S, P.R)); P.acc = dd;
     NK_UP(dd, double, (const double*)nullptr, (size_t)4 * std::max(P.R, 1)); P.res_acc = dd;
     NK_UP(dd, double, (const double*)nullptr, (size_t)nk_out_len(P.S, P.R)); P.out = dd;
+    P.hot_tab = nullptr;
+    if (P.is_slice && P.interp == NK_INTERP_NEAREST && ctx->use_tab) {
+        double2* dt2 = nullptr;
+        if (cudaMalloc(&dt2, (size_t)P.M * P.S * sizeof(double2)) == cudaSuccess) { ctx->owned.push_back(dt2); P.hot_tab = dt2; }
+        else cudaGetLastError();          // not enough memory: the direct variant is used
+    }
+    ctx->tab_dirty = true; ctx->step_blocks = 0;
     return 0;
 }
 
@@ -1279,6 +1496,7 @@ int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots) {
     if (!ctx->particles_bound) { ctx->err = "nk_bind_particles first"; return -1; }
     if (n_slots < 0 || n_slots > ctx->P.cap) { ctx->err = "n_slots out of range"; return -1; }
     NkDyn d; if (nk_read_dyn(ctx, &d)) return -1;
+    ctx->h_slots_hint = n_slots;
     d.n_slots = n_slots; d.fr_head = d.fr_tail = d.fr_snap = 0; d.n_hits = 0; d.n_emit = 0; d.blocks_done = 0;
     if (nk_write_dyn(ctx, &d)) return -1;
     unsigned long long* dc; NK_CK(cudaMalloc(&dc, 8)); NK_CK(cudaMemset(dc, 0, 8));
@@ -1310,6 +1528,7 @@ int nk_set_sv_temperature(nk_ctx* ctx, const double* T) {
     cudaSetDevice(ctx->device);
     NK_CK(cudaStreamSynchronize(ctx->stream));
     NK_CK(cudaMemcpy(ctx->P.T_sv, T, ctx->P.S * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->tab_dirty = true;
     return 0;
 }
 int nk_get_sv_temperature(nk_ctx* ctx, double* T) {
@@ -1423,7 +1642,15 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize) {
     const bool flux = ((ctx->h_step + 1) % P.n_dt_to_conv) == 0;
     int variant = ctx->step_variant;                          // 0: 2 particles/thread LDG.128, 1: TMA pipeline, 2: 1 particle/thread
     if (variant == 1 && (P.cap % NK_TILE) != 0) variant = 0;
+    // per-(mode, subvolume) tables pay off once there are a few particles per table entry
+    if (variant == 0 && ctx->use_tab && fast && P.hot_tab && (ctx->force_tab || ctx->h_slots_hint >= 2 * (long long)P.M * P.S)) variant = 4;
+    if (variant == 4 && ctx->tab_dirty) {
+        k_mode_tables<<<ctx->n_sm * 8, 256, nk_hot_smem_bytes(P.S), ctx->stream>>>(P);
+        NK_CK(cudaGetLastError());
+        ctx->tab_dirty = false;
+    }
     if (variant == 1) smem = NK_STAGES * sizeof(NkTileSmem) + (NK_STAGES + 1) * 8 + nk_step_smem(P);
+    if (variant == 3) smem = 2 * sizeof(NkPfStage) + nk_step_smem(P);
     nk_step_fn kern = nk_pick_step(variant, ctx->has_rough, fast, relax, flux);
     if (!ctx->step_blocks || ctx->step_blocks_variant != variant) {
         int per_sm = 0;
@@ -1445,7 +1672,16 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize) {
     else k_rare<false><<<ctx->n_sm * 16, NK_RARE_THREADS, fin_smem, ctx->stream>>>(P);
     NK_CK(cudaGetLastError());
     nk_prof_mark(ctx);
-    if (fuse_finalize) { ctx->h_step += 1; ctx->h_relax_pending = true; nk_prof_mark(ctx); }
+    if (fuse_finalize) {
+        ctx->h_step += 1; ctx->h_relax_pending = true; ctx->tab_dirty = true;
+        if (variant == 4) {            // next step's tables right away (T_sv is final once k_rare has finished)
+            k_mode_tables<<<ctx->n_sm * 8, 256, nk_hot_smem_bytes(P.S), ctx->stream>>>(P);
+            NK_CK(cudaGetLastError());
+            ctx->tab_dirty = false;
+        }
+        nk_prof_mark(ctx);
+    }
+    ctx->last_variant = variant;
     return 0;
 }
 
@@ -1458,7 +1694,12 @@ int nk_step_finalize(nk_ctx* ctx) {
     while (threads < P.S && threads < 1024) threads <<= 1;
     k_finalize<<<1, threads, 3 * (size_t)P.S * 8, ctx->stream>>>(P);
     NK_CK(cudaGetLastError());
-    ctx->h_step += 1; ctx->h_relax_pending = true;
+    ctx->h_step += 1; ctx->h_relax_pending = true; ctx->tab_dirty = true;
+    if (ctx->last_variant == 4) {
+        k_mode_tables<<<ctx->n_sm * 8, 256, nk_hot_smem_bytes(P.S), ctx->stream>>>(P);
+        NK_CK(cudaGetLastError());
+        ctx->tab_dirty = false;
+    }
     nk_prof_mark(ctx);
     return 0;
 }

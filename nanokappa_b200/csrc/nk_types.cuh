@@ -81,6 +81,7 @@ struct NkP {
     const double* tau;                // (NT, M)
     const NkTau4* tau4;               // (M) slabs tau_i0 .. tau_i0+3
     const NkModeHot* mhot;            // (M) hot record of the streaming kernel
+    double2* hot_tab;                 // (M, S) {n0(T_sv), exp(-dt/tau(T_sv))} rebuilt every step (slice + nearest T), or null
     int tau_i0;
     double Tg_inv_d;                  // 1 / (Tg[1]-Tg[0]) guess
     int nE; const double* Ea; const double* Ta;
