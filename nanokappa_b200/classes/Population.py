@@ -75,6 +75,7 @@ class PopulationSetup(Constants):
     def setup_host(self, arguments, geometry, phonon, seed=None):
         self.args = arguments
         self.results_folder_name = self.args.results_folder
+        os.makedirs(self.results_folder_name, exist_ok=True)
         self.n_dt_to_conv = 10
         self.norm = self.args.energy_normal[0]
         self.n_of_subvols = geometry.n_of_subvols

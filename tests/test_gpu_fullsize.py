@@ -1,0 +1,79 @@
+"""README / BASELINE configs[1] at full size (1e6 particles, box (2e4 A)^3, T/T + periodic walls, 20 slices,
+10 000-step run shortened to 200 steps), checked through size-independent properties: census
+conservation, containment, non-negative collision clocks, unique ids, determinism for a fixed seed,
+reproducibility of the sums across step-kernel variants, and a warming hot side."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+import argument_parser as ap
+
+pytestmark = pytest.mark.gpu
+
+PARAMS = """
+--mat_folder /nonexistent/ --hdf_file synthetic:11 --poscar_file POSCAR
+--geometry box --dimensions 20e3 20e3 20e3 --scale 1 1 1 --geo_rotation 0 0 0 xyz
+--subvolumes slice 20 0 --bound_pos relative -0.1 0.5 0.5 1.1 0.5 0.5 --bound_cond T T P
+--connect_pos relative 0.5 -0.1 0.5 0.5 1.1 0.5 0.5 0.5 -0.1 0.5 0.5 1.1 --bound_values 302 298
+--reference_temp local --temp_dist cold --temp_interp nearest --particles total 1e6 --part_dist random_subvol
+--timestep 1 --iterations 10000 --n_mean 10 --results_folder x --conv_crit 0 10 --output screen --max_sim_time 0-00:00:00
+"""
+
+
+def _run(tmp, seed, steps, env=None, monkeypatch=None):
+    from nanokappa_b200.classes.Geometry import Geometry
+    from nanokappa_b200.classes.Phonon import Phonon
+    from nanokappa_b200.classes.Population import Population
+    if monkeypatch is not None:
+        for k in ("NK_STEP_TAB", "NK_STEP_IMPL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in (env or {}).items():
+            monkeypatch.setenv(k, v)
+    args = ap.initialise_parser(False).parse_args(PARAMS.split())
+    args.results_folder = str(tmp)
+    with contextlib.redirect_stdout(io.StringIO()):
+        geo = Geometry(args)
+        ph = Phonon(args, 0)
+        np.random.seed(seed)
+        pop = Population(args, geo, ph, device=0, seed=seed)
+        pop.engine.sort_by_mode()
+        census = [pop.N_p]
+        for _ in range(steps // 10):
+            pop.engine.step(10)
+            census.append(pop.engine.results()["N_p"])
+    return geo, pop, census
+
+
+def test_readme_case_properties(tmp_path, monkeypatch):
+    geo, pop, census = _run(tmp_path / "a", 5, 200, {"NK_STEP_TAB": "force"}, monkeypatch)
+    eng = pop.engine
+    n_slots, n_alive = eng.slot_count()
+    res = eng.results()
+    assert n_alive == res["N_p"] == int(res["subvol_N_p"].sum())
+    assert abs(n_alive - 1_000_000) < 5_000 and n_slots <= eng.cap
+    t = eng.t
+    live = t["mode"][:n_slots] >= 0
+    assert int(live.sum().item()) == n_alive
+    ids = t["pid"][:n_slots][live]
+    assert torch.unique(ids).numel() == n_alive
+    lo = torch.as_tensor(geo.bounds[0] - 1e-6, device=eng.device); hi = torch.as_tensor(geo.bounds[1] + 1e-6, device=eng.device)
+    for k, name in enumerate(("px", "py", "pz")):
+        v = t[name][:n_slots][live]
+        assert bool(((v >= lo[k]) & (v <= hi[k])).all()), f"{name} left the box"
+    assert bool((t["tc"][:n_slots][live] >= 0).all()), "a live particle kept an expired collision clock"
+    assert bool((t["occ"][:n_slots][live] >= 0).all()) and bool(torch.isfinite(t["occ"][:n_slots][live]).all())
+    T = res["subvol_temperature"]
+    assert T[0] > 298.05 and abs(T[-1] - 298.0) < 0.05 and (np.diff(T[:6]) < 0).all()      # heat enters from the 302 K side
+    assert max(abs(np.diff(census))) < 2_000                                               # emission ~ absorption
+    # same seed, other kernel variant: identical integers, sums equal to rounding
+    geo2, pop2, census2 = _run(tmp_path / "b", 5, 200, {"NK_STEP_TAB": "0"}, monkeypatch)
+    assert census2 == census
+    r2 = pop2.engine.results()
+    assert np.array_equal(r2["subvol_N_p"], res["subvol_N_p"])
+    assert np.allclose(r2["subvol_temperature"], T, rtol=1e-12, atol=0)
+    a, b = pop.engine.particles(), pop2.engine.particles()
+    assert np.array_equal(a["ids"], b["ids"]) and np.array_equal(a["modes"], b["modes"])
+    assert np.array_equal(a["collision_facets"], b["collision_facets"]) and np.array_equal(a["positions"], b["positions"])
