@@ -228,6 +228,8 @@ class Population(PopulationSetup):
         key = self.args.part_dist[0]
         S = self.n_of_subvols
         occupation = None
+        if self._can_init_on_device(geometry, key):
+            return self._initialise_on_device(geometry, phonon)
         if key in ('random_domain', 'center_domain'):
             positions = self.generate_positions(self.N_p, geometry.mesh, key.split('_')[0])
         elif key == 'random_subvol':
@@ -278,6 +280,125 @@ class Population(PopulationSetup):
                 old = np.copy(self.subvol_temperature)
         print('Initialising local quantities...')
         self._host_census(geometry, phonon)
+
+    # ---- initialisation at scale: positions, modes and occupations created on the device ----
+    def _can_init_on_device(self, geometry, key):
+        thr = float(os.environ.get('NK_DEVICE_INIT_MIN', 2e5))
+        return (key in ('random_subvol', 'random_domain') and geometry.shape in ('cuboid', 'box') and geometry.subvol_type == 'slice'
+                and self.rotation_free(geometry) and self.n_of_empty_subvols == 0 and self.N_p >= thr and self.T_distribution != 'custom')
+
+    @staticmethod
+    def rotation_free(geometry):
+        return geometry.rotation is None or not np.any(np.asarray(geometry.rotation, dtype=float) != 0)
+
+    def _initialise_on_device(self, geometry, phonon):
+        """Box + slice subvolumes: the reference fills every slice with ceil(N V_s / V) uniform points and keeps
+        the first N (Population.py:209-246); here each slice's quota is drawn directly inside the slice
+        with the device generator (same distribution, no rejection), modes are tiled / drawn as in
+        initialise_modes (:127-144), occupations are Bose-Einstein at the slice temperature."""
+        import torch
+        eng = self.engine
+        dev = eng.device
+        N, S, ax = int(self.N_p), self.n_of_subvols, self.slice_axis
+        g = torch.Generator(device=dev); g.manual_seed(self.seed)
+        cap = int(N * float(os.environ.get('NK_CAPACITY_FACTOR', 1.25))) + 1024
+        eng.allocate(cap)
+        t = eng.t
+        lo = geometry.bounds[0]; ext = np.ptp(geometry.bounds, axis=0)
+        key = self.args.part_dist[0]
+        for k, name in enumerate(('px', 'py', 'pz')):
+            t[name][:N] = lo[k] + torch.rand(N, generator=g, dtype=torch.float64, device=dev) * ext[k]
+        if key == 'random_subvol':
+            quota = int(np.ceil(N * geometry.subvol_volume[0] / geometry.subvol_volume.sum()))
+            sl = torch.clamp(torch.arange(N, device=dev, dtype=torch.int64) // quota, max=S - 1).to(torch.float64)
+            u = torch.rand(N, generator=g, dtype=torch.float64, device=dev)
+            t[('px', 'py', 'pz')[ax]][:N] = lo[ax] + (sl + u) * (ext[ax] / S)
+            del sl, u
+        print('Assigning modes...')
+        act = torch.as_tensor(np.nonzero(~phonon.inactive_modes_mask.reshape(-1))[0].astype(np.int32), device=dev)
+        if self.particles_pmps >= 1:
+            idx = torch.arange(N, device=dev, dtype=torch.int64) % act.numel()
+        else:
+            idx = torch.randint(0, act.numel(), (N,), generator=g, device=dev)
+        t['mode'][:N] = act[idx]; t['omode'][:N] = act[idx]; t['mode'][N:] = -1
+        t['pid'][:N] = torch.arange(N, device=dev, dtype=torch.int64)
+        del idx
+        _, self.subvol_temperature = self.assign_temperatures(np.zeros(1, dtype=int), geometry)
+        eng.set_sv_temperature(self.subvol_temperature)
+        torch.cuda.synchronize(dev)
+        from ..engine import _dp
+        from .._lib import check
+        check(eng.ctx, eng.L.nk_set_slot_count(eng.ctx, N), 'nk_set_slot_count')
+        pos = torch.stack((t['px'][:N], t['py'][:N], t['pz'][:N]), dim=1).contiguous()
+        Tp = torch.empty(N, dtype=torch.float64, device=dev)
+        check(eng.ctx, eng.L.nk_particle_temperature(eng.ctx, N, _dp(pos), _dp(Tp)), 'nk_particle_temperature')
+        if self.temp_interp_type != 'nearest':      # initial occupation uses the subvolume temperature, not the interpolated one
+            sv = torch.empty(N, dtype=torch.int32, device=dev)
+            check(eng.ctx, eng.L.nk_classify(eng.ctx, N, _dp(pos), _dp(sv), None), 'nk_classify')
+            Tp = torch.as_tensor(self.subvol_temperature, device=dev)[sv.long()]
+        om = torch.as_tensor(phonon.omega.reshape(-1), device=dev)[t['mode'][:N].long()]
+        check(eng.ctx, eng.L.nk_occupation(eng.ctx, N, _dp(Tp), _dp(om), _dp(t['occ'])), 'nk_occupation')
+        del pos, Tp, om
+        print('Getting first boundary collisions...')
+        eng.set_timestep(0)
+        eng.init_collisions()
+        eng.sort_by_mode()
+        print('Initialising local quantities...')
+        self._device_census(geometry, phonon)
+
+    def _device_census(self, geometry, phonon):
+        """Initial per-subvolume counts / energies without pulling the particles to the host: every particle
+        starts at equilibrium with its subvolume, so the deviational energy and heat flux are zero and the
+        energy density is E(T_sv) (what Population.calculate_energy gives at start, Population.py:318-321)."""
+        import torch
+        eng = self.engine
+        n, _ = eng.slot_count()
+        t = eng.t
+        pos = torch.stack((t['px'][:n], t['py'][:n], t['pz'][:n]), dim=1).contiguous()
+        sv, counts = None, torch.zeros(self.n_of_subvols, dtype=torch.int64, device=eng.device)
+        from ..engine import _dp
+        from .._lib import check
+        svt = torch.empty(n, dtype=torch.int32, device=eng.device)
+        check(eng.ctx, eng.L.nk_classify(eng.ctx, n, _dp(pos), _dp(svt), _dp(counts)), 'nk_classify')
+        eng.synchronize()
+        self.subvol_N_p = counts.cpu().numpy()
+        self.N_p = int(self.subvol_N_p.sum())
+        self.subvol_energy = np.interp(self.subvol_temperature, phonon.T_array, phonon.energy_array)
+        self.subvol_heat_flux = np.zeros((self.n_of_subvols, 3))
+        self.total_energy = 0.0
+        self.calculate_kappa(geometry)
+        self.res_energy_balance = np.zeros(self.n_of_reservoirs)
+        self.res_heat_flux = np.zeros((self.n_of_reservoirs, 3))
+        self.N_leaving = np.zeros(self.n_of_reservoirs, dtype=int)
+
+    # ---- binary checkpoint (SURVEY 8f item 2): everything needed to continue bit-exactly ---------------------------
+    def save_checkpoint(self, path):
+        """Live particles (f64 positions, unlike the 1e-3 A text dump), collision clocks, reservoir counters,
+        subvolume temperatures, step counter and the Philox seed.  `np.savez` container."""
+        p = self.engine.particles(flush=True)
+        r = self.engine.results()
+        np.savez(path, ids=p['ids'], positions=p['positions'], modes=p['modes'], omega_modes=p['omega_modes'],
+                 occupation=p['occupation'], n_timesteps=p['n_timesteps'], collision_facets=p['collision_facets'],
+                 collision_positions=p['collision_positions'], res_counter=self.engine.res_counter(),
+                 subvol_temperature=np.asarray(self.subvol_temperature if self.current_timestep == 0 else r['subvol_temperature']),
+                 current_timestep=self.current_timestep, seed=self.seed)
+
+    def load_checkpoint(self, path):
+        z = np.load(path)
+        J = self.engine.J
+        if int(z['seed']) != self.seed:
+            raise Exception('checkpoint was written with seed {} but this run uses {}'.format(int(z['seed']), self.seed))
+        self.engine.set_tables(self.tables, res_counter=z['res_counter'].reshape(self.res_counter.shape))
+        self.engine.allocate(int(z['ids'].shape[0] * float(os.environ.get('NK_CAPACITY_FACTOR', 1.25))) + 1024)
+        self.engine.load_particles(z['positions'], z['modes'][:, 0] * J + z['modes'][:, 1], z['occupation'], ids=z['ids'],
+                                   omodes=z['omega_modes'], n_timesteps=z['n_timesteps'], collision_facets=z['collision_facets'],
+                                   collision_positions=z['collision_positions'])
+        self.subvol_temperature = z['subvol_temperature']
+        self.engine.set_sv_temperature(self.subvol_temperature)
+        self.current_timestep = int(z['current_timestep'])
+        self.t = self.current_timestep * self.dt
+        self.engine.set_timestep(self.current_timestep)
+        self._cache_key = None
 
     def assign_temperatures(self, subvol_id, geometry):
         """Initial subvolume temperatures for --temp_dist (Population.py:565-655)."""

@@ -97,3 +97,31 @@ def test_statistical_agreement_with_oracle(tmp_path):
     assert np.abs(pop.subvol_temperature - st.subvol_temperature).max() < 0.12
     fo, fg = np.mean(flux_o[5:], axis=0)[:3].mean(), np.mean(flux_g[5:], axis=0)[:3].mean()
     assert fo > 0 and abs(fg - fo) < 0.25 * fo
+
+
+def test_binary_checkpoint_continues_exactly(tmp_path):
+    """save_checkpoint at a convergence-row boundary, continue in a fresh Population: same particles as the
+    uninterrupted run (integers and positions identical, occupations to 1e-12: only the order of the sums
+    changes because the slots are compacted on load)."""
+    text = gen_golden.PARAMS_C1.format(eta=2, n=12000)
+    a = tmp_path / "a"; b = tmp_path / "b"
+    args, geo, ph, pop = _population(text, a, seed=21)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(20):
+            pop.run_timestep(geo, ph)
+        pop.save_checkpoint(os.path.join(tmp_path, "ckpt.npz"))
+        for _ in range(20):
+            pop.run_timestep(geo, ph)
+    args2, geo2, ph2, pop2 = _population(text, b, seed=21)
+    with contextlib.redirect_stdout(io.StringIO()):
+        pop2.load_checkpoint(os.path.join(tmp_path, "ckpt.npz"))
+        assert pop2.current_timestep == 20
+        for _ in range(20):
+            pop2.run_timestep(geo2, ph2)
+    p, q = pop._particles(), pop2._particles()
+    assert np.array_equal(p["ids"], q["ids"]) and np.array_equal(p["modes"], q["modes"])
+    assert np.array_equal(p["collision_facets"], q["collision_facets"])
+    assert np.array_equal(p["positions"], q["positions"]) and np.array_equal(p["n_timesteps"], q["n_timesteps"])
+    assert np.allclose(p["occupation"], q["occupation"], rtol=1e-12, atol=0)
+    assert np.allclose(pop.subvol_temperature, pop2.subvol_temperature, rtol=1e-13, atol=0)
+    assert np.array_equal(pop.engine.res_counter(), pop2.engine.res_counter())
