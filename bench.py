@@ -44,13 +44,30 @@ PARAMS = """
 """
 
 
+PARAMS_C1 = """
+--mat_folder {mat} --hdf_file synthetic:{mesh} --poscar_file POSCAR
+--geometry box --dimensions 5e3 1e3 1e3 --scale 1 1 1 --geo_rotation 0 0 0 xyz
+--subvolumes slice 10 0
+--bound_pos relative -0.1 0.5 0.5 1.1 0.5 0.5 0.5 0.5 -0.1 0.5 0.5 1.1
+--bound_cond T T R R P --connect_pos relative 0.5 -0.1 0.5 0.5 1.1 0.5
+--bound_values 302 298 {eta} {eta}
+--reference_temp local --temp_dist cold --temp_interp linear
+--particles total {n} --part_dist random_subvol --timestep 1 --iterations 1000
+--n_mean 10 --results_folder bench --conv_crit 0 10 --output screen --max_sim_time 0-00:00:00
+"""
+CASE = {"name": "c2"}
+
+
 def workload(n_total, mesh):
     """Geometry / Phonon / host set-up tables of the benchmark case (no GPU needed)."""
     import argument_parser as ap
     from nanokappa_b200.classes.Geometry import Geometry
     from nanokappa_b200.classes.Phonon import Phonon
     from nanokappa_b200.classes.Population import PopulationSetup
-    text = PARAMS.format(mat="/nonexistent_material_folder/", mesh=mesh, n=int(n_total))
+    if CASE["name"] == "c1":      # parameters_test.txt geometry (configs[0]): rough walls + linear T interpolation -> general kernel path
+        text = PARAMS_C1.format(mat="/nonexistent_material_folder/", mesh=mesh, n=int(n_total), eta=CASE.get("eta", 0))
+    else:
+        text = PARAMS.format(mat="/nonexistent_material_folder/", mesh=mesh, n=int(n_total))
     args = ap.initialise_parser(False).parse_args(text.split())
     args.results_folder = "/tmp"
     with contextlib.redirect_stdout(io.StringIO()):
@@ -219,12 +236,14 @@ def reference_arm(a):
 
 
 def config_dict(a, n_per_gpu, where):
-    return {"workload": "si_thin_film_crossplane: box (2e4 A)^3, T 302/298 K on x faces, periodic sides, 20 slice SVs, nearest T, dt 1 ps "
-                        "(BASELINE configs[1] geometry at configs[4] scale)",
-            "particles_per_gpu": int(n_per_gpu), "mode_table": f"synthetic {a.mesh}^3 x 6", "subvolumes": 20,
+    wl = ("si_thin_film_crossplane: box (2e4 A)^3, T 302/298 K on x faces, periodic sides, 20 slice SVs, nearest T, dt 1 ps "
+          "(BASELINE configs[1] geometry at configs[4] scale)") if CASE["name"] == "c2" else \
+         (f"parameters_test geometry: box 5e3x1e3x1e3 A, T/T/R/R/P, eta {CASE.get('eta', 0)} A, 10 slice SVs, linear T (BASELINE configs[0] scaled up; diagnostic)")
+    return {"workload": wl,
+            "particles_per_gpu": int(n_per_gpu), "mode_table": f"synthetic {a.mesh}^3 x 6", "subvolumes": 20 if CASE["name"] == "c2" else 10,
             "particle_order": "tiled modes (as initialised)" if getattr(a, "no_sort", False) else "sorted by mode at set-up",
             "l2_policy": "inputs larger than L2 (no flush)" if n_per_gpu * 44 > 2.6e8 else "state fits L2; L2 flushed between timed steps",
-            "parallelism": f"particle shards x{a.gpus}, per-step all-reduce of the per-SV vectors" if a.gpus > 1 else "single GPU"}
+            "parallelism": f"particle shards x{a.gpus}, per-step all-reduce of the per-SV vectors ({getattr(a, 'exchange', '?')})" if a.gpus > 1 else "single GPU"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -278,14 +297,14 @@ def gpu_arm(a):
     if not a.no_sort:
         eng.sort_by_mode()          # set-up-time layout choice: neighbours share mode records
 
-    acc_t = None
+    acc_t, fused = None, False
     if world > 1:
-        ptr = C.c_void_p(); ln = C.c_int64()
-        check(eng.ctx, eng.L.nk_acc_buffer(eng.ctx, C.byref(ptr), C.byref(ln)), "nk_acc_buffer")
-
-        class _Acc:
-            __cuda_array_interface__ = {"shape": (ln.value,), "typestr": "<f8", "data": (ptr.value, False), "version": 3}
-        acc_t = torch.as_tensor(_Acc(), device=dev)
+        from nanokappa_b200.parallel import ShardedEngine
+        sh = ShardedEngine(eng, rank, world)
+        acc_t = sh.acc
+        if not a.nccl:
+            fused = sh.enable_fused_exchange()       # in-kernel exchange over NVLink peer memory, NCCL as fall-back
+    a.exchange = "single GPU" if world == 1 else ("fused in-kernel all-reduce over NVLink peer memory" if fused else "NCCL all-reduce between the step halves")
 
     flush_buf = None
     if n * 44 <= 2.6e8:
@@ -294,7 +313,7 @@ def gpu_arm(a):
     def one_step():
         if flush_buf is not None:
             flush_buf.zero_()
-        if world > 1:
+        if world > 1 and not fused:
             eng.step_local()
             dist.all_reduce(acc_t)
             eng.step_finalize()
@@ -307,6 +326,7 @@ def gpu_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    barrier()                                   # ranks leave the host set-up at different times
     for _ in range(max(a.warmup, 3)):
         one_step()
     barrier()
@@ -371,7 +391,7 @@ def gpu_arm(a):
             "metric": "particle-timestep updates/s", "value": value, "unit": "updates/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(a, n, "gpu"),
-            "clocks": clocks, "gpu_launches": int((2 if world == 1 else 3) * a.steps),
+            "clocks": clocks, "gpu_launches": int((3 if (world == 1 or fused) else 4) * a.steps),
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                     "timesteps_per_call": 1, "calls": e2e["calls"], "api": e2e["api"]},
             "roofline": roofline, "cpu_baseline": cpu,
@@ -449,8 +469,12 @@ def main():
     p.add_argument("--cpu-steps", type=int, default=20)
     p.add_argument("--e2e-calls", type=int, default=3)
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--nccl", action="store_true", help="multi-GPU: use the NCCL all-reduce between the step halves instead of the fused exchange")
     p.add_argument("--no-sort", action="store_true", help="keep the tiled mode order of Population.initialise_modes")
+    p.add_argument("--case", default="c2", choices=["c2", "c1"], help="c2: README cross-plane film (headline); c1: parameters_test.txt geometry (diagnostic)")
+    p.add_argument("--eta", type=float, default=0.0, help="roughness of the R facets in --case c1")
     a = p.parse_args()
+    CASE["name"] = a.case; CASE["eta"] = a.eta
     if a.impl == "reference":
         reference_arm(a)
     else:

@@ -195,7 +195,10 @@ int nk_set_rank(nk_ctx* ctx, int rank, int world);
 int nk_acc_buffer(nk_ctx* ctx, double** dev_ptr, int64_t* n_doubles);
 int nk_step_local(nk_ctx* ctx);      /* kernels of one step up to the accumulators */
 int nk_step_finalize(nk_ctx* ctx);   /* accumulators -> T_sv, results; closes the step */
-/* fused exchange over NVLink peer memory: every rank exports its mailbox, imports the others */
+/* Fused exchange over NVLink peer memory (replaces the all-reduce above): every rank exports its mailbox as a
+ * 64-byte CUDA IPC handle, imports the handles of all ranks (own rank included, in rank order) and enables the
+ * exchange; nk_step then needs no collective: the block that closes a step stores the rank's sums into every
+ * mailbox, waits (bounded) for the peers' and adds them in rank order.  One box, <= 8 ranks. */
 int nk_comm_export(nk_ctx* ctx, void* handle_out_64B);
 int nk_comm_import(nk_ctx* ctx, int peer_rank, const void* handle_64B);
 int nk_comm_enable(nk_ctx* ctx, int enable);

@@ -476,7 +476,7 @@ __device__ __forceinline__ void nk_cp8(void* dst, const void* src) {
 }
 template <bool HAS_ROUGH, bool FAST, bool RELAX, bool FLUX>
 __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step_pf(NkP P) {
-    extern __shared__ __align__(16) unsigned char smraw[];
+    extern __shared__ __align__(128) unsigned char smraw[];
     NkPfStage* stage = reinterpret_cast<NkPfStage*>(smraw);
     double* sm = reinterpret_cast<double*>(smraw + 2 * sizeof(NkPfStage));
     NkSvSmem s = nk_load_sv(P, sm);
@@ -1043,6 +1043,44 @@ __device__ void nk_finalize_block(const NkP& P, double* sm) {
     }
 }
 
+// All-reduce (sum) of the accumulator vector across the ranks of one box, done by the block that closes the
+// step: every rank stores its vector straight into every peer's mailbox over NVLink (peer-mapped memory),
+// publishes a sequence number, waits for the peers' numbers and adds the world's vectors in rank order, so
+// all ranks get bit-identical sums without a separate collective launch.  Two mailbox parities: a rank can be
+// at most one step ahead of the slowest one.  The wait is bounded (~20 s): a missing peer raises NK_ERR_COMM
+// instead of hanging the GPU.
+__device__ void nk_exchange_sums(const NkP& P) {
+    const int len = nk_acc_len(P.S, P.R);
+    const int W = P.world;
+    const unsigned long long seq = (unsigned long long)(P.dyn->step + 1);
+    const int par = (int)(seq & 1ull);
+    for (int r = 0; r < W; ++r) {
+        double* dst = P.peer_mbox[r] + ((size_t)par * W + P.rank) * len;
+        for (int i = threadIdx.x; i < len; i += blockDim.x) dst[i] = __ldcg(P.acc + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < W) {
+        volatile unsigned long long* f = P.peer_flags[threadIdx.x] + (size_t)par * W + P.rank;
+        *f = seq;
+        __threadfence_system();
+        volatile unsigned long long* mine = P.flags_local + (size_t)par * W + threadIdx.x;
+        const long long t0 = clock64();
+        while (*mine != seq) {
+            if (clock64() - t0 > 40000000000LL) { atomicOr(&P.dyn->error, NK_ERR_COMM); break; }   // ~20 s
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        double sum = 0.0;
+        for (int r = 0; r < W; ++r) sum += *((volatile double*)(P.mbox_local + ((size_t)par * W + r) * len + i));
+        P.acc[i] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(1024) k_finalize(NkP P) {
     extern __shared__ double sm[];
     nk_finalize_block(P, sm);
@@ -1114,6 +1152,7 @@ __global__ void __launch_bounds__(NK_RARE_THREADS) k_rare(NkP P) {
         __syncthreads();
         if (s_last) {
             __threadfence();
+            if (P.comm_on) nk_exchange_sums(P);
             nk_finalize_block(P, sm_fin);
         }
     }
@@ -1165,7 +1204,9 @@ struct nk_ctx {
     bool force_tab = false;        // NK_STEP_TAB=force: use it regardless of the particle count (tests)
     bool tab_dirty = true;         // T_sv changed since k_mode_tables last ran
     long long h_slots_hint = 0;
-    int last_variant = 0;    // slot count at the last nk_set_slot_count
+    int last_variant = 0;
+    void* comm_block = nullptr;    // flags + mailboxes of the fused exchange
+    unsigned int comm_imported = 0;    // slot count at the last nk_set_slot_count
     bool profiling = false;
     long long h_step = 0;          // host mirror of NkDyn::step
     bool h_relax_pending = false;  // host mirror of NkDyn::relax_pending
@@ -1516,7 +1557,8 @@ int nk_get_slot_count(nk_ctx* ctx, int64_t* n_slots, int64_t* n_alive) {
     if (d.error) {
         ctx->err = std::string("device error bits: ") + ((d.error & NK_ERR_CAPACITY) ? "[particle capacity exhausted] " : "") +
                    ((d.error & NK_ERR_EVENTS) ? "[boundary event cap / broken periodic pair] " : "") +
-                   ((d.error & NK_ERR_CMAX) ? "[more than 64 copies of one mode emitted in a step] " : "");
+                   ((d.error & NK_ERR_CMAX) ? "[more than 64 copies of one mode emitted in a step] " : "") +
+                   ((d.error & NK_ERR_COMM) ? "[a peer rank did not deliver its sums within the time-out] " : "");
         return -2;
     }
     if (n_slots) *n_slots = d.n_slots;
@@ -1542,6 +1584,7 @@ int nk_set_timestep(nk_ctx* ctx, int64_t k) {
     NkDyn d; if (nk_read_dyn(ctx, &d)) return -1;
     d.step = k; d.relax_pending = 0;
     ctx->h_step = k; ctx->h_relax_pending = false;
+    if (ctx->comm_block) NK_CK(cudaMemset(ctx->comm_block, 0, 256));
     return nk_write_dyn(ctx, &d);
 }
 int nk_get_timestep(nk_ctx* ctx, int64_t* k) {
@@ -1727,9 +1770,10 @@ int nk_profile_end(nk_ctx* ctx, double* ms, int64_t* n_steps) {
 }
 
 int nk_step(nk_ctx* ctx, int n_steps) {
+    const bool fused = ctx->P.world == 1 || ctx->P.comm_on;      // otherwise the caller must all-reduce between the halves
+    if (!fused) { ctx->err = "nk_step with world > 1 needs nk_comm_enable; or use nk_step_local / all-reduce / nk_step_finalize"; return -1; }
     for (int k = 0; k < n_steps; ++k)
-        if (nk_step_kernels(ctx, ctx->P.world == 1)) return -1;
-        else if (ctx->P.world != 1 && nk_step_finalize(ctx)) return -1;
+        if (nk_step_kernels(ctx, true)) return -1;
     return 0;
 }
 
@@ -1827,8 +1871,54 @@ int nk_acc_buffer(nk_ctx* ctx, double** p, int64_t* n) {
     *p = ctx->P.acc; *n = nk_acc_len(ctx->P.S, ctx->P.R);
     return 0;
 }
-int nk_comm_export(nk_ctx* ctx, void*) { ctx->err = "fused peer exchange not built yet"; return -1; }
-int nk_comm_import(nk_ctx* ctx, int, const void*) { ctx->err = "fused peer exchange not built yet"; return -1; }
-int nk_comm_enable(nk_ctx* ctx, int) { ctx->err = "fused peer exchange not built yet"; return -1; }
+// ---- fused exchange over NVLink peer memory ---------------------------------------------------------------------
+int nk_comm_export(nk_ctx* ctx, void* handle_out) {
+    cudaSetDevice(ctx->device);
+    NkP& P = ctx->P;
+    if (!P.acc) { ctx->err = "set the tables first (accumulator length unknown)"; return -1; }
+    if (P.world < 1 || P.world > 8) { ctx->err = "fused exchange supports 1..8 ranks"; return -1; }
+    if (!ctx->comm_block) {
+        const size_t flag_bytes = 256;
+        const size_t bytes = flag_bytes + 2 * (size_t)P.world * nk_acc_len(P.S, P.R) * sizeof(double);
+        NK_CK(cudaMalloc(&ctx->comm_block, bytes));
+        NK_CK(cudaMemset(ctx->comm_block, 0, bytes));
+        ctx->owned.push_back(ctx->comm_block);
+        P.flags_local = reinterpret_cast<unsigned long long*>(ctx->comm_block);
+        P.mbox_local = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->comm_block) + flag_bytes);
+    }
+    cudaIpcMemHandle_t h;
+    NK_CK(cudaIpcGetMemHandle(&h, ctx->comm_block));
+    static_assert(sizeof(h) == 64, "IPC handle is 64 bytes");
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+int nk_comm_import(nk_ctx* ctx, int peer, const void* handle) {
+    cudaSetDevice(ctx->device);
+    NkP& P = ctx->P;
+    if (!ctx->comm_block) { ctx->err = "call nk_comm_export first"; return -1; }
+    if (peer < 0 || peer >= P.world) { ctx->err = "peer rank out of range"; return -1; }
+    void* base = ctx->comm_block;
+    if (peer != P.rank) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, sizeof(h));
+        NK_CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    P.peer_flags[peer] = reinterpret_cast<unsigned long long*>(base);
+    P.peer_mbox[peer] = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + 256);
+    ctx->comm_imported |= 1u << peer;
+    return 0;
+}
+
+int nk_comm_enable(nk_ctx* ctx, int enable) {
+    NkP& P = ctx->P;
+    if (enable) {
+        if (P.world > 1 && ctx->comm_imported != (1u << P.world) - 1u) { ctx->err = "not every peer mailbox has been imported"; return -1; }
+        P.comm_on = P.world > 1 ? 1 : 0;
+    } else {
+        P.comm_on = 0;
+    }
+    return 0;
+}
 
 }  // extern "C"

@@ -55,6 +55,7 @@ struct NkDyn {                   // device-resident, mutated by kernels
 #define NK_ERR_CAPACITY 1        // emission ran out of slots
 #define NK_ERR_EVENTS   2        // a particle exceeded the per-step event cap
 #define NK_ERR_CMAX     4        // a mode emitted more than NK_EMIT_CMAX copies in one step
+#define NK_ERR_COMM     8        // a peer did not deliver its sums in time (fused exchange)
 
 struct NkP {
     // ---- mesh
@@ -110,6 +111,12 @@ struct NkP {
     double* out;                      // results block, see NK_OUT_* offsets
     NkDyn* dyn;
     int rank, world;
+    // ---- fused exchange of the accumulator vector over NVLink peer memory (nk_comm_*)
+    int comm_on;                      // 1: the last block of k_rare all-reduces P.acc through the mailboxes
+    double* mbox_local;               // [2][world][acc_len] written by the peers (parity, sender)
+    unsigned long long* flags_local;  // [2][world] sequence numbers written by the peers
+    double* peer_mbox[8];             // every rank's mailbox (own entry = mbox_local)
+    unsigned long long* peer_flags[8];
 };
 
 // accumulator layout (all double so that ONE f64 all-reduce covers it)

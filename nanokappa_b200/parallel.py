@@ -48,9 +48,45 @@ class ShardedEngine:
             __cuda_array_interface__ = {"shape": (ln.value,), "typestr": "<f8", "data": (ptr.value, False), "version": 3}
         self.acc = torch.as_tensor(_Acc(), device=engine.device)
 
+        self.fused = False
+        self._synced = False
+
+    def enable_fused_exchange(self):
+        """Replace the per-step NCCL all-reduce by the in-kernel exchange: every rank exports its mailbox as a
+        CUDA IPC handle, imports the peers' (NVLink peer mapping) and from then on the block that closes a step
+        stores the rank's sums into all mailboxes, waits for the peers and adds them in rank order
+        (csrc: nk_exchange_sums).  Returns False (and keeps NCCL) if peer mapping is not available."""
+        if self.world == 1:
+            return False
+        eng = self.engine
+        mine = (C.c_ubyte * 64)()
+        try:
+            check(eng.ctx, eng.L.nk_comm_export(eng.ctx, mine), "nk_comm_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine), group=self.group)
+            for r, h in enumerate(handles):
+                buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                check(eng.ctx, eng.L.nk_comm_import(eng.ctx, r, buf), "nk_comm_import")
+            check(eng.ctx, eng.L.nk_comm_enable(eng.ctx, 1), "nk_comm_enable")
+            ok = 1
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], device=eng.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)      # all ranks or none
+        self.fused = bool(flag.item())
+        if not self.fused:
+            eng.L.nk_comm_enable(eng.ctx, 0)
+        return self.fused
+
     def step(self, n=1):
+        if self.fused and not self._synced:
+            torch.cuda.synchronize(self.engine.device)
+            dist.barrier(group=self.group)      # the in-kernel wait is bounded: start the first step together
+            self._synced = True
+        if self.fused or self.world == 1:
+            self.engine.step(n)
+            return
         for _ in range(int(n)):
             self.engine.step_local()
-            if self.world > 1:
-                dist.all_reduce(self.acc, group=self.group)
+            dist.all_reduce(self.acc, group=self.group)
             self.engine.step_finalize()
