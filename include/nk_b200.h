@@ -174,6 +174,14 @@ int nk_get_results(nk_ctx* ctx, double* T_sv, double* E_sv, int64_t* N_sv, doubl
 
 /* Population.contains_check (Population.py:1712-1722): not yet on the GPU path. */
 
+/* ---- set-up helper (no ctx) ------------------------------------------------------------------------------------ */
+
+/* Phonon.initialise_temperature_function's energy table (Phonon.py:352-384) on the device: out[i] =
+ * sum over active modes of hbar*omega*n0(T[i], omega) / dens_norm + zero_point.  Host pointers; omega, active (M).
+ * The sum order differs from NumPy's (1e-16 relative).  Error text: nk_last_error(NULL). */
+int nk_energy_table(int device, int n_modes, const double* omega, const uint8_t* active, int nT, const double* T,
+                    double hbar, double kb, double dens_norm, double zero_point, double* out);
+
 /* ---- host-buffer end-to-end call ---------------------------------------------------------------- */
 
 /* Upload n particles (host SoA, pinned or pageable), run n_steps, download the state and the per-SV

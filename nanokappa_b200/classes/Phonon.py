@@ -233,15 +233,41 @@ class Phonon(Constants):
             if os.path.isfile(path):
                 self.energy_array = np.load(path)
                 return
-        chunk = max(1, int(4e6 // max(1, self.number_of_modes)))
-        parts = [self.calculate_crystal_energy(self.T_array[i:i + chunk]) for i in range(0, self.T_array.shape[0], chunk)]
-        self.energy_array = np.concatenate(parts).reshape(-1)
+        self.energy_array = self._energy_table_device() if self.number_of_modes * self.T_array.shape[0] >= 2e8 else None
+        if self.energy_array is None:
+            chunk = max(1, int(4e6 // max(1, self.number_of_modes)))
+            parts = [self.calculate_crystal_energy(self.T_array[i:i + chunk]) for i in range(0, self.T_array.shape[0], chunk)]
+            self.energy_array = np.concatenate(parts).reshape(-1)
         if path:
             try:
                 os.makedirs(cache, exist_ok=True)
                 np.save(path, self.energy_array)
             except OSError:
                 pass
+
+    def _energy_table_device(self):
+        """Large tables (31^3 x 6 modes x 10 001 temperatures = 1.8e9 exponentials, ~40 s in NumPy) are summed
+        by the CUDA library when a GPU is visible; None -> caller falls back to the NumPy evaluation."""
+        if os.environ.get('NK_ENERGY_TABLE', 'auto') == 'host':
+            return None
+        try:
+            import ctypes as C
+            import torch
+            if not torch.cuda.is_available():
+                return None
+            from .. import _lib
+            L = _lib.lib()
+            dev = int(os.environ.get('LOCAL_RANK', 0)) % max(torch.cuda.device_count(), 1)
+            om = np.ascontiguousarray(self.omega.reshape(-1), dtype=np.float64)
+            act = np.ascontiguousarray(~self.inactive_modes_mask.reshape(-1), dtype=np.uint8)
+            T = np.ascontiguousarray(self.T_array, dtype=np.float64)
+            out = np.zeros(T.shape[0])
+            p = lambda a: a.ctypes.data_as(C.c_void_p)
+            rc = L.nk_energy_table(dev, om.shape[0], p(om), p(act), T.shape[0], p(T), float(self.hbar), float(self.kb),
+                                   float(self.number_of_qpoints * self.volume_unitcell), float(self.zero_point), p(out))
+            return out if rc == 0 else None
+        except Exception:
+            return None
 
     def temperature_function(self, E):
         if self.engine is not None:

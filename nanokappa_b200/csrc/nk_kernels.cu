@@ -1871,6 +1871,54 @@ int nk_acc_buffer(nk_ctx* ctx, double** p, int64_t* n) {
     *p = ctx->P.acc; *n = nk_acc_len(ctx->P.S, ctx->P.R);
     return 0;
 }
+// ---- set-up helper: E(T) table of Phonon.initialise_temperature_function on the device --------------------------
+// crystal_energy(T) = sum_active hbar*omega*n0(T, omega) / (Q V_uc) + zero_point   (Phonon.py:352-362).  One block per
+// temperature, f64 tree reduction (the order of the sum differs from NumPy's pairwise sum: ~1e-16 relative).
+__global__ void __launch_bounds__(256) k_energy_table(int M, const double* __restrict__ omega, const unsigned char* __restrict__ active,
+                                                      int nT, const double* __restrict__ T, double hbar, double kb, double dens_norm,
+                                                      double zero_point, double* __restrict__ out) {
+    __shared__ double red[256];
+    for (int it = blockIdx.x; it < nT; it += gridDim.x) {
+        const double Tk = T[it];
+        double acc = 0.0;
+        for (int m = threadIdx.x; m < M; m += blockDim.x) {
+            const double w = omega[m];
+            if (active[m] && Tk > 0.0 && w > 0.0) {
+                const double x = nk_div(nk_mul(w, hbar), nk_mul(Tk, kb));
+                acc += nk_mul(nk_mul(hbar, w), nk_div(1.0, nk_sub(exp(x), 1.0)));
+            }
+        }
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[it] = nk_add(nk_div(red[0], dens_norm), zero_point);
+        __syncthreads();
+    }
+}
+
+int nk_energy_table(int device, int M, const double* omega, const uint8_t* active, int nT, const double* T, double hbar, double kb,
+                    double dens_norm, double zero_point, double* out) {
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_err = "nk_energy_table: no such CUDA device"; return -1; }
+    double *d_w = nullptr, *d_T = nullptr, *d_o = nullptr; unsigned char* d_a = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t c) { if (e == cudaSuccess) e = c; return c == cudaSuccess; };
+    ok(cudaMalloc(&d_w, (size_t)M * 8)); ok(cudaMalloc(&d_a, (size_t)M)); ok(cudaMalloc(&d_T, (size_t)nT * 8)); ok(cudaMalloc(&d_o, (size_t)nT * 8));
+    if (e == cudaSuccess) {
+        ok(cudaMemcpy(d_w, omega, (size_t)M * 8, cudaMemcpyHostToDevice));
+        ok(cudaMemcpy(d_a, active, (size_t)M, cudaMemcpyHostToDevice));
+        ok(cudaMemcpy(d_T, T, (size_t)nT * 8, cudaMemcpyHostToDevice));
+        k_energy_table<<<std::min(nT, 148 * 8), 256>>>(M, d_w, d_a, nT, d_T, hbar, kb, dens_norm, zero_point, d_o);
+        ok(cudaGetLastError());
+        ok(cudaMemcpy(out, d_o, (size_t)nT * 8, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_w); cudaFree(d_a); cudaFree(d_T); cudaFree(d_o);
+    if (e != cudaSuccess) { g_create_err = std::string("nk_energy_table: ") + cudaGetErrorString(e); return -1; }
+    return 0;
+}
+
 // ---- fused exchange over NVLink peer memory ---------------------------------------------------------------------
 int nk_comm_export(nk_ctx* ctx, void* handle_out) {
     cudaSetDevice(ctx->device);

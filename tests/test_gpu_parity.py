@@ -250,3 +250,19 @@ def test_step_kernel_variants_agree(name, golden_dir, monkeypatch):
             assert np.array_equal(p[f], p0[f], equal_nan=True), f"{label}: {f} differs from the direct kernel"
         assert np.array_equal(r["subvol_N_p"], r0["subvol_N_p"])
         _close(f"{label} T_sv", r["subvol_temperature"], r0["subvol_temperature"], 1e-13)
+
+
+def test_energy_table_on_device_matches_numpy(golden_dir):
+    """Set-up helper nk_energy_table against Phonon.calculate_crystal_energy (NumPy) and the reference's table."""
+    import ctypes as C
+    from nanokappa_b200 import _lib
+    tb, st, _ = _load("c2_crossplane", golden_dir)
+    L = _lib.lib()
+    om = np.ascontiguousarray(tb["omega"].reshape(-1)); act = np.ascontiguousarray((np.abs(tb["group_vel"]).sum(axis=2) != 0).reshape(-1), dtype=np.uint8)
+    T = np.ascontiguousarray(tb["T_array"]); out = np.zeros_like(T)
+    Q = tb["omega"].shape[0]
+    zero = tb["hbar"] * tb["omega"].sum() / 2 / (Q * tb["volume_unitcell"])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = L.nk_energy_table(0, om.shape[0], p(om), p(act), T.shape[0], p(T), tb["hbar"], tb["kb"], Q * tb["volume_unitcell"], zero, p(out))
+    assert rc == 0, L.nk_last_error(None)
+    _close("E(T) table", out, tb["energy_array"], 1e-13)
