@@ -185,12 +185,20 @@ int nk_energy_table(int device, int n_modes, const double* omega, const uint8_t*
 /* ---- host-buffer end-to-end call ---------------------------------------------------------------- */
 
 /* Upload n particles (host SoA, pinned or pageable), run n_steps, download the state and the per-SV
- * results.  This is the call bench.py times as `e2e`: host<->device copies are inside it. */
+ * results.  This is the call bench.py times as `e2e`: host<->device copies are inside it.
+ * The host arrays are the caller's copy of Population's particle arrays (Population.py:1724-1800 reads and writes
+ * self.positions, self.n_timesteps, self.occupation, self.modes, ... in place); on return they hold the state after
+ * the step(s).  For one step of >= 2^20 particles the call is pipelined: slots are cut into chunks, chunk c+1 is
+ * uploaded while chunk c streams through the kernel and chunk c-1's positions/clocks are downloaded; arrays the
+ * streaming kernel never writes come back as a packed patch of the slots the rare path touched (NK_HOST_PIPELINE=0
+ * selects the plain upload-all / step / download-all sequence; both leave identical host arrays). */
 int nk_advance_host(nk_ctx* ctx, int64_t n_in, int n_steps,
                     double* px, double* py, double* pz, double* tc, double* occ,
                     int32_t* mode, int32_t* omode, int32_t* cfacet,
                     double* cx, double* cy, double* cz, int64_t* pid,
                     int64_t* n_out, double* T_sv_out, double* E_sv_out, int64_t* N_sv_out);
+/* Bytes the last nk_advance_host call moved over PCIe in each direction (counted from the copies it issued). */
+int nk_last_transfer_bytes(nk_ctx* ctx, int64_t* h2d, int64_t* d2h);
 
 /* ---- multi-GPU ------------------------------------------------------------------------------------ */
 

@@ -20,6 +20,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <chrono>
+#include <thread>
 #include <vector>
 #include <cmath>
 #include <cstdlib>
@@ -421,13 +423,13 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step(Nk
     for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0; binC[i] = 0u; for (int k = 0; k < 3; ++k) binF[3 * i + k] = 0; for (int k = 0; k < 4; ++k) binX[4 * i + k] = 0.0; }
     __syncthreads();
 
-    nk_emit_scan(P);
-    const long long n = P.dyn->n_slots;
+    if (P.scan_emit) nk_emit_scan(P);
+    const long long n = min((long long)P.dyn->n_slots, P.slot_hi);
     const unsigned int lane = threadIdx.x & 31u;
 
     // the loop bound is WARP-uniform (lane 0's index) because the hit-list append uses full-mask warp
     // votes; lanes past the end carry dead slots
-    for (long long wbase = 2 * ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); wbase < n;
+    for (long long wbase = P.slot_lo + 2 * ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); wbase < n;
          wbase += 2 * (long long)gridDim.x * blockDim.x) {
         const long long base = wbase + 2 * lane;
         const bool inb = base < n;
@@ -629,10 +631,10 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step_ta
     for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0; binC[i] = 0u; for (int k = 0; k < 3; ++k) binF[3 * i + k] = 0; for (int k = 0; k < 4; ++k) binX[4 * i + k] = 0.0; }
     __syncthreads();
 
-    nk_emit_scan(P);
-    const long long n = P.dyn->n_slots;
+    if (P.scan_emit) nk_emit_scan(P);
+    const long long n = min((long long)P.dyn->n_slots, P.slot_hi);
     const unsigned int lane = threadIdx.x & 31u;
-    for (long long wbase = 2 * ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); wbase < n;
+    for (long long wbase = P.slot_lo + 2 * ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); wbase < n;
          wbase += 2 * (long long)gridDim.x * blockDim.x) {
         const long long base = wbase + 2 * lane;
         const bool inb = base < n;
@@ -931,6 +933,10 @@ __device__ __forceinline__ void nk_emit_entry(const NkP& P, const NkGeo& G, doub
         if (slot < 0) continue;
         nk_store_particle(P, slot, p);
         P.pid[slot] = p.id;
+        {
+            const unsigned int k = atomicAdd(&P.dyn->n_new, 1u);
+            if ((long long)k < P.newslots_cap) P.newslots[k] = (int)slot;
+        }
         nk_accumulate(P, acc, p, with_flux);
     }
 }
@@ -1036,8 +1042,10 @@ __device__ void nk_finalize_block(const NkP& P, double* sm) {
         NkDyn* d = P.dyn;
         d->step = step_done;
         d->relax_pending = 1;
+        d->last_hits = d->n_hits; d->last_new = d->n_new;
         d->n_hits = 0;
         d->n_emit = 0;
+        d->n_new = 0;
         d->fr_snap = d->fr_tail;           // slots freed in this step become recyclable from the next one
         d->blocks_done = 0;
     }
@@ -1182,6 +1190,25 @@ __global__ void __launch_bounds__(256) k_flush_relax(NkP P) {
 }
 __global__ void k_clear_relax(NkP P) { P.dyn->relax_pending = 0; }
 
+// Host-buffer pipeline: the slots the rare path touched in the step just closed (hit list + emitted slots) are
+// packed into a small patch so that the host does not have to download the cold arrays of all particles again.
+struct NkPatch {                  // structure of arrays, `cap` records each
+    int *slot, *mode, *omode, *cfacet; long long* pid;
+    double *x, *y, *z, *tc, *cx, *cy, *cz;
+};
+__global__ void __launch_bounds__(256) k_pack_dirty(NkP P, NkPatch out, long long cap, unsigned int* count) {
+    const unsigned int nh = P.dyn->last_hits, nn = P.dyn->last_new;
+    const unsigned long long total = (unsigned long long)nh + nn;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { count[0] = nh; count[1] = nn; }
+    if ((long long)total > cap || (long long)nn > P.newslots_cap) return;       // host falls back to a full download
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const int s = i < nh ? P.hitlist[i] : P.newslots[i - nh];
+        out.slot[i] = s; out.mode[i] = P.mode[s]; out.omode[i] = P.omode[s]; out.cfacet[i] = P.cfacet[s]; out.pid[i] = P.pid[s];
+        out.x[i] = P.px[s]; out.y[i] = P.py[s]; out.z[i] = P.pz[s]; out.tc[i] = P.tc[s];
+        out.cx[i] = P.cx[s]; out.cy[i] = P.cy[s]; out.cz[i] = P.cz[s];
+    }
+}
+
 // =================================================================================================
 // host side
 // =================================================================================================
@@ -1205,6 +1232,13 @@ struct nk_ctx {
     bool tab_dirty = true;         // T_sv changed since k_mode_tables last ran
     long long h_slots_hint = 0;
     int last_variant = 0;
+    // chunked host-buffer pipeline (nk_advance_host)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_k;
+    void* patch_dev = nullptr; void* patch_host = nullptr; long long patch_cap = 0;
+    unsigned int* patch_count_dev = nullptr;
+    bool use_pipeline = true;      // NK_HOST_PIPELINE=0 disables it
+    long long xfer_h2d = 0, xfer_d2h = 0;   // bytes of the last nk_advance_host call
     void* comm_block = nullptr;    // flags + mailboxes of the fused exchange
     unsigned int comm_imported = 0;    // slot count at the last nk_set_slot_count
     bool profiling = false;
@@ -1274,6 +1308,8 @@ int nk_create(int device, nk_ctx** out) {
     cudaGetDeviceProperties(&prop, device);
     ctx->n_sm = prop.multiProcessorCount;
     ctx->P.world = 1;
+    ctx->P.slot_lo = 0; ctx->P.slot_hi = 0x7fffffffffffffffLL; ctx->P.scan_emit = 1;
+    if (const char* e = getenv("NK_HOST_PIPELINE")) ctx->use_pipeline = strcmp(e, "0") != 0;
     if (const char* e = getenv("NK_STEP_TAB")) { ctx->use_tab = strcmp(e, "0") != 0; ctx->force_tab = !strcmp(e, "force"); }
     if (const char* e = getenv("NK_STEP_IMPL")) ctx->step_variant = !strcmp(e, "tma") ? 1 : (!strcmp(e, "ldg1") ? 2 : (!strcmp(e, "pf") ? 3 : 0));
     NkDyn z; memset(&z, 0, sizeof(z));
@@ -1288,6 +1324,12 @@ void nk_destroy(nk_ctx* ctx) {
     cudaDeviceSynchronize();
     for (void* p : ctx->owned) cudaFree(p);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_k) cudaEventDestroy(e);
+    if (ctx->s_in) { cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out); }
+    if (ctx->patch_dev) cudaFree(ctx->patch_dev);
+    if (ctx->patch_host) cudaFreeHost(ctx->patch_host);
+    if (ctx->patch_count_dev) cudaFree(ctx->patch_count_dev);
     delete ctx;
 }
 
@@ -1471,6 +1513,8 @@ int nk_set_reservoirs(nk_ctx* ctx, int R, const int32_t* res_facet, const double
     NK_UP(dd, double, enter_prob, (size_t)R * P.M); P.enter_prob = dd;
     NK_UP(dd, double, res_counter, (size_t)R * P.M); P.res_counter = dd;
     int2* de; NK_UP(de, int2, (const int2*)nullptr, (size_t)std::max(R, 1) * P.M); P.emitlist = de;
+    P.newslots_cap = (long long)std::max(R, 1) * P.M * 2;
+    int* dn; NK_UP(dn, int, (const int*)nullptr, (size_t)P.newslots_cap); P.newslots = dn;
     return nk_alloc_scratch(ctx);
 }
 
@@ -1538,7 +1582,7 @@ int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots) {
     if (n_slots < 0 || n_slots > ctx->P.cap) { ctx->err = "n_slots out of range"; return -1; }
     NkDyn d; if (nk_read_dyn(ctx, &d)) return -1;
     ctx->h_slots_hint = n_slots;
-    d.n_slots = n_slots; d.fr_head = d.fr_tail = d.fr_snap = 0; d.n_hits = 0; d.n_emit = 0; d.blocks_done = 0;
+    d.n_slots = n_slots; d.fr_head = d.fr_tail = d.fr_snap = 0; d.n_hits = 0; d.n_emit = 0; d.n_new = 0; d.last_hits = 0; d.last_new = 0; d.blocks_done = 0;
     if (nk_write_dyn(ctx, &d)) return -1;
     unsigned long long* dc; NK_CK(cudaMalloc(&dc, 8)); NK_CK(cudaMemset(dc, 0, 8));
     k_count_alive<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->P, dc);
@@ -1672,8 +1716,12 @@ int nk_init_collisions(nk_ctx* ctx) {
 
 static size_t nk_step_smem(const NkP& P) { return (nk_sv_smem_doubles(P.S) + 8 * (size_t)P.S) * 8 + ((size_t)P.S + 2) * 4 + nk_hot_smem_bytes(P.S) + 32; }
 
+// chunked launch of the streaming kernel for the host-buffer pipeline: chunk c waits for its upload event and
+// signals its own completion event
+struct NkChunkPlan { int n; long long chunk, total; cudaEvent_t* ev_in; cudaEvent_t* ev_k; };
+
 // kernels of one step; fuse_finalize: the last block of k_rare closes the step (no collective in between)
-static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize) {
+static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* plan = nullptr) {
     cudaSetDevice(ctx->device);
     if (nk_check_ready(ctx)) return -1;
     const NkP& P = ctx->P;
@@ -1707,7 +1755,20 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize) {
         ctx->step_blocks_variant = variant;
     }
     nk_prof_mark(ctx);
-    kern<<<ctx->step_blocks, NK_STEP_THREADS, smem, ctx->stream>>>(P);
+    if (!plan) {
+        kern<<<ctx->step_blocks, NK_STEP_THREADS, smem, ctx->stream>>>(P);
+    } else {
+        if (variant != 0 && variant != 4) { ctx->err = "chunked launch needs the direct or table step kernel"; return -1; }
+        for (int c = 0; c < plan->n; ++c) {
+            NkP Pc = P;
+            Pc.slot_lo = (long long)c * plan->chunk;
+            Pc.slot_hi = std::min(Pc.slot_lo + plan->chunk, plan->total);
+            Pc.scan_emit = c == 0;
+            NK_CK(cudaStreamWaitEvent(ctx->stream, plan->ev_in[c], 0));
+            kern<<<ctx->step_blocks, NK_STEP_THREADS, smem, ctx->stream>>>(Pc);
+            NK_CK(cudaEventRecord(plan->ev_k[c], ctx->stream));
+        }
+    }
     NK_CK(cudaGetLastError());
     nk_prof_mark(ctx);
     const size_t fin_smem = (3 * (size_t)P.S + nk_acc_len(P.S, P.R)) * 8;
@@ -1811,13 +1872,11 @@ int nk_get_results(nk_ctx* ctx, double* T_sv, double* E_sv, int64_t* N_sv, doubl
     return 0;
 }
 
-int nk_advance_host(nk_ctx* ctx, int64_t n_in, int n_steps, double* px, double* py, double* pz, double* tc, double* occ,
-                    int32_t* mode, int32_t* omode, int32_t* cfacet, double* cx, double* cy, double* cz, int64_t* pid,
-                    int64_t* n_out, double* T_sv_out, double* E_sv_out, int64_t* N_sv_out) {
-    cudaSetDevice(ctx->device);
-    if (nk_check_ready(ctx)) return -1;
+// Plain version: upload everything, step, download everything.
+static int nk_advance_host_simple(nk_ctx* ctx, int64_t n_in, int n_steps, double* px, double* py, double* pz, double* tc, double* occ,
+                                  int32_t* mode, int32_t* omode, int32_t* cfacet, double* cx, double* cy, double* cz, int64_t* pid,
+                                  int64_t* n_out) {
     NkP& P = ctx->P;
-    if (n_in > P.cap) { ctx->err = "n_in exceeds bound capacity"; return -1; }
     cudaStream_t st = ctx->stream;
     size_t n = (size_t)n_in;
     NK_CK(cudaMemcpyAsync(P.px, px, n * 8, cudaMemcpyHostToDevice, st));
@@ -1851,8 +1910,185 @@ int nk_advance_host(nk_ctx* ctx, int64_t n_in, int n_steps, double* px, double* 
     NK_CK(cudaMemcpyAsync(cz, P.cz, m * 8, cudaMemcpyDeviceToHost, st));
     NK_CK(cudaMemcpyAsync(pid, P.pid, m * 8, cudaMemcpyDeviceToHost, st));
     NK_CK(cudaStreamSynchronize(st));
+    ctx->xfer_h2d = (long long)n * 84; ctx->xfer_d2h = (long long)m * 84;
     if (n_out) *n_out = ns;
+    return 0;
+}
+
+// Pipelined single-step version: the slots are cut into chunks; chunk c+1 is uploaded (stream s_in) while chunk c
+// runs through the streaming kernel (ctx stream) and the positions / collision clocks of chunk c-1 are downloaded
+// (stream s_out), so the PCIe link works in both directions at once.  The arrays k_step never writes (modes,
+// collision data, ids) are not downloaded again: the few slots the rare path touched come back as a packed patch
+// that is applied to the host arrays.  Occupations are downloaded after the deferred relaxation has been flushed.
+#define NK_PIPE_CHUNKS 16
+static int nk_advance_host_pipelined(nk_ctx* ctx, int64_t n_in, double* px, double* py, double* pz, double* tc, double* occ,
+                                     int32_t* mode, int32_t* omode, int32_t* cfacet, double* cx, double* cy, double* cz, int64_t* pid,
+                                     int64_t* n_out) {
+    NkP& P = ctx->P;
+    cudaStream_t st = ctx->stream;
+    if (!ctx->s_in) {
+        NK_CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        NK_CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        ctx->ev_in.resize(NK_PIPE_CHUNKS); ctx->ev_k.resize(NK_PIPE_CHUNKS);
+        for (int c = 0; c < NK_PIPE_CHUNKS; ++c) {
+            NK_CK(cudaEventCreateWithFlags(&ctx->ev_in[c], cudaEventDisableTiming));
+            NK_CK(cudaEventCreateWithFlags(&ctx->ev_k[c], cudaEventDisableTiming));
+        }
+        NK_CK(cudaMalloc(&ctx->patch_count_dev, 2 * sizeof(unsigned int)));
+    }
+    long long want = std::max<long long>(1 << 16, P.cap / 64);
+    if (const char* e = getenv("NK_PIPE_PATCH_CAP")) want = std::max<long long>(1, atoll(e));     // tests: force the fallback
+    if (ctx->patch_cap != want) {
+        if (ctx->patch_dev) cudaFree(ctx->patch_dev);
+        if (ctx->patch_host) cudaFreeHost(ctx->patch_host);
+        NK_CK(cudaMalloc(&ctx->patch_dev, (size_t)want * 80));
+        NK_CK(cudaMallocHost(&ctx->patch_host, (size_t)want * 80));
+        ctx->patch_cap = want;
+    }
+    const long long cap = ctx->patch_cap;
+    auto carve = [&](void* base) {
+        NkPatch q; char* b = (char*)base;
+        q.x = (double*)b; q.y = q.x + cap; q.z = q.y + cap; q.tc = q.z + cap; q.cx = q.tc + cap; q.cy = q.cx + cap; q.cz = q.cy + cap;
+        q.pid = (long long*)(q.cz + cap); q.slot = (int*)(q.pid + cap); q.mode = q.slot + cap; q.omode = q.mode + cap; q.cfacet = q.omode + cap;
+        return q;
+    };
+    const NkPatch pd = carve(ctx->patch_dev), ph = carve(ctx->patch_host);
+
+    const size_t n = (size_t)n_in;
+    NK_CK(cudaStreamSynchronize(st));
+    static const bool trace = getenv("NK_PIPE_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (trace) fprintf(stderr, "[nk pipe] %-10s %8.2f ms\n", what,
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    };
+    // 1. the slot census needs the modes
+    NK_CK(cudaMemcpyAsync(P.mode, mode, n * 4, cudaMemcpyHostToDevice, ctx->s_in));
+    NK_CK(cudaStreamSynchronize(ctx->s_in));
+    if (nk_set_slot_count(ctx, n_in)) return -1;
+    lap("census");
+    // 2. uploads, chunk by chunk
+    long long chunk = ((long long)n_in + NK_PIPE_CHUNKS - 1) / NK_PIPE_CHUNKS;
+    chunk = (chunk + 511) / 512 * 512;
+    const int nc = (int)(((long long)n_in + chunk - 1) / chunk);
+    for (int c = 0; c < nc; ++c) {
+        const size_t lo = (size_t)c * chunk, len = std::min<size_t>(chunk, n - lo);
+        NK_CK(cudaMemcpyAsync(P.px + lo, px + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.py + lo, py + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.pz + lo, pz + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.tc + lo, tc + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.occ + lo, occ + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.omode + lo, omode + lo, len * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.cfacet + lo, cfacet + lo, len * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.cx + lo, cx + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.cy + lo, cy + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.cz + lo, cz + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.pid + lo, pid + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+    }
+    // 3. streaming kernel per chunk + rare path + finalize on the ctx stream
+    NkChunkPlan plan{nc, chunk, (long long)n_in, ctx->ev_in.data(), ctx->ev_k.data()};
+    if (nk_step_kernels(ctx, true, &plan)) return -1;
+    // 4. positions and clocks of every chunk go back as soon as its kernel is done (stale for the few slots the
+    //    rare path rewrites afterwards: the patch below overrides them)
+    for (int c = 0; c < nc; ++c) {
+        const size_t lo = (size_t)c * chunk, len = std::min<size_t>(chunk, n - lo);
+        NK_CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_k[c], 0));
+        NK_CK(cudaMemcpyAsync(px + lo, P.px + lo, len * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        NK_CK(cudaMemcpyAsync(py + lo, P.py + lo, len * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        NK_CK(cudaMemcpyAsync(pz + lo, P.pz + lo, len * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        NK_CK(cudaMemcpyAsync(tc + lo, P.tc + lo, len * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    // 5. tail: flush the deferred relaxation, pack the dirty slots
+    if (nk_flush_relaxation(ctx)) return -1;
+    k_pack_dirty<<<ctx->n_sm * 4, 256, 0, st>>>(P, pd, cap, ctx->patch_count_dev);
+    NK_CK(cudaGetLastError());
+    unsigned int cnt[2] = {0, 0};
+    NK_CK(cudaMemcpyAsync(cnt, ctx->patch_count_dev, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    lap("enqueued");
+    NK_CK(cudaStreamSynchronize(st));
+    lap("kernels");
+    int64_t ns = 0, na = 0;
+    if (nk_get_slot_count(ctx, &ns, &na)) return -1;
+    const size_t m = (size_t)ns;
+    const long long nd = (long long)cnt[0] + cnt[1];
+    const bool patch_ok = nd <= cap && (long long)cnt[1] <= P.newslots_cap;
+    // the (small) patch first, on s_out; the occupations follow on the ctx stream while the host applies the patch
+    if (patch_ok) {
+        const size_t k = (size_t)nd;
+        double* const dsrc[7] = {pd.x, pd.y, pd.z, pd.tc, pd.cx, pd.cy, pd.cz};
+        double* const ddst[7] = {ph.x, ph.y, ph.z, ph.tc, ph.cx, ph.cy, ph.cz};
+        for (int a = 0; a < 7; ++a) NK_CK(cudaMemcpyAsync(ddst[a], dsrc[a], k * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        NK_CK(cudaMemcpyAsync(ph.pid, pd.pid, k * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        int* const isrc[4] = {pd.slot, pd.mode, pd.omode, pd.cfacet};
+        int* const idst[4] = {ph.slot, ph.mode, ph.omode, ph.cfacet};
+        for (int a = 0; a < 4; ++a) NK_CK(cudaMemcpyAsync(idst[a], isrc[a], k * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    NK_CK(cudaMemcpyAsync(occ, P.occ, m * 8, cudaMemcpyDeviceToHost, st));
+    if (!patch_ok) {
+        NK_CK(cudaStreamSynchronize(ctx->s_out));    // the chunk downloads write the same host arrays
+        NK_CK(cudaMemcpyAsync(mode, P.mode, m * 4, cudaMemcpyDeviceToHost, st));
+        NK_CK(cudaMemcpyAsync(omode, P.omode, m * 4, cudaMemcpyDeviceToHost, st));
+        NK_CK(cudaMemcpyAsync(cfacet, P.cfacet, m * 4, cudaMemcpyDeviceToHost, st));
+        NK_CK(cudaMemcpyAsync(cx, P.cx, m * 8, cudaMemcpyDeviceToHost, st));
+        NK_CK(cudaMemcpyAsync(cy, P.cy, m * 8, cudaMemcpyDeviceToHost, st));
+        NK_CK(cudaMemcpyAsync(cz, P.cz, m * 8, cudaMemcpyDeviceToHost, st));
+        NK_CK(cudaMemcpyAsync(pid, P.pid, m * 8, cudaMemcpyDeviceToHost, st));
+        NK_CK(cudaMemcpyAsync(px, P.px, m * 8, cudaMemcpyDeviceToHost, st));      // stale for the rewritten slots
+        NK_CK(cudaMemcpyAsync(py, P.py, m * 8, cudaMemcpyDeviceToHost, st));
+        NK_CK(cudaMemcpyAsync(pz, P.pz, m * 8, cudaMemcpyDeviceToHost, st));
+        NK_CK(cudaMemcpyAsync(tc, P.tc, m * 8, cudaMemcpyDeviceToHost, st));
+    }
+    NK_CK(cudaStreamSynchronize(ctx->s_out));    // all chunk downloads (enqueued before the patch) and the patch
+    lap("d2h patch");
+    if (patch_ok) {
+        // scattered writes, latency-bound on one core: a few host threads (a slot listed twice carries the same values)
+        auto apply = [&](long long i0, long long i1) {
+            for (long long i = i0; i < i1; ++i) {
+                const int s = ph.slot[i];
+                px[s] = ph.x[i]; py[s] = ph.y[i]; pz[s] = ph.z[i]; tc[s] = ph.tc[i];
+                cx[s] = ph.cx[i]; cy[s] = ph.cy[i]; cz[s] = ph.cz[i];
+                mode[s] = ph.mode[i]; omode[s] = ph.omode[i]; cfacet[s] = ph.cfacet[i]; pid[s] = ph.pid[i];
+            }
+        };
+        const unsigned hw = std::thread::hardware_concurrency();
+        const int nt = nd < 8192 ? 1 : (int)std::min<unsigned>(8, hw ? hw : 1);
+        if (nt <= 1) apply(0, nd);
+        else {
+            std::vector<std::thread> th;
+            for (int k = 0; k < nt; ++k) th.emplace_back(apply, nd * k / nt, nd * (k + 1) / nt);
+            for (auto& t : th) t.join();
+        }
+    }
+    lap("patched");
+    NK_CK(cudaStreamSynchronize(st));
+    lap("d2h occ");
+    ctx->xfer_h2d = (long long)n * 84;
+    ctx->xfer_d2h = (long long)n * 32 + (long long)m * 8 + 8 + (patch_ok ? nd * 80 : (long long)m * 76);
+    if (trace) fprintf(stderr, "[nk pipe] patch entries %lld (hits %u, new %u)\n", nd, cnt[0], cnt[1]);
+    if (n_out) *n_out = ns;
+    return 0;
+}
+
+int nk_advance_host(nk_ctx* ctx, int64_t n_in, int n_steps, double* px, double* py, double* pz, double* tc, double* occ,
+                    int32_t* mode, int32_t* omode, int32_t* cfacet, double* cx, double* cy, double* cz, int64_t* pid,
+                    int64_t* n_out, double* T_sv_out, double* E_sv_out, int64_t* N_sv_out) {
+    cudaSetDevice(ctx->device);
+    if (nk_check_ready(ctx)) return -1;
+    NkP& P = ctx->P;
+    if (n_in > P.cap) { ctx->err = "n_in exceeds bound capacity"; return -1; }
+    const bool pipe = ctx->use_pipeline && n_steps == 1 && P.world == 1 && n_in >= (1 << 20) && !ctx->profiling &&
+                      (ctx->step_variant == 0);
+    int rc = pipe ? nk_advance_host_pipelined(ctx, n_in, px, py, pz, tc, occ, mode, omode, cfacet, cx, cy, cz, pid, n_out)
+                  : nk_advance_host_simple(ctx, n_in, n_steps, px, py, pz, tc, occ, mode, omode, cfacet, cx, cy, cz, pid, n_out);
+    if (rc) return rc;
     return nk_get_results(ctx, T_sv_out, E_sv_out, N_sv_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int nk_last_transfer_bytes(nk_ctx* ctx, int64_t* h2d, int64_t* d2h) {
+    if (h2d) *h2d = ctx->xfer_h2d;
+    if (d2h) *d2h = ctx->xfer_d2h;
+    return 0;
 }
 
 // ---- multi-GPU plumbing ---------------------------------------------------------------------------------------

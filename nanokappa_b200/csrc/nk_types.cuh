@@ -46,6 +46,10 @@ struct NkDyn {                   // device-resident, mutated by kernels
     long long step;              // Population.current_timestep
     unsigned int n_hits;         // particles whose collision falls inside this step
     unsigned int n_emit;         // emission-list entries of this step
+    unsigned int n_new;          // slots filled by emission in this step (newslots list)
+    unsigned int last_hits;      // n_hits / n_new of the step that was closed last (dirty-slot list for host patches)
+    unsigned int last_new;
+    unsigned int pad2;
     int relax_pending;           // lifetime_scattering of step-1 still to be applied to `occ`
     int error;                   // sticky device-side error bits
     unsigned int blocks_done;    // last-block detection
@@ -105,6 +109,9 @@ struct NkP {
     // ---- scratch owned by the ctx
     int* hitlist; int* freelist;
     int2* emitlist;                   // (R*M) {reservoir << 8 | copies, mode} of the entries emitting this step
+    int* newslots; long long newslots_cap;   // slots that received an emitted particle in this step
+    long long slot_lo, slot_hi;       // slot range the streaming kernel covers in this launch (chunked host pipeline)
+    int scan_emit;                    // 1: this launch advances the reservoir counters
     double* T_sv;                     // (S) current subvolume temperatures
     double* acc;                      // per-step accumulators, see layout below
     double* res_acc;                  // (R*4) E_bal + flux accumulated over the convergence window

@@ -77,3 +77,42 @@ def test_readme_case_properties(tmp_path, monkeypatch):
     a, b = pop.engine.particles(), pop2.engine.particles()
     assert np.array_equal(a["ids"], b["ids"]) and np.array_equal(a["modes"], b["modes"])
     assert np.array_equal(a["collision_facets"], b["collision_facets"]) and np.array_equal(a["positions"], b["positions"])
+
+
+def test_host_buffer_call_pipelined_equals_simple(tmp_path, monkeypatch):
+    """nk_advance_host (host SoA in, one timestep, host SoA out): the chunked pipeline (H2D / kernel / D2H overlapped,
+    cold arrays returned as a patch of the rewritten slots) must hand back exactly what the plain
+    upload-step-download version does, call after call."""
+    import ctypes as C
+    from nanokappa_b200._lib import check
+    out = {}
+    for label, env in (("pipelined", {"NK_HOST_PIPELINE": "1"}), ("simple", {"NK_HOST_PIPELINE": "0"}),
+                       ("patch_overflow", {"NK_HOST_PIPELINE": "1", "NK_PIPE_PATCH_CAP": "64"})):
+        monkeypatch.delenv("NK_PIPE_PATCH_CAP", raising=False)
+        geo, pop, _ = _run(tmp_path / label, 3, 0, dict(env, NK_STEP_TAB="0"), monkeypatch)
+        eng = pop.engine
+        n, _ = eng.slot_count()
+        names = ("px", "py", "pz", "tc", "occ", "mode", "omode", "cfacet", "cx", "cy", "cz", "pid")
+        host = {k: torch.empty(eng.cap, dtype=eng.t[k].dtype, pin_memory=True) for k in names}
+        for k in names:
+            host[k][:n].copy_(eng.t[k][:n])
+        torch.cuda.synchronize()
+        S = eng.S
+        Tsv = np.zeros(S); Esv = np.zeros(S); Nsv = np.zeros(S, dtype=np.int64)
+        hp = lambda k: C.c_void_p(host[k].data_ptr())
+        for _ in range(4):
+            n_out = C.c_int64()
+            check(eng.ctx, eng.L.nk_advance_host(eng.ctx, n, 1, *[hp(k) for k in names], C.byref(n_out),
+                                                 Tsv.ctypes.data_as(C.c_void_p), Esv.ctypes.data_as(C.c_void_p), Nsv.ctypes.data_as(C.c_void_p)),
+                  "nk_advance_host")
+            n = n_out.value
+        live = (host["mode"][:n] >= 0).numpy()
+        order = np.argsort(host["pid"][:n].numpy()[live])
+        out[label] = ({k: host[k][:n].numpy()[live][order] for k in names}, Tsv.copy(), Nsv.copy(), n)
+    b = out["simple"]
+    for label in ("pipelined", "patch_overflow"):
+        a = out[label]
+        assert np.array_equal(a[2], b[2]) and int(a[2].sum()) == a[0]["pid"].shape[0]
+        for k in a[0]:
+            assert np.array_equal(a[0][k], b[0][k], equal_nan=True), f"{k}: {label} host-buffer call differs from the simple one"
+        assert np.allclose(a[1], b[1], rtol=1e-12, atol=0)
