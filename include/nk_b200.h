@@ -35,6 +35,8 @@ typedef struct nk_ctx nk_ctx;
 
 #define NK_INTERP_NEAREST 0   /* --temp_interp nearest (Population.py:570-573) */
 #define NK_INTERP_LINEAR  1   /* --temp_interp linear, slice subvolumes only (Population.py:570-571) */
+#define NK_INTERP_RADIAL  2   /* --temp_interp radial, and linear on non-slice subvolumes: scipy RBFInterpolator(kernel='cubic')
+                                 (Population.py:574-588, :697-702); needs nk_set_rbf */
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
 int         nk_create(int device, nk_ctx** out);
@@ -70,6 +72,14 @@ int nk_set_mesh(nk_ctx* ctx, int n_faces,
  * SubvolClassifier (Geometry.py:1198-1213), Population.assign_temperatures (Population.py:570-590). */
 int nk_set_subvols(nk_ctx* ctx, int n_subvols, const double* centres, const double* volumes,
                    int is_slice, int slice_axis, int temp_interp);
+/* Cubic RBF temperature field of NK_INTERP_RADIAL (call after nk_set_subvols).  scipy's system
+ * [[|c_i-c_j|^3, P], [P^T, 0]] depends on the subvolume centres only, so the host set-up inverts it once:
+ * weights (S+n_dims+1, S) row-major = lhs^-1[:, :S]; every step the library forms coeffs = weights . T_sv and evaluates
+ * T(x) = sum_s coeffs[s] |x-c_s|^3 + coeffs[S] + sum_k coeffs[S+1+k] (x[dims[k]] - shift[k]) / scale[k].
+ * dims (n_dims <= 3): the coordinates the interpolator sees (a grid with a collapsed direction drops it,
+ * Population.py:697-699); shift, scale (n_dims): scipy's polynomial normalisation. */
+int nk_set_rbf(nk_ctx* ctx, int n_dims, const int32_t* dims, const double* shift, const double* scale,
+               const double* weights);
 
 /* Mode tables: Phonon.load_base_properties / calculate_lifetime / initialise_temperature_function
  * (Phonon.py:66-151, :326-336, :372-390).  omega (Q,J) rad THz, group_vel (Q,J,3) A THz,

@@ -21,6 +21,7 @@ from .Constants import Constants
 from .Visualisation import Visualisation
 from ..engine import Engine
 from ..routines import boundary_tables
+from ..routines.rbf import interp_dims
 
 BC_CODE = {'T': 0, 'P': 1, 'R': 2, 'F': 3}
 
@@ -49,7 +50,8 @@ def build_tables(args, geometry, phonon, pop):
         flat.extend(int(i) for i in fct); ptr.append(len(flat))
     tb['facet_faces_ptr'], tb['facet_faces'] = np.array(ptr), np.array(flat)
     tb.update(sv_centres=geometry.subvol_center, sv_volume=geometry.subvol_volume, sv_slice=geometry.subvol_type == 'slice',
-              slice_axis=int(getattr(geometry, 'slice_axis', 0)), temp_interp=pop.temp_interp_type)
+              slice_axis=int(getattr(geometry, 'slice_axis', 0)), temp_interp=pop.temp_interp_type,
+              interp_dims=interp_dims(geometry))
     tb.update(omega=phonon.omega, group_vel=phonon.group_vel, tau=phonon.lifetime, T_grid=phonon.temperature_array,
               energy_array=phonon.energy_array, T_array=phonon.T_array, hbar=phonon.hbar, kb=phonon.kb,
               volume_unitcell=phonon.volume_unitcell, n_active=int(phonon.number_of_active_modes),
@@ -113,10 +115,13 @@ class PopulationSetup(Constants):
         self.connected_facets = geometry.connected_facets
         self.T_distribution = self.args.temp_dist[0]
         self.temp_interp_type = self.args.temp_interp[0]
+        if self.temp_interp_type not in ('nearest', 'linear', 'radial'):
+            raise Exception('Invalid T interpolator type.')
         if self.temp_interp_type == 'linear' and geometry.subvol_type != 'slice':
-            raise Exception('Linear T interpolation is valid for slice subvolumes only; the radial (RBF) fallback is not on the GPU path yet. Use --temp_interp nearest.')
-        if self.temp_interp_type == 'radial':
-            raise Exception('--temp_interp radial (RBF) is not on the GPU path yet. Use nearest (or linear with slices).')
+            print('Linear T interpolation is currently valid for slice subvolumes only. Defaulting to RBF interpolation to avoid extrapolation problems.')
+            self.temp_interp_type = 'radial'
+        if self.temp_interp_type == 'radial' and geometry.subvol_type == 'slice':
+            raise Exception('Radial T interpolation needs grid or voronoi subvolumes: the centres of slices are collinear and the RBF system is singular.')
         self.colormap = self.args.colormap[0]
         self.fig_plot = self.args.fig_plot
         self.current_timestep = 0

@@ -137,6 +137,27 @@ NK_DEVI int nk_classify(const NkP& P, const double* svc, const double* sv_mid, d
     return best;
 }
 
+// scipy RBFInterpolator(kernel='cubic') evaluation (Population.py:588, :697-702) with the step's coefficients
+NK_DEVI double nk_rbf_T(const NkP& P, const double* svc, const double* coef, double x, double y, double z) {
+    const int nd = P.rbf_nd, S = P.S;
+    double acc = 0.0;
+    for (int s = 0; s < S; ++s) {
+        double r2 = 0.0;
+        for (int k = 0; k < nd; ++k) {
+            const int d = P.rbf_dim[k];
+            const double dx = (d == 0 ? x : (d == 1 ? y : z)) - svc[3 * s + d];
+            r2 += dx * dx;
+        }
+        acc += coef[s] * (r2 * sqrt(r2));
+    }
+    acc += coef[S];
+    for (int k = 0; k < nd; ++k) {
+        const int d = P.rbf_dim[k];
+        acc += coef[S + 1 + k] * (((d == 0 ? x : (d == 1 ? y : z)) - P.rbf_shift[k]) / P.rbf_scale[k]);
+    }
+    return acc;
+}
+
 // temperature_interpolator(x) (Population.py:570-590, :694-702; scipy interp1d formulas restated in
 // oracle/nk_oracle.py:particle_temperature).  `sv` is the particle's subvolume if already known (-1
 // otherwise); it is only used by the non-slice nearest rule.
@@ -154,6 +175,7 @@ NK_DEVI double nk_particle_T(const NkP& P, const double* svc, const double* sv_a
         int idx = P.S > 1 ? nk_searchsorted_left(sv_mid, P.S - 1, xa, P.sv_inv_dx) : 0;
         return T_sv[min(idx, P.S - 1)];
     }
+    if (P.interp == NK_INTERP_RADIAL) return nk_rbf_T(P, svc, P.rbf_coef, x, y, z);
     if (sv < 0) sv = nk_classify(P, svc, sv_mid, x, y, z);
     return T_sv[sv];
 }

@@ -960,6 +960,17 @@ __device__ __forceinline__ void nk_hit_entry(const NkP& P, const NkGeo& G, doubl
     }
 }
 
+// coef = rbf_w . T (T may live in shared memory); all threads of the block take rows
+__device__ __forceinline__ void nk_rbf_refresh(const NkP& P, const double* T) {
+    const int rows = P.S + P.rbf_nd + 1;
+    for (int j = threadIdx.x; j < rows; j += blockDim.x) {
+        const double* w = P.rbf_w + (size_t)j * P.S;
+        double a = 0.0;
+        for (int s = 0; s < P.S; ++s) a += w[s] * T[s];
+        P.rbf_coef[j] = a;
+    }
+}
+
 // ---- close the step: calculate_energy normalisation, temperature_function, heat flux, kappa,
 //      reservoir balances (Population.py:704-728, :692, :730-788, :1685-1699).  One block. -----------------------
 __device__ void nk_finalize_block(const NkP& P, double* sm) {
@@ -1037,6 +1048,7 @@ __device__ void nk_finalize_block(const NkP& P, double* sm) {
     }
     __syncthreads();
     for (int s = threadIdx.x; s < S; s += blockDim.x) P.T_sv[s] = sT[s];
+    if (P.interp == NK_INTERP_RADIAL) nk_rbf_refresh(P, sT);
     for (int i = threadIdx.x; i < nk_acc_len(S, R); i += blockDim.x) acc[i] = 0.0;
     if (threadIdx.x == 0) {
         NkDyn* d = P.dyn;
@@ -1399,8 +1411,15 @@ int nk_set_subvols(nk_ctx* ctx, int S, const double* centres, const double* volu
     cudaSetDevice(ctx->device);
     NkP& P = ctx->P;
     if (S < 1) { ctx->err = "n_subvols must be >= 1"; return -1; }
-    if (interp == NK_INTERP_LINEAR && !is_slice) { ctx->err = "linear temperature interpolation needs slice subvolumes (radial/RBF not on the GPU path yet)"; return -1; }
+    if (interp == NK_INTERP_LINEAR && !is_slice) { ctx->err = "linear temperature interpolation needs slice subvolumes; the reference falls back to NK_INTERP_RADIAL there"; return -1; }
+    if (interp == NK_INTERP_RADIAL && is_slice) { ctx->err = "radial temperature interpolation on slice subvolumes is singular upstream (collinear centres)"; return -1; }
+    if (interp < NK_INTERP_NEAREST || interp > NK_INTERP_RADIAL) { ctx->err = "unknown temp_interp"; return -1; }
     P.S = S; P.is_slice = is_slice; P.axis = axis; P.interp = interp;
+    P.rbf_nd = 0; P.rbf_w = nullptr;
+    {
+        std::vector<double> z(S + 4, 0.0);
+        NK_UP(P.rbf_coef, double, z.data(), z.size());
+    }
     double* dd;
     NK_UP(dd, double, centres, 3 * (size_t)S); P.svc = dd;
     NK_UP(dd, double, volumes, S); P.sv_volume = dd;
@@ -1610,11 +1629,39 @@ int nk_get_slot_count(nk_ctx* ctx, int64_t* n_slots, int64_t* n_alive) {
     return 0;
 }
 
+// coefficients of the cubic RBF temperature field for the current T_sv (outside a step: set-up, restart)
+__global__ void k_rbf_coef(NkP P) {
+    nk_rbf_refresh(P, P.T_sv);
+}
+
+int nk_set_rbf(nk_ctx* ctx, int n_dims, const int32_t* dims, const double* shift, const double* scale, const double* weights) {
+    cudaSetDevice(ctx->device);
+    NkP& P = ctx->P;
+    if (!P.svc) { ctx->err = "nk_set_subvols first"; return -1; }
+    if (P.interp != NK_INTERP_RADIAL) { ctx->err = "nk_set_rbf needs temp_interp = NK_INTERP_RADIAL"; return -1; }
+    if (n_dims < 1 || n_dims > 3) { ctx->err = "n_dims must be 1..3"; return -1; }
+    for (int k = 0; k < n_dims; ++k) {
+        if (dims[k] < 0 || dims[k] > 2) { ctx->err = "dims entries must be 0..2"; return -1; }
+        if (!(scale[k] != 0.0)) { ctx->err = "scale must be non-zero"; return -1; }
+        P.rbf_dim[k] = dims[k]; P.rbf_shift[k] = shift[k]; P.rbf_scale[k] = scale[k];
+    }
+    P.rbf_nd = n_dims;
+    double* dd;
+    NK_UP(dd, double, weights, (size_t)(P.S + n_dims + 1) * P.S); P.rbf_w = dd;
+    k_rbf_coef<<<1, 128, 0, ctx->stream>>>(P);
+    NK_CK(cudaGetLastError());
+    return 0;
+}
+
 int nk_set_sv_temperature(nk_ctx* ctx, const double* T) {
     cudaSetDevice(ctx->device);
     NK_CK(cudaStreamSynchronize(ctx->stream));
     NK_CK(cudaMemcpy(ctx->P.T_sv, T, ctx->P.S * sizeof(double), cudaMemcpyHostToDevice));
     ctx->tab_dirty = true;
+    if (ctx->P.interp == NK_INTERP_RADIAL && ctx->P.rbf_w) {
+        k_rbf_coef<<<1, 128, 0, ctx->stream>>>(ctx->P);
+        NK_CK(cudaGetLastError());
+    }
     return 0;
 }
 int nk_get_sv_temperature(nk_ctx* ctx, double* T) {
@@ -1703,6 +1750,7 @@ static int nk_check_ready(nk_ctx* ctx) {
     if (!ctx->particles_bound) { ctx->err = "particles not bound"; return -1; }
     if (!P.faces || !P.svc || !P.mprop || !P.mhot || !P.acc) { ctx->err = "tables missing: call nk_set_mesh, nk_set_subvols, nk_set_phonon, nk_set_population, nk_set_reservoirs first"; return -1; }
     if (P.dt <= 0) { ctx->err = "nk_set_population not called"; return -1; }
+    if (P.interp == NK_INTERP_RADIAL && !P.rbf_w) { ctx->err = "temp_interp radial: nk_set_rbf not called"; return -1; }
     return 0;
 }
 

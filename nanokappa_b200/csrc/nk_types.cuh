@@ -79,6 +79,12 @@ struct NkP {
     const double* sv_volume;
     double sv_inv_dx;                 // 1 / slice spacing (guess only; exactness comes from fix-up)
     double sv_x0;                     // lower end of slice 0 on the slice axis (guess only)
+    // cubic RBF temperature field (--temp_interp radial, nk_set_rbf): T(x) = sum_s coef[s] |x-c_s|^3 + coef[S] +
+    // sum_k coef[S+1+k] (x_k - shift_k)/scale_k over the rbf_nd coordinates rbf_dim[]; coef = rbf_w . T_sv
+    int rbf_nd; int rbf_dim[3];
+    double rbf_shift[3], rbf_scale[3];
+    const double* rbf_w;              // (S + rbf_nd + 1, S) row-major
+    double* rbf_coef;                 // (S + rbf_nd + 1), refreshed whenever T_sv changes
     // ---- modes
     int Q, J, M, NT;
     const double* Tg;                 // (NT)

@@ -12,7 +12,7 @@ mesh      face_normals (F,3) face_k (F) face_lo/face_hi (F,3) face_origins (F,3)
 facets    facet_bc (nf; 0 T,1 P,2 R,3 F) facet_normal facet_centroid (nf,3) facet_area (nf)
           facet_partner facet_res facet_rough (nf; -1 = none) facet_faces_ptr/facet_faces (CSR) bounds (2,3)
                                                                                  [Geometry.py:652-726]
-subvols   sv_centres (S,3) sv_volume (S) sv_slice (bool) slice_axis temp_interp ('nearest'|'linear')
+subvols   sv_centres (S,3) sv_volume (S) sv_slice (bool) slice_axis temp_interp ('nearest'|'linear'|'radial') [interp_dims]
                                                                                  [Geometry.py:446-544]
 modes     omega (Q,J) group_vel (Q,J,3) tau (NT,Q,J) T_grid (NT) energy_array/T_array (nE)
           hbar kb volume_unitcell n_active eVpsa2_in_Wm2 a_in_m                 [Phonon.py:66-151, :326-401]
@@ -29,7 +29,7 @@ import torch
 from . import _lib
 from ._lib import NkError, check
 
-INTERP_CODE = {"nearest": 0, "linear": 1}
+INTERP_CODE = {"nearest": 0, "linear": 1, "radial": 2}
 
 
 def _f64(a):
@@ -103,9 +103,16 @@ class Engine:
         self.S = S
         interp = tb["temp_interp"]
         if interp not in INTERP_CODE:
-            raise NkError(f"temp_interp '{interp}' is not on the GPU path (nearest, linear)")
+            raise NkError(f"temp_interp '{interp}' is not one of nearest, linear, radial")
+        if interp == "linear" and not bool(tb["sv_slice"]):
+            interp = "radial"      # Population.py:574-576: linear is for slices only, upstream falls back to the RBF
         check(ctx, L.nk_set_subvols(ctx, S, a(tb["sv_centres"]), a(tb["sv_volume"]), int(bool(tb["sv_slice"])),
                                     int(tb["slice_axis"]), INTERP_CODE[interp]), "nk_set_subvols")
+        if interp == "radial":
+            from .routines.rbf import cubic_rbf_weights
+            dims = np.asarray(tb.get("interp_dims", np.arange(3)), dtype=np.int32)
+            shift, scale, W = cubic_rbf_weights(tb["sv_centres"], dims)
+            check(ctx, L.nk_set_rbf(ctx, int(dims.shape[0]), a(dims, _i32), a(shift), a(scale), a(W)), "nk_set_rbf")
         NT = tb["T_grid"].shape[0]
         check(ctx, L.nk_set_phonon(ctx, Q, J, NT, a(tb["T_grid"]), a(tb["omega"]), a(tb["group_vel"]), a(tb["tau"]),
                                    float(tb["hbar"]), float(tb["kb"]), float(tb["volume_unitcell"]), int(tb["n_active"]),

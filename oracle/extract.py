@@ -58,6 +58,11 @@ def tables_from_reference(geo, ph, pop):
     tb["sv_slice"] = bool(geo.subvol_type == "slice")
     tb["slice_axis"] = int(getattr(geo, "slice_axis", 0))
     tb["temp_interp"] = str(pop.temp_interp_type)
+    # coordinates the non-slice interpolator sees (Population.py:697-702): a grid with a collapsed direction drops it
+    if geo.subvol_type == "grid" and np.any(np.asarray(geo.grid) == 1):
+        tb["interp_dims"] = np.nonzero(np.asarray(geo.grid) != 1)[0].astype(np.int64)
+    else:
+        tb["interp_dims"] = np.arange(3, dtype=np.int64)
 
     tb["omega"] = np.array(ph.omega, dtype=float)
     tb["group_vel"] = np.array(ph.group_vel, dtype=float)

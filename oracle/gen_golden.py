@@ -68,6 +68,19 @@ PARAMS_C4 = """
 --n_mean 10 --results_folder x --conv_crit 0 10 --colormap jet --output screen --max_sim_time 0-00:00:00
 """
 
+# box with a 3 x 2 x 1 grid of subvolumes (collapsed z -> 2-D interpolator), cubic RBF temperature, rough walls
+PARAMS_C5 = """
+--mat_folder test_material/Si/ --hdf_file kappa-m313131.hdf5 --poscar_file POSCAR
+--geometry box --dimensions 4e3 2e3 1e3 --scale 1 1 1 --geo_rotation 0 0 0 xyz
+--subvolumes grid 3 2 1
+--bound_pos relative -0.1 0.5 0.5 1.1 0.5 0.5 0.5 0.5 -0.1 0.5 0.5 1.1
+--bound_cond T T R R P --connect_pos relative 0.5 -0.1 0.5 0.5 1.1 0.5
+--bound_values 303 297 {eta} {eta}
+--reference_temp local --temp_dist cold --temp_interp radial
+--particles total {n} --part_dist random_subvol --timestep 1 --iterations 1000
+--n_mean 10 --results_folder x --conv_crit 0 10 --colormap jet --output screen --max_sim_time 0-00:00:00
+"""
+
 CONFIGS = {
     # name: (parameter text, table mesh n, lattice)
     "c1_specular": (PARAMS_C1.format(eta=0, n=4000), 5),
@@ -75,6 +88,8 @@ CONFIGS = {
     "c1_mixed": (PARAMS_C1.format(eta=0.5, n=4000), 5),
     "c2_crossplane": (PARAMS_C2.format(n=6000), 5),
     "c4_cylinder_voronoi": (PARAMS_C4.format(eta=3, n=3000), 5),
+    "c5_box_grid_radial": (PARAMS_C5.format(eta=2, n=3000), 5),
+    "c6_cylinder_voronoi_radial": (PARAMS_C4.format(eta=3, n=3000).replace("--temp_interp nearest", "--temp_interp radial"), 5),
 }
 
 STATE_FIELDS = ("positions", "modes", "omega", "group_vel", "occupation", "n_timesteps", "collision_facets",

@@ -267,9 +267,42 @@ def particle_temperature(tb, T_sv, x):
         xb = xb[1:] + xb[:-1]
         idx = np.searchsorted(xb, xn, side="left").clip(0, len(xs) - 1)
         return T_sv[idx]
+    dims = np.asarray(tb.get("interp_dims", np.arange(3)), dtype=int)
     if kind == "nearest":
-        return T_sv[classify(tb, x)]
-    raise NotImplementedError("radial (RBF cubic) temperature interpolation is SURVEY 8f item 4")
+        if dims.shape[0] == 3:
+            return T_sv[classify(tb, x)]
+        from scipy.interpolate import NearestNDInterpolator
+        return NearestNDInterpolator(tb["sv_centres"][:, dims], T_sv)(x[:, dims])
+    # 'radial', and 'linear' on non-slice subvolumes (Population.py:574-588): the third-party call itself,
+    # scipy.interpolate.RBFInterpolator(kernel='cubic') -> degree-1 polynomial tail, epsilon 1, no smoothing
+    from scipy.interpolate import RBFInterpolator
+    if x.shape[0] == 0:
+        return np.zeros(0)
+    return RBFInterpolator(tb["sv_centres"][:, dims], T_sv, kernel="cubic")(x[:, dims])
+
+
+def rbf_weights(centres, dims):
+    """Restatement of scipy's cubic RBF system (scipy/interpolate/_rbfinterp_np.py:40-89 and the pythran
+    `_build_system`): lhs = [[|c_i - c_j|^3, P], [P^T, 0]] with P = [1, (c - shift)/scale]; returns
+    (shift, scale, W) with W = lhs^-1[:, :S], so that coeffs = W @ T_sv and
+    T(x) = sum_s coeffs[s] |x - c_s|^3 + coeffs[S] + sum_k coeffs[S+1+k] (x_k - shift_k)/scale_k.
+    This is what the host set-up of the CUDA path uploads (nk_set_rbf); tests compare it with RBFInterpolator."""
+    y = np.asarray(centres, dtype=float)[:, np.asarray(dims, dtype=int)]
+    S, nd = y.shape
+    mins, maxs = y.min(axis=0), y.max(axis=0)
+    shift = (maxs + mins) / 2
+    scale = (maxs - mins) / 2
+    scale[scale == 0.0] = 1.0
+    yhat = (y - shift) / scale
+    lhs = np.zeros((S + nd + 1, S + nd + 1))
+    r = np.linalg.norm(y[:, None, :] - y[None, :, :], axis=-1)
+    lhs[:S, :S] = r ** 3
+    lhs[:S, S] = 1.0
+    lhs[:S, S + 1:] = yhat
+    lhs[S:, :S] = lhs[:S, S:].T
+    rhs = np.zeros((S + nd + 1, S))
+    rhs[:S, :] = np.eye(S)
+    return shift, scale, np.linalg.solve(lhs, rhs)
 
 
 def sample_surface_points(tb, f, s, r):

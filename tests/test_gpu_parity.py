@@ -117,6 +117,26 @@ def test_table_operators(name, golden_dir):
     _close("particle T", eng.particle_temperature(x), nko.particle_temperature(tb, T_sv, x), 1e-14)
 
 
+@pytest.mark.parametrize("name", ["c5_box_grid_radial", "c6_cylinder_voronoi_radial"])
+def test_particle_temperature_radial(name, golden_dir):
+    """--temp_interp radial: the device's cubic RBF field (weights factorised at set-up, coefficients refreshed with
+    T_sv) against scipy's RBFInterpolator, inside and outside the mesh, after set_sv_temperature and after steps."""
+    tb, st, _ = _load(name, golden_dir)
+    eng = _engine(tb, st)
+    r = np.random.default_rng(5)
+    lo, hi = tb["bounds"]
+    x = lo - 0.05 * (hi - lo) + r.random((20000, 3)) * (hi - lo) * 1.1
+    T_sv = 298 + 4 * r.random(tb["sv_centres"].shape[0])
+    eng.set_sv_temperature(T_sv)
+    _close("particle T (radial)", eng.particle_temperature(x), nko.particle_temperature(tb, T_sv, x), 1e-9)
+    eng.set_sv_temperature(st.subvol_temperature)
+    eng.step(3)
+    T_now = eng.results()["subvol_temperature"]
+    _close("particle T after steps", eng.particle_temperature(x), nko.particle_temperature(tb, T_now, x), 1e-9)
+    sv = eng.classify(x)
+    assert np.array_equal(sv, nko.classify(tb, x))
+
+
 def _compare_step(k, eng, st, tb):
     p = eng.particles()
     order = np.argsort(st.ids)

@@ -111,3 +111,23 @@ def test_parameters_file_round_trip(tmp_path):
     args = ap.read_args(False, ["nanokappa.py", "-ff", str(p)])
     assert args.particles == ["total", "1000"] and args.bound_cond == ["T", "T", "R", "R", "P"]
     assert args.subvolumes == ["slice", "10", "0"] and args.from_file == str(p)
+
+
+@pytest.mark.parametrize("name", ["c5_box_grid_radial", "c6_cylinder_voronoi_radial"])
+def test_rbf_weights_reproduce_scipy_interpolator(name, golden_dir):
+    """--temp_interp radial: the factorised system the host uploads (nk_set_rbf) must evaluate to what the reference's
+    per-step scipy RBFInterpolator(kernel='cubic') gives, for the fixture's centres and for a 100-centre cloud."""
+    from scipy.interpolate import RBFInterpolator
+    from nanokappa_b200.routines.rbf import cubic_rbf_weights
+    tb, st, refs = gen_golden.load_fixture(os.path.join(golden_dir, name + ".npz"))
+    rng = np.random.default_rng(3)
+    cases = [(tb["sv_centres"], tb["interp_dims"], refs[20]["subvol_temperature"], st.positions),
+             (rng.random((100, 3)) * [3000, 600, 600], np.arange(3), 300 + 5 * rng.random(100), rng.random((2000, 3)) * [3000, 600, 600])]
+    for c, dims, T, x in cases:
+        shift, scale, W = cubic_rbf_weights(c, dims)
+        S = c.shape[0]
+        coef = W @ T
+        r = np.linalg.norm(x[:, None, dims] - c[None][:, :, dims], axis=-1)
+        got = (r ** 3) @ coef[:S] + coef[S] + ((x[:, dims] - shift) / scale) @ coef[S + 1:]
+        want = RBFInterpolator(c[:, dims], T, kernel="cubic")(x[:, dims])
+        assert np.allclose(got, want, rtol=1e-9, atol=0)
