@@ -101,6 +101,17 @@ int nk_set_population(nk_ctx* ctx, double dt, int norm_mean, double particle_den
 int nk_set_reservoirs(nk_ctx* ctx, int R, const int32_t* res_facet, const double* res_T,
                       const double* enter_prob, const double* res_counter);
 int nk_get_res_counter(nk_ctx* ctx, double* res_counter_host);
+/* --reservoir_gen (Population.fill_reservoirs, Population.py:356-489); call after nk_set_reservoirs, default constant.
+ *   constant   : fractional counters per (reservoir, mode)                                   (:358-406)
+ *   fixed_rate : a fresh uniform per (reservoir, mode) and step instead of the counter       (:408-455)
+ *   one_to_one : every reservoir re-emits what it absorbed in the previous step, modes from the roulette
+ *                cumsum(enter_prob[r]) / max, entry time uniform in the step                 (:457-489)
+ * n_leaving (R doubles, may be NULL): particles "absorbed" before the first step; NULL keeps the reference's initial
+ * value round(sum(enter_prob[r])) (Population.py:344). */
+#define NK_RESGEN_CONSTANT   0
+#define NK_RESGEN_FIXED_RATE 1
+#define NK_RESGEN_ONE_TO_ONE 2
+int nk_set_reservoir_mode(nk_ctx* ctx, int mode, const double* n_leaving);
 
 /* Rough-wall tables: calculate_fbz_specularity / find_specular_correspondences /
  * diffuse_scat_probability (Population.py:852-939, :1042-1461).  All (Fr, Q*J); spec_out is the

@@ -31,6 +31,7 @@ SIGNATURES = {
                               C.c_int, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
     "nk_set_subvols": (C.c_int, [VP, C.c_int, VP, VP, C.c_int, C.c_int, C.c_int]),
     "nk_set_rbf": (C.c_int, [VP, C.c_int, VP, VP, VP, VP]),
+    "nk_set_reservoir_mode": (C.c_int, [VP, C.c_int, VP]),
     "nk_set_phonon": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP, C.c_double, C.c_double, C.c_double,
                                 C.c_int64, C.c_int, VP, VP]),
     "nk_set_population": (C.c_int, [VP, C.c_double, C.c_int, C.c_double, C.c_int, C.c_uint64, C.c_double, C.c_double,

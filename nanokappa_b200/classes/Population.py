@@ -51,7 +51,7 @@ def build_tables(args, geometry, phonon, pop):
     tb['facet_faces_ptr'], tb['facet_faces'] = np.array(ptr), np.array(flat)
     tb.update(sv_centres=geometry.subvol_center, sv_volume=geometry.subvol_volume, sv_slice=geometry.subvol_type == 'slice',
               slice_axis=int(getattr(geometry, 'slice_axis', 0)), temp_interp=pop.temp_interp_type,
-              interp_dims=interp_dims(geometry))
+              interp_dims=interp_dims(geometry), res_gen=pop.res_gen)
     tb.update(omega=phonon.omega, group_vel=phonon.group_vel, tau=phonon.lifetime, T_grid=phonon.temperature_array,
               energy_array=phonon.energy_array, T_array=phonon.T_array, hbar=phonon.hbar, kb=phonon.kb,
               volume_unitcell=phonon.volume_unitcell, n_active=int(phonon.number_of_active_modes),
@@ -105,8 +105,6 @@ class PopulationSetup(Constants):
         self.subvol_volume = geometry.subvol_volume
         self.bound_cond = geometry.bound_cond
         self.res_gen = self.args.reservoir_gen[0]
-        if self.res_gen != 'constant':
-            raise Exception("--reservoir_gen '{}' is a debug mode that is not on the GPU path (constant only).".format(self.res_gen))
         if self.args.reference_temp[0] != 'local':
             raise Exception('--reference_temp with a fixed value is a debug mode that is not on the GPU path (local only).')
         self.T_reference = 'local'

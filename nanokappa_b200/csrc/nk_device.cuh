@@ -22,7 +22,8 @@ NK_DEVI double norm3(double x, double y, double z) { return sqrt(dot3(x, y, z, x
 // ------------------------------------------------------------------------------------------------
 #define NK_STREAM_EMIT_A 0u
 #define NK_STREAM_EMIT_B 1u
-#define NK_STREAM_ROUGH0 2u
+#define NK_STREAM_ROUGH0 2u          // + index of the boundary event within the step
+#define NK_STREAM_EMIT_C 65536u      // fixed_rate dice / one_to_one (mode, entry time)
 
 NK_DEVI void philox4x32_10(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3,
                            unsigned int k0, unsigned int k1, unsigned int out[4]) {

@@ -290,19 +290,44 @@ __device__ __forceinline__ double nk_relax_particle(const NkP& P, const NkSvSmem
 // (R, Q*J) table advances its fractional counter; entries that emit this step are appended to the
 // emission list that k_rare consumes.  Runs as the prologue of the streaming kernel (grid-stride over all
 // its blocks): it does not depend on the particles at all.
+__device__ __forceinline__ long long nk_one_to_one_share(const NkP& P, int r) {
+    const long long n = (long long)P.res_nleave[r];
+    return n > P.rank ? (n - P.rank + P.world - 1) / P.world : 0;
+}
+
 __device__ __forceinline__ void nk_emit_scan(const NkP& P) {
+    if (P.res_gen == NK_RESGEN_ONE_TO_ONE) {
+        // one_to_one (Population.py:457-489): as many particles as the reservoir absorbed in the previous step; the
+        // k-th of them belongs to rank k % world.  No table scan: k_rare decodes (reservoir, k) from the item index.
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned int total = 0;
+            for (int r = 0; r < P.R; ++r) total += (unsigned int)nk_one_to_one_share(P, r);
+            P.dyn->n_emit = total;
+        }
+        return;
+    }
     const int mspan = P.emit_m_hi - P.emit_m_lo;
     const long long total = (long long)P.R * mspan;
+    const long long step = P.dyn->step;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(e / mspan);
         const int m = P.emit_m_lo + (int)(e % mspan);
         const size_t idx = (size_t)r * P.M + m;
         const double prob = P.enter_prob[idx];
         const double fixed = floor(prob);
-        double cnt = nk_add(P.res_counter[idx], nk_sub(prob, fixed));
-        const int extra = cnt >= 1.0 ? 1 : 0;
-        cnt = nk_sub(cnt, (double)extra);
-        P.res_counter[idx] = cnt;
+        int extra;
+        if (P.res_gen == NK_RESGEN_FIXED_RATE) {
+            // fixed_rate (Population.py:408-417): a fresh dice per (reservoir, mode) and step instead of the counter
+            double dice, unused;
+            nk_uniforms(P, NK_EMIT_ID_BASE + (((step * P.R + r) * (long long)P.M + m) * NK_EMIT_CMAX), step, NK_STREAM_EMIT_C, dice, unused);
+            extra = dice <= nk_sub(prob, fixed) ? 1 : 0;
+            P.emit_u[idx] = dice;
+        } else {
+            double cnt = nk_add(P.res_counter[idx], nk_sub(prob, fixed));
+            extra = cnt >= 1.0 ? 1 : 0;
+            cnt = nk_sub(cnt, (double)extra);
+            P.res_counter[idx] = cnt;
+        }
         int n_new = (int)fixed + extra;
         if (n_new == 0) continue;
         if (n_new > NK_EMIT_CMAX) { atomicOr(&P.dyn->error, NK_ERR_CMAX); n_new = NK_EMIT_CMAX; }
@@ -317,11 +342,12 @@ __device__ __forceinline__ void nk_emit_scan(const NkP& P) {
 // in 64-bit FIXED POINT built from two native 32-bit adds: the low word's returned old value tells this
 // add whether it wrapped, and the carry rides on the high word's add (two's complement, so signed terms
 // just work, and the result does not depend on the order of the adds).  Quantum: 2^-46 eV for energies
-// (1.4e-14 eV, the size of the f64 rounding noise of the reference's own sum), 2^-30 for flux terms.  A
+// (1.4e-14 eV, the size of the f64 rounding noise of the reference's own sum), 2^-38 for flux terms
+// (|v e| is at most ~0.03 eV A/ps for a few K of temperature difference, so 1e-8 of a single typical term).  A
 // term outside the fixed-point range (|q| >= 2^40; never for physical occupations) or non-finite goes to
 // an f64 side bin.  A block adds at most a few million terms: |sum| < 2^62.
 #define NK_QE 70368744177664.0          // 2^46
-#define NK_QF 1073741824.0              // 2^30
+#define NK_QF 274877906944.0            // 2^38
 __device__ __forceinline__ void nk_bin_add(long long* q, double* side, double v, double scale) {
     const double t = v * scale;
     if (fabs(t) < 1099511627776.0) {
@@ -893,52 +919,83 @@ __device__ __forceinline__ long long nk_take_slot(const NkP& P) {
 
 // One emission-list entry: n_new copies of mode m entering through reservoir r (Population.py:385-406,
 // :491-508, add_reservoir_particles :525-552, Mesh.sample_surface Mesh.py:923-951).
+// One new particle of reservoir r in mode m entering the domain dt_in before the end of the step
+// (Population.fill_reservoirs :491-508 + add_reservoir_particles :525-552 + Mesh.sample_surface :923-951).
+__device__ __forceinline__ void nk_emit_particle(const NkP& P, const NkGeo& G, double* acc, int r, int m, long long id, double dt_in,
+                                                 double uface, double us, double ur, long long step, bool with_flux) {
+    const double dt = P.dt;
+    const NkMode mp = P.mprop[m];
+    NkParticle p;
+    p.id = id;
+    // face ~ area: searchsorted(cdf, u, side='right') as np.random.choice does
+    const int f0 = P.res_face_ptr[r], f1 = P.res_face_ptr[r + 1];
+    int lo = f0, hi = f1;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (P.res_face_cdf[mid] <= uface) lo = mid + 1; else hi = mid; }
+    const int face = P.res_faces[min(lo, f1 - 1)];
+    const double* V = P.face_vertices + 9 * (size_t)face;
+    const double rs = sqrt(us);
+    const double a0 = nk_sub(1.0, rs), a1 = nk_mul(nk_sub(1.0, ur), rs), a2 = nk_mul(ur, rs);
+    const double x0 = nk_add(nk_add(nk_mul(a0, V[0]), nk_mul(a1, V[3])), nk_mul(a2, V[6]));
+    const double y0 = nk_add(nk_add(nk_mul(a0, V[1]), nk_mul(a1, V[4])), nk_mul(a2, V[7]));
+    const double z0 = nk_add(nk_add(nk_mul(a0, V[2]), nk_mul(a1, V[5])), nk_mul(a2, V[8]));
+    p.mode = m; p.omode = m; p.omega = mp.omega; p.vx = mp.vx; p.vy = mp.vy; p.vz = mp.vz;
+    double t;
+    nk_find_boundary_1(P, G.faces, x0, y0, z0, p.vx, p.vy, p.vz, p.cx, p.cy, p.cz, t, p.cf);
+    p.tc = nk_sub(nk_div(t, dt), nk_div(dt_in, dt));
+    p.x = nk_add(x0, nk_mul(p.vx, dt_in)); p.y = nk_add(y0, nk_mul(p.vy, dt_in)); p.z = nk_add(z0, nk_mul(p.vz, dt_in));
+    p.occ = nk_bose(P, P.res_T[r], p.omega);
+    p.alive = true;
+    atomicAdd(acc + NK_ACC_NEMIT(P.S, P.R), 1.0);
+    if (p.tc < 0.0) nk_boundary_events(P, G, p, step, acc);
+    if (!p.alive) { atomicAdd(acc + NK_ACC_NABS(P.S, P.R), 1.0); return; }   // crossed the whole domain within the step
+    const long long slot = nk_take_slot(P);
+    if (slot < 0) return;
+    nk_store_particle(P, slot, p);
+    P.pid[slot] = p.id;
+    {
+        const unsigned int k = atomicAdd(&P.dyn->n_new, 1u);
+        if ((long long)k < P.newslots_cap) P.newslots[k] = (int)slot;
+    }
+    nk_accumulate(P, acc, p, with_flux);
+}
+
+// One emission-list entry (constant / fixed_rate): n_new copies of mode m from reservoir r.
 __device__ __forceinline__ void nk_emit_entry(const NkP& P, const NkGeo& G, double* acc, int r, int m, int n_new, long long step, bool with_flux) {
-    const NkFace* faces = G.faces;
     const double dt = P.dt;
     const size_t idx = (size_t)r * P.M + m;
     const double prob = P.enter_prob[idx];
-    const double cnt = P.res_counter[idx];                 // value after this step's update
-    const NkMode mp = P.mprop[m];
+    // numerator of the first copy's entry time: the counter after this step's update, or this step's dice
+    const double lead = P.res_gen == NK_RESGEN_FIXED_RATE ? P.emit_u[idx] : P.res_counter[idx];
     for (int c = n_new; c >= 1; --c) {
-        NkParticle p;
-        p.id = NK_EMIT_ID_BASE + (((step * P.R + r) * (long long)P.M + m) * NK_EMIT_CMAX + (c - 1));
+        const long long id = NK_EMIT_ID_BASE + (((step * P.R + r) * (long long)P.M + m) * NK_EMIT_CMAX + (c - 1));
         double ua, uface, us, ur;
-        nk_uniforms(P, p.id, step, NK_STREAM_EMIT_A, ua, uface);
-        nk_uniforms(P, p.id, step, NK_STREAM_EMIT_B, us, ur);
-        const double dt_in = (c == 1) ? nk_mul(dt, nk_sub(1.0, nk_div(cnt, prob)))
+        nk_uniforms(P, id, step, NK_STREAM_EMIT_A, ua, uface);
+        nk_uniforms(P, id, step, NK_STREAM_EMIT_B, us, ur);
+        const double dt_in = (c == 1) ? nk_mul(dt, nk_sub(1.0, nk_div(lead, prob)))
                                       : nk_mul(dt, nk_sub(1.0, nk_div(nk_add((double)(c - 1), ua), prob)));
-        // face ~ area: searchsorted(cdf, u, side='right') as np.random.choice does
-        const int f0 = P.res_face_ptr[r], f1 = P.res_face_ptr[r + 1];
-        int lo = f0, hi = f1;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (P.res_face_cdf[mid] <= uface) lo = mid + 1; else hi = mid; }
-        const int face = P.res_faces[min(lo, f1 - 1)];
-        const double* V = P.face_vertices + 9 * (size_t)face;
-        const double rs = sqrt(us);
-        const double a0 = nk_sub(1.0, rs), a1 = nk_mul(nk_sub(1.0, ur), rs), a2 = nk_mul(ur, rs);
-        const double x0 = nk_add(nk_add(nk_mul(a0, V[0]), nk_mul(a1, V[3])), nk_mul(a2, V[6]));
-        const double y0 = nk_add(nk_add(nk_mul(a0, V[1]), nk_mul(a1, V[4])), nk_mul(a2, V[7]));
-        const double z0 = nk_add(nk_add(nk_mul(a0, V[2]), nk_mul(a1, V[5])), nk_mul(a2, V[8]));
-        p.mode = m; p.omode = m; p.omega = mp.omega; p.vx = mp.vx; p.vy = mp.vy; p.vz = mp.vz;
-        double t;
-        nk_find_boundary_1(P, faces, x0, y0, z0, p.vx, p.vy, p.vz, p.cx, p.cy, p.cz, t, p.cf);
-        p.tc = nk_sub(nk_div(t, dt), nk_div(dt_in, dt));
-        p.x = nk_add(x0, nk_mul(p.vx, dt_in)); p.y = nk_add(y0, nk_mul(p.vy, dt_in)); p.z = nk_add(z0, nk_mul(p.vz, dt_in));
-        p.occ = nk_bose(P, P.res_T[r], p.omega);
-        p.alive = true;
-        atomicAdd(acc + NK_ACC_NEMIT(P.S, P.R), 1.0);
-        if (p.tc < 0.0) nk_boundary_events(P, G, p, step, acc);
-        if (!p.alive) { atomicAdd(acc + NK_ACC_NABS(P.S, P.R), 1.0); continue; }   // crossed the whole domain within the step
-        const long long slot = nk_take_slot(P);
-        if (slot < 0) continue;
-        nk_store_particle(P, slot, p);
-        P.pid[slot] = p.id;
-        {
-            const unsigned int k = atomicAdd(&P.dyn->n_new, 1u);
-            if ((long long)k < P.newslots_cap) P.newslots[k] = (int)slot;
-        }
-        nk_accumulate(P, acc, p, with_flux);
+        nk_emit_particle(P, G, acc, r, m, id, dt_in, uface, us, ur, step, with_flux);
     }
+}
+
+// One re-emitted particle of the one_to_one mode: k-th particle of reservoir r (Population.py:457-489).
+__device__ __forceinline__ void nk_emit_one_to_one(const NkP& P, const NkGeo& G, double* acc, long long e, long long step, bool with_flux) {
+    int r = 0;
+    for (; r < P.R; ++r) {
+        const long long share = nk_one_to_one_share(P, r);
+        if (e < share) break;
+        e -= share;
+    }
+    if (r >= P.R) return;
+    const long long k = P.rank + e * P.world;
+    const long long id = NK_EMIT_ID_BASE + (step * P.R + r) * ((long long)P.M * NK_EMIT_CMAX) + k;
+    double ua, uface, us, ur, umode, udt;
+    nk_uniforms(P, id, step, NK_STREAM_EMIT_A, ua, uface);
+    nk_uniforms(P, id, step, NK_STREAM_EMIT_B, us, ur);
+    nk_uniforms(P, id, step, NK_STREAM_EMIT_C, umode, udt);
+    const double* rou = P.res_roulette + (size_t)r * P.M;
+    int lo = 0, hi = P.M;                                    // searchsorted left
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (rou[mid] < umode) lo = mid + 1; else hi = mid; }
+    nk_emit_particle(P, G, acc, r, min(lo, P.M - 1), id, nk_mul(P.dt, udt), uface, us, ur, step, with_flux);
 }
 
 // One hit-list entry: the boundary event loop of an existing particle.
@@ -1008,6 +1065,7 @@ __device__ void nk_finalize_block(const NkP& P, double* sm) {
     // reservoirs: accumulate this step, normalise on convergence steps
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
         out[NK_OUT_NLEAVE(S, R) + r] = __ldcg(acc + NK_ACC_NLEAVE(S, R) + r);
+        P.res_nleave[r] = __ldcg(acc + NK_ACC_NLEAVE(S, R) + r);
         double eb = nk_add(P.res_acc[r], __ldcg(acc + NK_ACC_EBAL(S, R) + r));
         double fx[3];
         for (int k = 0; k < 3; ++k) fx[k] = nk_add(P.res_acc[R + 3 * r + k], __ldcg(acc + NK_ACC_RFLUX(S, R) + 3 * r + k));
@@ -1150,8 +1208,12 @@ __global__ void __launch_bounds__(NK_RARE_THREADS) k_rare(NkP P) {
         if (w < nh) {
             nk_hit_entry(P, G, racc, P.hitlist[w], step, with_flux);
         } else {
-            const int2 e = P.emitlist[w - nh];
-            nk_emit_entry(P, G, racc, e.x >> 8, e.y, e.x & 0xff, step, with_flux);
+            if (P.res_gen == NK_RESGEN_ONE_TO_ONE) {
+                nk_emit_one_to_one(P, G, racc, (long long)(w - nh), step, with_flux);
+            } else {
+                const int2 e = P.emitlist[w - nh];
+                nk_emit_entry(P, G, racc, e.x >> 8, e.y, e.x & 0xff, step, with_flux);
+            }
         }
     }
     __syncthreads();
@@ -1534,7 +1596,35 @@ int nk_set_reservoirs(nk_ctx* ctx, int R, const int32_t* res_facet, const double
     int2* de; NK_UP(de, int2, (const int2*)nullptr, (size_t)std::max(R, 1) * P.M); P.emitlist = de;
     P.newslots_cap = (long long)std::max(R, 1) * P.M * 2;
     int* dn; NK_UP(dn, int, (const int*)nullptr, (size_t)P.newslots_cap); P.newslots = dn;
+    // emission-mode extras (nk_set_reservoir_mode): initial N_leaving (Population.py:344), roulette of one_to_one (:465-466)
+    P.res_gen = NK_RESGEN_CONSTANT;
+    std::vector<double> nl(std::max(R, 1), 0.0), rou((size_t)std::max(R, 1) * P.M, 0.0);
+    for (int r = 0; r < R; ++r) {
+        const double* p = enter_prob + (size_t)r * P.M;
+        double sum = 0.0;                                    // np.sum is pairwise, np.cumsum sequential
+        for (int m = 0; m < P.M; ++m) { sum += p[m]; rou[(size_t)r * P.M + m] = sum; }
+        double mx = 0.0;
+        for (int m = 0; m < P.M; ++m) mx = std::max(mx, rou[(size_t)r * P.M + m]);
+        for (int m = 0; m < P.M; ++m) rou[(size_t)r * P.M + m] /= mx;
+        nl[r] = std::nearbyint(sum);
+    }
+    NK_UP(dd, double, rou.data(), rou.size()); P.res_roulette = dd;
+    NK_UP(dd, double, nl.data(), nl.size()); P.res_nleave = dd;
+    NK_UP(dd, double, (const double*)nullptr, (size_t)std::max(R, 1) * P.M); P.emit_u = dd;
     return nk_alloc_scratch(ctx);
+}
+
+int nk_set_reservoir_mode(nk_ctx* ctx, int mode, const double* n_leaving) {
+    cudaSetDevice(ctx->device);
+    NkP& P = ctx->P;
+    if (!P.res_nleave) { ctx->err = "nk_set_reservoirs first"; return -1; }
+    if (mode < NK_RESGEN_CONSTANT || mode > NK_RESGEN_ONE_TO_ONE) { ctx->err = "unknown reservoir generation mode"; return -1; }
+    P.res_gen = mode;
+    if (n_leaving && P.R > 0) {
+        NK_CK(cudaStreamSynchronize(ctx->stream));
+        NK_CK(cudaMemcpy(P.res_nleave, n_leaving, P.R * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return 0;
 }
 
 int nk_get_res_counter(nk_ctx* ctx, double* h) {

@@ -104,6 +104,10 @@ struct NkP {
     // ---- reservoirs
     int R; const int* res_facet; const double* res_T; const double* enter_prob; double* res_counter;
     int emit_m_lo, emit_m_hi;         // this rank's share of every reservoir's mode table
+    int res_gen;                      // NK_RESGEN_* (--reservoir_gen)
+    double* emit_u;                   // (R, M) this step's dice (fixed_rate)
+    const double* res_roulette;       // (R, M) cumsum(enter_prob[r]) / max (one_to_one)
+    double* res_nleave;               // (R) particles absorbed per reservoir in the previous step (one_to_one)
     // ---- rough-wall LUTs (Fr, M)
     int Fr; const double* specularity; const unsigned char* true_spec; const int* spec_out; const double* roulette;
     // ---- particles (borrowed)

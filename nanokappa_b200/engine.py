@@ -30,6 +30,7 @@ from . import _lib
 from ._lib import NkError, check
 
 INTERP_CODE = {"nearest": 0, "linear": 1, "radial": 2}
+RESGEN_CODE = {"constant": 0, "fixed_rate": 1, "one_to_one": 2}
 
 
 def _f64(a):
@@ -128,6 +129,12 @@ class Engine:
             res_counter = np.zeros((R, Q, J))
         check(ctx, L.nk_set_reservoirs(ctx, R, a(tb["res_facet"], _i32), a(tb["res_T"]), a(tb["enter_prob"]),
                                        a(res_counter)), "nk_set_reservoirs")
+        res_gen = str(tb.get("res_gen", "constant"))
+        if res_gen not in RESGEN_CODE:
+            raise NkError(f"reservoir_gen '{res_gen}' is not one of constant, fixed_rate, one_to_one")
+        if R > 0:
+            n_leaving = np.sum(np.asarray(tb["enter_prob"], dtype=float), axis=(1, 2)).round()       # Population.py:344
+            check(ctx, L.nk_set_reservoir_mode(ctx, RESGEN_CODE[res_gen], a(n_leaving)), "nk_set_reservoir_mode")
         Fr = tb["specularity"].shape[0]
         u8 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.uint8))
         check(ctx, L.nk_set_boundary_luts(ctx, Fr, a(tb["specularity"]), a(tb["true_specular"], u8),

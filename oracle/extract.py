@@ -58,6 +58,7 @@ def tables_from_reference(geo, ph, pop):
     tb["sv_slice"] = bool(geo.subvol_type == "slice")
     tb["slice_axis"] = int(getattr(geo, "slice_axis", 0))
     tb["temp_interp"] = str(pop.temp_interp_type)
+    tb["res_gen"] = str(pop.res_gen)
     # coordinates the non-slice interpolator sees (Population.py:697-702): a grid with a collapsed direction drops it
     if geo.subvol_type == "grid" and np.any(np.asarray(geo.grid) == 1):
         tb["interp_dims"] = np.nonzero(np.asarray(geo.grid) != 1)[0].astype(np.int64)
@@ -137,7 +138,7 @@ def state_from_reference(ph, pop):
     st.subvol_heat_flux = np.array(pop.subvol_heat_flux, dtype=float)
     st.res_energy_balance = np.array(pop.res_energy_balance, dtype=float) if R > 0 else np.zeros(0)
     st.res_heat_flux = np.array(pop.res_heat_flux, dtype=float) if R > 0 else np.zeros((0, 3))
-    st.N_leaving = np.zeros(R, dtype=int)
+    st.N_leaving = np.array(pop.N_leaving, dtype=int) if R > 0 else np.zeros(0, dtype=int)     # Population.py:344
     st.current_timestep = int(pop.current_timestep)
     return st
 
@@ -146,7 +147,10 @@ def reference_step(pop, geo, ph):
     """``run_timestep`` minus the every-100-step output branch (Population.py:1743-1769)."""
     pop.drift()
     if pop.n_of_reservoirs > 0:
-        pop.fill_reservoirs(geo, ph)
+        if pop.res_gen == "one_to_one":                                  # Population.py:1746-1749
+            pop.fill_reservoirs(geo, ph, n_leaving=pop.N_leaving)
+        else:
+            pop.fill_reservoirs(geo, ph)
         pop.add_reservoir_particles(geo)
     pop.boundary_scattering(geo, ph)
     pop.refresh_temperatures(geo, ph)

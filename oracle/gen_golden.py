@@ -90,6 +90,9 @@ CONFIGS = {
     "c4_cylinder_voronoi": (PARAMS_C4.format(eta=3, n=3000), 5),
     "c5_box_grid_radial": (PARAMS_C5.format(eta=2, n=3000), 5),
     "c6_cylinder_voronoi_radial": (PARAMS_C4.format(eta=3, n=3000).replace("--temp_interp nearest", "--temp_interp radial"), 5),
+    # the two debug emission modes of Population.fill_reservoirs on the cross-plane film
+    "c7_fixed_rate": (PARAMS_C2.format(n=3000) + "--reservoir_gen fixed_rate\n", 5),
+    "c8_one_to_one": (PARAMS_C2.format(n=3000) + "--reservoir_gen one_to_one\n", 5),
 }
 
 STATE_FIELDS = ("positions", "modes", "omega", "group_vel", "occupation", "n_timesteps", "collision_facets",
@@ -130,8 +133,9 @@ def load_fixture(path):
     """-> (tb, st0, refs{k: dict})  used by the tests."""
     z = np.load(path, allow_pickle=False)
     tb = unpack(z, "tb_")
-    for k in ("temp_interp",):
-        tb[k] = str(tb[k])
+    for k in ("temp_interp", "res_gen"):
+        if k in tb:
+            tb[k] = str(tb[k])
     s0 = unpack(z, "st0_")
     st = nko.State(**{k: s0[k] for k in ("positions", "modes", "omega", "group_vel", "occupation", "n_timesteps",
                                          "collision_facets", "collision_positions", "collision_cond", "temperatures",
@@ -140,7 +144,7 @@ def load_fixture(path):
               "res_heat_flux", "omega_modes"):
         setattr(st, k, s0[k])
     st.N_p = int(st.subvol_N_p.sum())
-    st.N_leaving = np.zeros(tb["res_facet"].shape[0], dtype=int)
+    st.N_leaving = np.sum(tb["enter_prob"], axis=(1, 2)).round().astype(int)      # Population.py:344
     st.current_timestep = 0
     refs = {}
     for k in z.files:

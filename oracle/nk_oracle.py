@@ -97,6 +97,15 @@ class SequenceRNG:
     def emit_dt_uniform(self, n, ids, step):
         return np.random.rand(n)                                   # Population.py:393
 
+    def emit_dice(self, shape, ids, step):
+        return np.random.rand(*shape)                              # Population.py:410 (fixed_rate)
+
+    def one_to_one_mode(self, n, ids, step):
+        return np.random.rand(n)                                   # Population.py:471
+
+    def one_to_one_dt(self, n, ids, step):
+        return np.random.rand(n)                                   # Population.py:483
+
     def surface(self, n, faces, p, ids, step):
         f = np.random.choice(faces, size=n, p=p)                   # Mesh.py:937
         s = np.random.rand(n, 1)                                    # Mesh.py:941
@@ -119,6 +128,15 @@ class KeyedRNG:
 
     def emit_dt_uniform(self, n, ids, step):
         return philox.uniforms(ids, step, philox.STREAM_EMIT_A, self.seed)[0]
+
+    def emit_dice(self, shape, ids, step):
+        return philox.uniforms(ids, step, philox.STREAM_EMIT_C, self.seed)[0].reshape(shape)
+
+    def one_to_one_mode(self, n, ids, step):
+        return philox.uniforms(ids, step, philox.STREAM_EMIT_C, self.seed)[0]
+
+    def one_to_one_dt(self, n, ids, step):
+        return philox.uniforms(ids, step, philox.STREAM_EMIT_C, self.seed)[1]
 
     def surface(self, n, faces, p, ids, step):
         u_face = philox.uniforms(ids, step, philox.STREAM_EMIT_A, self.seed)[1]
@@ -331,16 +349,61 @@ def drift(tb, st):
     st.n_timesteps -= 1
 
 
-def fill_reservoirs(tb, st, rng):
-    """Constant-rate emission.  Population.py:356-406, :491-508.  Returns the new-particle arrays."""
+def _fill_one_to_one(tb, st, rng):
+    """--reservoir_gen one_to_one (Population.py:457-489): every reservoir re-emits as many particles as it absorbed in
+    the previous step, modes drawn from the entry-probability roulette, entry time uniform in the step."""
     dt = tb["dt"]
     enter_prob = tb["enter_prob"]
     R, Q, J = enter_prob.shape
     step = st.current_timestep
+    pos = np.zeros((0, 3)); modes = np.zeros((0, 2), dtype=int); facet_id = np.zeros(0, dtype=int)
+    dt_in = np.zeros(0); ids = np.zeros(0, dtype=np.int64)
+    for i in range(R):
+        facet = tb["res_facet"][i]
+        n = int(st.N_leaving[i])
+        if n > 0:
+            roulette = np.cumsum(enter_prob[i, :, :])
+            roulette /= roulette.max()
+            r_ids = philox.one_to_one_id(step, R, i, np.arange(n), Q * J)
+            u = rng.one_to_one_mode(n, r_ids, step)
+            flat_i = bisect_left_fixed(roulette, u) if rng.keyed else np.searchsorted(roulette, u)
+            new_q = np.floor(flat_i / J).astype(int)
+            new_j = flat_i - new_q * J
+            modes = np.vstack((modes, np.vstack((new_q, new_j)).T))
+            dt_in = np.concatenate((dt_in, dt * rng.one_to_one_dt(n, r_ids, step)))
+            facet_id = np.concatenate((facet_id, (np.ones(n) * facet).astype(int)))
+            faces = facet_faces(tb, facet)
+            areas = tb["face_areas"][faces]
+            f, s, r = rng.surface(n, faces, areas / areas.sum(), r_ids, step)
+            pos = np.vstack((pos, sample_surface_points(tb, f, s, r)))
+            ids = np.concatenate((ids, r_ids))
+    return pos, modes, facet_id, dt_in, ids
+
+
+def fill_reservoirs(tb, st, rng):
+    """Emission.  Population.py:356-406 (constant), :408-455 (fixed_rate), :457-489 (one_to_one), :491-508.
+    Returns the new-particle arrays."""
+    dt = tb["dt"]
+    enter_prob = tb["enter_prob"]
+    R, Q, J = enter_prob.shape
+    step = st.current_timestep
+    res_gen = str(tb.get("res_gen", "constant"))
     fixed_np = np.floor(enter_prob).astype(int)
-    st.res_counter += enter_prob - fixed_np
-    in_mask = (st.res_counter >= 1).astype(int)
-    st.res_counter -= in_mask
+    if res_gen == "constant":
+        st.res_counter += enter_prob - fixed_np
+        in_mask = (st.res_counter >= 1).astype(int)
+        st.res_counter -= in_mask
+        lead = st.res_counter                      # numerator of the c == 1 entry time
+    elif res_gen == "fixed_rate":
+        rr, mm = np.meshgrid(np.arange(R), np.arange(Q * J), indexing="ij")
+        dice = rng.emit_dice((R, Q, J), philox.emission_id(step, R, rr.ravel(), mm.ravel(), Q * J, 1), step)
+        in_mask = (dice <= (enter_prob - fixed_np)).astype(int)
+        lead = dice
+    elif res_gen == "one_to_one":
+        pos, modes, facet_id, dt_in, ids = _fill_one_to_one(tb, st, rng)
+        return _new_particle_arrays(tb, pos, modes, facet_id, dt_in, ids)
+    else:
+        raise ValueError("unknown reservoir generation mode " + res_gen)
     in_np = fixed_np + in_mask
     N_p_facet = in_np.sum(axis=(1, 2))
 
@@ -357,7 +420,7 @@ def fill_reservoirs(tb, st, rng):
                 c_ids = philox.emission_id(step, R, i, c_modes[:, 0] * J + c_modes[:, 1], Q * J, c)
                 p = enter_prob[i, c_modes[:, 0], c_modes[:, 1]]
                 if c == 1:
-                    c_dt_in = dt * (1 - (st.res_counter[i, c_modes[:, 0], c_modes[:, 1]] / p))
+                    c_dt_in = dt * (1 - (lead[i, c_modes[:, 0], c_modes[:, 1]] / p))
                 else:
                     u = rng.emit_dt_uniform(c_modes.shape[0], c_ids, step)
                     c_dt_in = dt * (1 - (c - 1 + u) / p)
@@ -371,6 +434,11 @@ def fill_reservoirs(tb, st, rng):
             f, s, r = rng.surface(n, faces, areas / areas.sum(), r_ids, step)
             pos = np.vstack((pos, sample_surface_points(tb, f, s, r)))
             ids = np.concatenate((ids, r_ids))
+    return _new_particle_arrays(tb, pos, modes, facet_id, dt_in, ids)
+
+
+def _new_particle_arrays(tb, pos, modes, facet_id, dt_in, ids):
+    """Population.py:491-508."""
     new = dict(positions=pos, modes=modes, facet_id=facet_id, dt_in=dt_in, ids=ids)
     if modes.shape[0] > 0:
         new["group_vel"] = tb["group_vel"][modes[:, 0], modes[:, 1], :]

@@ -24,7 +24,8 @@ MASK = np.uint64(0xFFFFFFFF)
 
 STREAM_EMIT_A = 0
 STREAM_EMIT_B = 1
-STREAM_ROUGH0 = 2
+STREAM_ROUGH0 = 2          # + index of the boundary event within the step (< 2**16)
+STREAM_EMIT_C = 1 << 16    # fixed_rate dice / one_to_one (mode, entry time)
 
 EMIT_ID_BASE = np.int64(1) << np.int64(62)
 EMIT_CMAX = 64
@@ -71,3 +72,9 @@ def emission_id(step, n_res, r, qj, n_modes, c):
     """Stable 64-bit id of the c-th copy (c >= 1) of mode qj emitted by reservoir r at `step`."""
     step = np.asarray(step, dtype=np.int64)
     return EMIT_ID_BASE + ((step * n_res + np.asarray(r, dtype=np.int64)) * n_modes + np.asarray(qj, dtype=np.int64)) * EMIT_CMAX + (np.asarray(c, dtype=np.int64) - 1)
+
+
+def one_to_one_id(step, n_res, r, k, n_modes):
+    """Id of the k-th particle re-emitted by reservoir r at `step` in the one_to_one mode (k < n_modes * EMIT_CMAX)."""
+    step = np.asarray(step, dtype=np.int64)
+    return EMIT_ID_BASE + (step * n_res + np.asarray(r, dtype=np.int64)) * (np.int64(n_modes) * EMIT_CMAX) + np.asarray(k, dtype=np.int64)
