@@ -131,3 +131,41 @@ def test_rbf_weights_reproduce_scipy_interpolator(name, golden_dir):
         got = (r ** 3) @ coef[:S] + coef[S] + ((x[:, dims] - shift) / scale) @ coef[S + 1:]
         want = RBFInterpolator(c[:, dims], T, kernel="cubic")(x[:, dims])
         assert np.allclose(got, want, rtol=1e-9, atol=0)
+
+
+def test_wire_primitives_are_closed_and_have_the_analytic_volume():
+    """zigzag / corrugated / castle / star / freewire (reference Geometry.py:144-412): parameter meaning as upstream,
+    checked through the closed-surface property and the analytic volume of the stacked prisms / frusta."""
+    from nanokappa_b200.classes.Mesh import Mesh
+    from nanokappa_b200.routines.primitives import generate
+    area = lambda R, n: 0.5 * n * R * R * np.sin(2 * np.pi / n)
+    frustum = lambda a, b, L: L / 3 * (a + b + np.sqrt(a * b))
+    cases = [
+        ("zigzag", [500, 100, 30, 20, 8, 4], 4 * 500 * area(100, 8)),
+        ("corrugated", [300, 100, 60, 10, 5], 5 * frustum(area(100, 10), area(60, 10), 300)),
+        ("castle", [400, 200, 100, 50, 12, 5, 1], 3 * 400 * area(100, 12) + 2 * 200 * area(50, 12)),
+        ("castle", [400, 200, 100, 50, 12, 4, 0], 2 * 400 * area(100, 12) + 2 * 200 * area(50, 12)),
+        ("star", [300, 100, 40, 5], 300 * 5 * 100 * 40 * np.sin(np.pi / 5)),
+        ("freewire", [100, 300, 60, 200, 80, 100, 9], frustum(area(100, 9), area(60, 9), 300) + frustum(area(60, 9), area(80, 9), 200)),
+    ]
+    for shape, dims, volume in cases:
+        v, f = generate(shape, dims)
+        edges = np.sort(np.vstack((f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]])), axis=1)
+        _, counts = np.unique(edges, axis=0, return_counts=True)
+        assert (counts == 2).all(), f"{shape}: surface is not closed"
+        m = Mesh(v, f)
+        assert np.isclose(m.volume, volume, rtol=1e-12), shape
+        x = m.sample_volume(200)
+        assert m.contains(x).all()
+
+
+def test_geometry_accepts_wire_primitive(tmp_path):
+    from nanokappa_b200.classes.Geometry import Geometry
+    text = gen_golden.PARAMS_C4.format(eta=3, n=100).replace("--geometry cylinder --dimensions 3000 600 10", "--geometry corrugated --dimensions 500 300 200 10 4") \
+        .replace("--subvolumes voronoi 6", "--subvolumes slice 4 2")
+    args = ap.initialise_parser(False).parse_args(text.replace("kappa-m313131.hdf5", "synthetic:3").split())
+    args.results_folder = str(tmp_path)
+    with contextlib.redirect_stdout(io.StringIO()):
+        geo = Geometry(args)
+    assert len(geo.res_facets) == 2 and len(geo.rough_facets) == geo.n_of_facets - 2
+    assert np.isclose(np.ptp(geo.bounds[:, 2]), 2000.0)
