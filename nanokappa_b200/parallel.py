@@ -11,6 +11,11 @@ coupling is the per-subvolume / per-reservoir sums.  So:
   per reservoir N_leaving / E_bal / flux, emitted, absorbed]`` (<= a few KB) between the two halves of
   the step: ``step_local`` (stream + emit + boundary kernels) and ``step_finalize`` (T_sv, results).
 
+* live counts drift apart because absorption depends on position: ``ShardedEngine.rebalance`` (every ~100 steps, outside
+  a timestep) all-gathers the live counts and migrates whole particle rows from the fullest to the emptiest ranks with
+  point-to-point NCCL sends over NVLink.  Which rank owns a particle has no effect on the physics (ids and draws are
+  keyed by the particle, sums are global), so results are unchanged.
+
 ``ShardedEngine`` is the torch.distributed plumbing around ``Engine``; the collective is NCCL over
 NVLink on GPUs (``backend='nccl'``).  ``reduce_fn`` can be replaced (tests use gloo on host copies).
 """
@@ -27,6 +32,31 @@ from ._lib import check
 def mode_range(rank, world, n_modes):
     """Contiguous share [lo, hi) of the flat mode index owned by `rank` (same split as nk_set_rank)."""
     return (n_modes * rank) // world, (n_modes * (rank + 1)) // world
+
+
+F64_FIELDS = ("px", "py", "pz", "tc", "occ", "cx", "cy", "cz", "pid")      # pid travels as its bit pattern
+I32_FIELDS = ("mode", "omode", "cfacet")
+
+
+def rebalance_plan(counts):
+    """Deterministic transfer list [(src, dst, n)] that brings every rank to total // W (+1 for the first total % W ranks).
+    Every rank computes the same plan from the all-gathered live counts."""
+    counts = [int(c) for c in counts]
+    W, total = len(counts), sum(counts)
+    target = [total // W + (1 if r < total % W else 0) for r in range(W)]
+    surplus = [[r, counts[r] - target[r]] for r in range(W) if counts[r] > target[r]]
+    deficit = [[r, target[r] - counts[r]] for r in range(W) if counts[r] < target[r]]
+    plan, i, j = [], 0, 0
+    while i < len(surplus) and j < len(deficit):
+        n = min(surplus[i][1], deficit[j][1])
+        plan.append((surplus[i][0], deficit[j][0], n))
+        surplus[i][1] -= n
+        deficit[j][1] -= n
+        if surplus[i][1] == 0:
+            i += 1
+        if deficit[j][1] == 0:
+            j += 1
+    return plan
 
 
 def shard_bounds(rank, world, n_particles):
@@ -90,3 +120,96 @@ class ShardedEngine:
             self.engine.step_local()
             dist.all_reduce(self.acc, group=self.group)
             self.engine.step_finalize()
+
+    # ---- periodic rebalance of the live particles ------------------------------------------------------
+    def live_counts(self):
+        _, alive = self.engine.slot_count()
+        if self.world == 1:
+            return [alive]
+        t = torch.zeros(self.world, dtype=torch.int64, device=self.engine.device)
+        t[self.rank] = alive
+        dist.all_reduce(t, group=self.group)
+        return [int(v) for v in t.tolist()]
+
+    def extract_for(self, plan):
+        """Remove the rows this rank sends under `plan` -> {dst: (f64 block (9, n), i32 block (3, n))}.  The rows are
+        a strided sample of the (mode-ordered, compacted) shard, so the mode mix of both sides stays representative."""
+        eng = self.engine
+        mine = [(dst, n) for src, dst, n in plan if src == self.rank and n > 0]
+        if not mine:
+            return {}
+        eng.flush_relaxation()
+        eng.sort_by_mode()                      # live particles in [0, n_live), free list dropped
+        n_live, _ = eng.slot_count()
+        n_out = sum(n for _, n in mine)
+        if n_out > n_live:
+            raise ValueError("rebalance plan asks for more particles than this rank holds")
+        t = eng.t
+        pick = torch.div(torch.arange(n_out, device=eng.device, dtype=torch.int64) * n_live, n_out, rounding_mode="floor")
+        out, lo = {}, 0
+        for dst, n in mine:
+            rows = pick[lo:lo + n]
+            f = torch.stack([t[k][rows] if k != "pid" else t[k][rows].view(torch.float64) for k in F64_FIELDS])
+            i = torch.stack([t[k][rows] for k in I32_FIELDS])
+            out[dst] = (f.contiguous(), i.contiguous())
+            lo += n
+        t["mode"][pick] = -1
+        eng.sort_by_mode()                      # compacts the holes away
+        return out
+
+    def insert_from(self, blocks):
+        """Append the rows received from other ranks ([(f64 block, i32 block)]) and restore the mode order."""
+        eng = self.engine
+        blocks = [b for b in blocks if b[0].shape[1] > 0]
+        if not blocks:
+            return 0
+        eng.flush_relaxation()
+        eng.sort_by_mode()
+        n_live, _ = eng.slot_count()
+        n_in = sum(b[0].shape[1] for b in blocks)
+        if n_live + n_in > eng.cap:
+            raise ValueError(f"rebalance: {n_live} + {n_in} particles exceed the capacity {eng.cap} of rank {self.rank}")
+        t, lo = eng.t, n_live
+        for f, i in blocks:
+            n = f.shape[1]
+            for a, k in enumerate(F64_FIELDS):
+                t[k][lo:lo + n] = f[a] if k != "pid" else f[a].view(torch.int64)
+            for a, k in enumerate(I32_FIELDS):
+                t[k][lo:lo + n] = i[a]
+            lo += n
+        torch.cuda.synchronize(eng.device)
+        check(eng.ctx, eng.L.nk_set_slot_count(eng.ctx, lo), "nk_set_slot_count")
+        eng.sort_by_mode()
+        return n_in
+
+    def rebalance(self, tolerance=0.02):
+        """All-gather the live counts; if the spread exceeds `tolerance` x mean, migrate rows (NCCL send / recv) so that
+        every rank holds total / world particles.  Call between timesteps.  Returns the number of rows this rank moved."""
+        if self.world == 1:
+            return 0
+        counts = self.live_counts()
+        mean = sum(counts) / self.world
+        if mean == 0 or (max(counts) - min(counts)) <= tolerance * mean:
+            return 0
+        plan = rebalance_plan(counts)
+        dev = self.engine.device
+        out = self.extract_for(plan)
+        ops, recv = [], []
+        for src, dst, n in plan:
+            if n == 0:
+                continue
+            if src == self.rank:
+                f, i = out[dst]
+                ops += [dist.P2POp(dist.isend, f, dst, group=self.group), dist.P2POp(dist.isend, i, dst, group=self.group)]
+            elif dst == self.rank:
+                f = torch.empty((len(F64_FIELDS), n), dtype=torch.float64, device=dev)
+                i = torch.empty((len(I32_FIELDS), n), dtype=torch.int32, device=dev)
+                recv.append((f, i))
+                ops += [dist.P2POp(dist.irecv, f, src, group=self.group), dist.P2POp(dist.irecv, i, src, group=self.group)]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        moved = sum(b[0].shape[1] for b in out.values()) + self.insert_from(recv)
+        if self.fused:
+            self._synced = False                # ranks leave the maintenance pass at different times
+        return moved

@@ -68,6 +68,29 @@ def main():
             ok &= bool(np.array_equal(rf["subvol_N_p"], rs["subvol_N_p"]))
             ok &= bool(np.allclose(rf["subvol_temperature"], rs["subvol_temperature"], rtol=1e-12, atol=0))
             print(f"[{name}] world={world} fused==nccl==single: {ok}  N_p={rs['N_p']}", flush=True)
+        # unbalanced shards (rank 0 owns 70 %), rebalanced by NCCL point-to-point migration half way: same union
+        n_all = st.positions.shape[0]
+        cut = [0] + [int(n_all * (0.7 + 0.3 * r / (world - 1))) for r in range(world)]
+        cut[-1] = n_all
+        sh = ShardedEngine(make(tb, st, slice(cut[rank], cut[rank + 1]), local), rank, world)
+        assert sh.enable_fused_exchange()
+        sh.step(STEPS // 2)
+        before = sh.live_counts()
+        moved = sh.rebalance(tolerance=0.01)
+        after = sh.live_counts()
+        sh.step(STEPS - STEPS // 2)
+        pr, rr = sh.engine.particles(), sh.engine.results()
+        ok &= bool(max(after) - min(after) <= 1 and sum(after) == sum(before) and (moved > 0 or world == 1))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {k: pr[k] for k in ("ids", "modes", "collision_facets")})
+        if rank == 0:
+            ids = np.concatenate([g["ids"] for g in gathered]); order = np.argsort(ids)
+            ok &= bool(np.array_equal(ids[order], ps["ids"]))
+            ok &= bool(np.array_equal(np.concatenate([g["modes"] for g in gathered])[order], ps["modes"]))
+            ok &= bool(np.array_equal(np.concatenate([g["collision_facets"] for g in gathered])[order], ps["collision_facets"]))
+            ok &= bool(np.array_equal(rr["subvol_N_p"], rs["subvol_N_p"]))
+            ok &= bool(np.allclose(rr["subvol_temperature"], rs["subvol_temperature"], rtol=1e-12, atol=0))
+            print(f"[{name}] rebalance {before} -> {after}: {ok}", flush=True)
     flag = torch.tensor([int(ok)], device=torch.device("cuda", local))
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -77,3 +77,54 @@ def test_two_shards_equal_one_context(name, golden_dir):
         assert np.array_equal(r["subvol_N_p"], rs["subvol_N_p"]) and np.array_equal(r["N_leaving"], rs["N_leaving"])
         assert np.allclose(r["subvol_temperature"], rs["subvol_temperature"], rtol=1e-12, atol=0)
     assert sum(e.slot_count()[1] for e in shards) == single.slot_count()[1]
+
+
+def test_rebalance_between_emulated_ranks_keeps_the_union(golden_dir):
+    """SURVEY 8e periodic rebalance: an 80/20 split of the particles, migrated to 50/50 half way through the run by
+    ShardedEngine.extract_for / insert_from (the NCCL send/recv in between is replaced by handing the blocks over),
+    must still give the single-context census, modes, facets and temperatures."""
+    from nanokappa_b200.parallel import ShardedEngine, rebalance_plan
+    tb, st, _ = gen_golden.load_fixture(os.path.join(golden_dir, "c1_mixed.npz"))
+    n = st.positions.shape[0]
+    cut = int(0.8 * n)
+    single = _engine(tb, st, slice(0, n))
+    shards = [ShardedEngine(_engine(tb, st, slice(0, cut)), 0, 2), ShardedEngine(_engine(tb, st, slice(cut, n)), 1, 2)]
+    accs = [_acc(s.engine) for s in shards]
+
+    def run(k):
+        for _ in range(k):
+            for s in shards:
+                s.engine.step_local()
+            torch.cuda.synchronize()
+            total = accs[0] + accs[1]
+            for a in accs:
+                a.copy_(total)
+            for s in shards:
+                s.engine.step_finalize()
+
+    single.step(24)
+    run(12)
+    counts = [s.engine.slot_count()[1] for s in shards]
+    plan = rebalance_plan(counts)
+    assert plan and plan[0][0] == 0 and plan[0][1] == 1
+    out = shards[0].extract_for(plan)
+    assert shards[1].extract_for(plan) == {}
+    moved = shards[1].insert_from([out[1]])
+    after = [s.engine.slot_count()[1] for s in shards]
+    assert moved == plan[0][2] and sum(after) == sum(counts) and abs(after[0] - after[1]) <= 1
+    run(12)
+    ps = single.particles()
+    parts = [s.engine.particles() for s in shards]
+    ids = np.concatenate([p["ids"] for p in parts])
+    order = np.argsort(ids)
+    assert np.array_equal(ids[order], ps["ids"])
+    cat = lambda k: np.concatenate([p[k] for p in parts])[order]
+    assert np.array_equal(cat("modes"), ps["modes"]) and np.array_equal(cat("omega_modes"), ps["omega_modes"])
+    assert np.array_equal(cat("collision_facets"), ps["collision_facets"])
+    assert np.allclose(cat("positions"), ps["positions"], rtol=1e-13, atol=1e-9, equal_nan=True)
+    assert np.allclose(cat("occupation"), ps["occupation"], rtol=1e-9, atol=0)
+    rs = single.results()
+    for s in shards:
+        r = s.engine.results()
+        assert np.array_equal(r["subvol_N_p"], rs["subvol_N_p"])
+        assert np.allclose(r["subvol_temperature"], rs["subvol_temperature"], rtol=1e-12, atol=0)

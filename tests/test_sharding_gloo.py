@@ -80,3 +80,23 @@ def test_mode_and_particle_partitions_cover_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             assert [shard_bounds(r, world, n) for r in range(world)] == spans
+
+
+def test_rebalance_plan_is_balanced_conservative_and_deterministic():
+    """Host logic of the periodic rebalance (nanokappa_b200.parallel.rebalance_plan): every rank derives the same
+    transfer list from the all-gathered live counts; applying it leaves max - min <= 1 and moves nothing twice."""
+    from nanokappa_b200.parallel import rebalance_plan
+    rng = np.random.default_rng(1)
+    for world in (1, 2, 3, 8):
+        for _ in range(50):
+            counts = rng.integers(0, 10 ** 6, world).tolist()
+            plan = rebalance_plan(counts)
+            assert plan == rebalance_plan(list(counts))
+            after = list(counts)
+            for src, dst, n in plan:
+                assert n > 0 and src != dst and counts[src] > counts[dst]
+                after[src] -= n
+                after[dst] += n
+            assert sum(after) == sum(counts) and max(after) - min(after) <= 1
+            assert len({s for s, _, _ in plan} & {d for _, d, _ in plan}) == 0     # nobody both sends and receives
+    assert rebalance_plan([5, 5, 5]) == []
