@@ -354,6 +354,16 @@ def gpu_arm(a):
     updates = 0.5 * (n_alive0 + n_alive1) * a.steps          # N_p is the global live count (all ranks)
     value = updates / (ms * 1e-3)
 
+    if os.environ.get("NK_TRACE", "0") != "0" and rank == 0:      # diagnostics only: device-side marks of single steps
+        for _ in range(4):
+            one_step()
+            tr = (C.c_uint64 * 8)()
+            check(eng.ctx, eng.L.nk_debug_trace(eng.ctx, tr), "nk_debug_trace")
+            t0 = tr[0] or tr[2]
+            print("[nk trace] us since streaming kernel start: " + " ".join(
+                f"{name}={((tr[i] - t0) / 1e3 if tr[i] else float('nan')):.1f}" for i, name in enumerate(
+                    ("step_in", "step_out", "rare_in", "rare_items_done", "finalize_in", "finalize_out"))), file=sys.stderr, flush=True)
+
     # ---- roofline of the streaming kernel: algorithmic bytes = 84 B x live particles of this rank per launch
     peak, peak_src = load_peaks()
     step_ms = prof["k_step"] / max(nprof, 1)

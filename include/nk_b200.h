@@ -220,6 +220,10 @@ int nk_advance_host(nk_ctx* ctx, int64_t n_in, int n_steps,
                     int64_t* n_out, double* T_sv_out, double* E_sv_out, int64_t* N_sv_out);
 /* Bytes the last nk_advance_host call moved over PCIe in each direction (counted from the copies it issued). */
 int nk_last_transfer_bytes(nk_ctx* ctx, int64_t* h2d, int64_t* d2h);
+/* Diagnostics (NK_TRACE=1 in the environment of nk_create): %globaltimer marks [ns] of the last step, then cleared:
+ * 0 streaming kernel first block in, 1 last block out, 2 rare-path kernel first block in, 3 last item done,
+ * 4 closing block enters the finalize, 5 leaves it; 6-7 unused. */
+int nk_debug_trace(nk_ctx* ctx, uint64_t* out8);
 
 /* ---- multi-GPU ------------------------------------------------------------------------------------ */
 

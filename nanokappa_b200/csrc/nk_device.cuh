@@ -20,6 +20,16 @@ NK_DEVI double norm3(double x, double y, double z) { return sqrt(dot3(x, y, z, x
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 keyed by (particle id, step, stream); see oracle/philox.py for the contract
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long nk_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// trace slots: 0 k_step first block in, 1 k_step last block out, 2 k_rare first block in, 3 k_rare last item done,
+//              4 finalize in, 5 finalize out
+#define NK_TRACE_MARK_FIRST(P, slot) do { if ((P).trace && threadIdx.x == 0 && blockIdx.x == 0) (P).trace[slot] = nk_globaltimer(); } while (0)
+#define NK_TRACE_MARK_MAX(P, slot)   do { if ((P).trace && threadIdx.x == 0) atomicMax((P).trace + (slot), nk_globaltimer()); } while (0)
+
 #define NK_STREAM_EMIT_A 0u
 #define NK_STREAM_EMIT_B 1u
 #define NK_STREAM_ROUGH0 2u          // + index of the boundary event within the step
@@ -99,6 +109,52 @@ NK_DEVI double nk_interp_table(const double* xp, const double* fp, int n, double
     if (xp[lo] == x) return fp[lo];
     double slope = nk_div(nk_sub(fp[lo + 1], fp[lo]), nk_sub(xp[lo + 1], xp[lo]));
     return nk_add(nk_mul(slope, nk_sub(x, xp[lo])), fp[lo]);
+}
+
+// Same result as nk_interp_table, but the bracket search starts at index `guess` and gallops outwards: a couple of
+// probes instead of log2(n) dependent loads when the guess is close (uniform grids, slowly changing temperatures).
+NK_DEVI double nk_interp_table_from(const double* xp, const double* fp, int n, double x, double below, double above, int guess) {
+    if (x != x) return x;
+    if (x < xp[0]) return below;
+    if (x > xp[n - 1]) return above;
+    int lo = max(0, min(guess, n - 2)), hi;
+    if (xp[lo] <= x) {
+        int stepw = 1;
+        hi = lo + 1;
+        while (hi < n - 1 && xp[hi] <= x) { lo = hi; hi = min(n - 1, hi + stepw); stepw <<= 1; }
+    } else {
+        int stepw = 1;
+        hi = lo; lo = max(0, hi - 1);
+        while (lo > 0 && xp[lo] > x) { hi = lo; lo = max(0, lo - stepw); stepw <<= 1; }
+    }
+    while (hi - lo > 1) {              // invariant xp[lo] <= x < xp[hi] (or hi == n-1)
+        int mid = (lo + hi) >> 1;
+        if (xp[mid] <= x) lo = mid; else hi = mid;
+    }
+    if (x >= xp[n - 1]) return fp[n - 1];
+    if (xp[lo] == x) return fp[lo];
+    double slope = nk_div(nk_sub(fp[lo + 1], fp[lo]), nk_sub(xp[lo + 1], xp[lo]));
+    return nk_add(nk_mul(slope, nk_sub(x, xp[lo])), fp[lo]);
+}
+
+// Warp-aggregated counter increment: the lanes that arrive together issue ONE atomic and share the range.
+NK_DEVI unsigned long long nk_agg_inc(unsigned long long* ctr) {
+    const unsigned int m = __activemask();
+    const unsigned int lane = threadIdx.x & 31u;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(ctr, (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+NK_DEVI unsigned int nk_agg_inc(unsigned int* ctr) {
+    const unsigned int m = __activemask();
+    const unsigned int lane = threadIdx.x & 31u;
+    const int leader = __ffs(m) - 1;
+    unsigned int base = 0;
+    if ((int)lane == leader) base = atomicAdd(ctr, (unsigned int)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -654,6 +654,7 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step_ta
     double* binX = reinterpret_cast<double*>(binF + 3 * S);
     unsigned int* binC = reinterpret_cast<unsigned int*>(binX + 4 * S);
     NkSvHot h = nk_load_hot(P, binC + S + (S & 1));
+    NK_TRACE_MARK_FIRST(P, 0);
     for (int i = threadIdx.x; i < S; i += blockDim.x) { binE[i] = 0; binC[i] = 0u; for (int k = 0; k < 3; ++k) binF[3 * i + k] = 0; for (int k = 0; k < 4; ++k) binX[4 * i + k] = 0.0; }
     __syncthreads();
 
@@ -690,6 +691,7 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step_ta
     }
     __syncthreads();
     nk_flush_bins<FLUX>(P, binE, binF, binX, binC);
+    NK_TRACE_MARK_MAX(P, 1);
 }
 
 // ---- variant A1: one particle per thread, 64-bit accesses (fewer live registers -> more resident warps) ------
@@ -900,15 +902,15 @@ __device__ __forceinline__ void nk_accumulate(const NkP& P, double* acc, const N
 // of the same launch never touch the same entry.
 __device__ __forceinline__ void nk_kill(const NkP& P, double* acc, long long i) {
     P.mode[i] = -1;
-    unsigned long long k = atomicAdd((unsigned long long*)&P.dyn->fr_tail, 1ull);
+    unsigned long long k = nk_agg_inc((unsigned long long*)&P.dyn->fr_tail);
     P.freelist[k % (unsigned long long)P.cap] = (int)i;
     atomicAdd(acc + NK_ACC_NABS(P.S, P.R), 1.0);
 }
 __device__ __forceinline__ long long nk_take_slot(const NkP& P) {
-    long long old = (long long)atomicAdd((unsigned long long*)&P.dyn->fr_head, 1ull);
+    // claims beyond fr_snap are not returned: the finalize clamps fr_head back to fr_snap
+    long long old = (long long)nk_agg_inc((unsigned long long*)&P.dyn->fr_head);
     if (old < P.dyn->fr_snap) return P.freelist[old % P.cap];
-    atomicAdd((unsigned long long*)&P.dyn->fr_head, (unsigned long long)(-1LL));       // nothing recyclable: append
-    long long slot = (long long)atomicAdd((unsigned long long*)&P.dyn->n_slots, 1ull);
+    long long slot = (long long)nk_agg_inc((unsigned long long*)&P.dyn->n_slots);      // nothing recyclable: append
     if (slot >= P.cap) {
         atomicAdd((unsigned long long*)&P.dyn->n_slots, (unsigned long long)(-1LL));
         atomicOr(&P.dyn->error, NK_ERR_CAPACITY);
@@ -953,7 +955,7 @@ __device__ __forceinline__ void nk_emit_particle(const NkP& P, const NkGeo& G, d
     nk_store_particle(P, slot, p);
     P.pid[slot] = p.id;
     {
-        const unsigned int k = atomicAdd(&P.dyn->n_new, 1u);
+        const unsigned int k = nk_agg_inc(&P.dyn->n_new);
         if ((long long)k < P.newslots_cap) P.newslots[k] = (int)slot;
     }
     nk_accumulate(P, acc, p, with_flux);
@@ -1045,9 +1047,12 @@ __device__ void nk_finalize_block(const NkP& P, double* sm) {
         if (P.norm_mean) { norm = nk_div(P.n_active, cnt); if (norm != norm) norm = 0.0; }
         else norm = nk_div(P.n_active, nk_mul(P.particle_density, P.sv_volume[s]));
         double Tprev = P.T_sv[s];
-        double ref = nk_interp_table(P.Ta, P.Ea, P.nE, Tprev, P.Ea[0], P.Ea[P.nE - 1]);
+        // both tables share the index of the (uniform) temperature grid, and T moves little per step: start the bracket
+        // searches at the previous temperature's index
+        const int ig = P.nE > 1 ? (int)((Tprev - P.Ta[0]) * P.Ta_inv_d) : 0;
+        double ref = nk_interp_table_from(P.Ta, P.Ea, P.nE, Tprev, P.Ea[0], P.Ea[P.nE - 1], ig);
         double E = nk_add(nk_div(nk_mul(esum, norm), P.dens_norm), ref);
-        double Tn = nk_interp_table(P.Ea, P.Ta, P.nE, E, P.Ta[0], P.Ta[P.nE - 1]);
+        double Tn = nk_interp_table_from(P.Ea, P.Ta, P.nE, E, P.Ta[0], P.Ta[P.nE - 1], ig);
         sT[s] = Tn; sN[s] = cnt;
         out[NK_OUT_T(S, R) + s] = Tn;
         out[NK_OUT_E(S, R) + s] = E;
@@ -1116,6 +1121,7 @@ __device__ void nk_finalize_block(const NkP& P, double* sm) {
         d->n_hits = 0;
         d->n_emit = 0;
         d->n_new = 0;
+        if (d->fr_head > d->fr_snap) d->fr_head = d->fr_snap;      // over-claims of an exhausted free list (nk_take_slot)
         d->fr_snap = d->fr_tail;           // slots freed in this step become recyclable from the next one
         d->blocks_done = 0;
     }
@@ -1172,7 +1178,10 @@ __global__ void __launch_bounds__(1024) k_finalize(NkP P) {
 #define NK_RARE_FACES 128
 #define NK_RARE_FACETS 64
 template <bool FUSE>
-__global__ void __launch_bounds__(NK_RARE_THREADS) k_rare(NkP P) {
+#ifndef NK_RARE_MIN_BLOCKS
+#define NK_RARE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(NkP P) {
     __shared__ NkFace sfaces[NK_RARE_FACES];
     __shared__ int sfi[4 * NK_RARE_FACETS];
     __shared__ double sfd[6 * NK_RARE_FACETS];
@@ -1181,6 +1190,7 @@ __global__ void __launch_bounds__(NK_RARE_THREADS) k_rare(NkP P) {
     NkGeo G;
     G.faces = P.faces; G.bc = P.facet_bc; G.partner = P.facet_partner; G.res = P.facet_res; G.rough = P.facet_rough;
     G.normal = P.facet_normal; G.centroid = P.facet_centroid;
+    NK_TRACE_MARK_FIRST(P, 2);
     if (P.F <= NK_RARE_FACES) {
         const double* src = reinterpret_cast<const double*>(P.faces);
         double* dst = reinterpret_cast<double*>(sfaces);
@@ -1217,6 +1227,7 @@ __global__ void __launch_bounds__(NK_RARE_THREADS) k_rare(NkP P) {
         }
     }
     __syncthreads();
+    NK_TRACE_MARK_MAX(P, 3);
     for (int k = threadIdx.x; k < nacc; k += blockDim.x)
         if (racc[k] != 0.0) atomicAdd(P.acc + k, racc[k]);
     if (threadIdx.x == 0) {
@@ -1235,7 +1246,10 @@ __global__ void __launch_bounds__(NK_RARE_THREADS) k_rare(NkP P) {
         if (s_last) {
             __threadfence();
             if (P.comm_on) nk_exchange_sums(P);
+            if (P.trace && threadIdx.x == 0) P.trace[4] = nk_globaltimer();
             nk_finalize_block(P, sm_fin);
+            __syncthreads();
+            if (P.trace && threadIdx.x == 0) P.trace[5] = nk_globaltimer();
         }
     }
 }
@@ -1384,6 +1398,12 @@ int nk_create(int device, nk_ctx** out) {
     ctx->P.world = 1;
     ctx->P.slot_lo = 0; ctx->P.slot_hi = 0x7fffffffffffffffLL; ctx->P.scan_emit = 1;
     if (const char* e = getenv("NK_HOST_PIPELINE")) ctx->use_pipeline = strcmp(e, "0") != 0;
+    ctx->P.trace = nullptr;
+    if (const char* e = getenv("NK_TRACE")) {
+        if (strcmp(e, "0") != 0 && cudaMalloc(&ctx->P.trace, 8 * sizeof(unsigned long long)) == cudaSuccess)
+            cudaMemset(ctx->P.trace, 0, 8 * sizeof(unsigned long long));
+    }
+    if (const char* e = getenv("NK_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));   // experiment: 32 / 64 / 128
     if (const char* e = getenv("NK_STEP_TAB")) { ctx->use_tab = strcmp(e, "0") != 0; ctx->force_tab = !strcmp(e, "force"); }
     if (const char* e = getenv("NK_STEP_IMPL")) ctx->step_variant = !strcmp(e, "tma") ? 1 : (!strcmp(e, "ldg1") ? 2 : (!strcmp(e, "pf") ? 3 : 0));
     NkDyn z; memset(&z, 0, sizeof(z));
@@ -1546,6 +1566,7 @@ int nk_set_phonon(nk_ctx* ctx, int Q, int J, int NT, const double* Tg, const dou
     P.nE = nE; P.hbar = hbar; P.kb = kb; P.V_uc = V_uc; P.n_active = (double)n_active;
     P.dens_norm = (double)Q * V_uc;
     P.Tg_inv_d = 1.0 / (Tg[1] - Tg[0]);
+    P.Ta_inv_d = (nE > 1 && Ta[nE - 1] != Ta[0]) ? (nE - 1) / (Ta[nE - 1] - Ta[0]) : 0.0;
     ctx->h_mode.resize(4 * (size_t)M);
     for (int m = 0; m < M; ++m) { ctx->h_mode[4 * (size_t)m] = mp[m].omega; ctx->h_mode[4 * (size_t)m + 1] = mp[m].vx; ctx->h_mode[4 * (size_t)m + 2] = mp[m].vy; ctx->h_mode[4 * (size_t)m + 3] = mp[m].vz; }
     ctx->h_tau.assign(tau, tau + (size_t)NT * M);
@@ -2221,6 +2242,15 @@ int nk_advance_host(nk_ctx* ctx, int64_t n_in, int n_steps, double* px, double* 
                   : nk_advance_host_simple(ctx, n_in, n_steps, px, py, pz, tc, occ, mode, omode, cfacet, cx, cy, cz, pid, n_out);
     if (rc) return rc;
     return nk_get_results(ctx, T_sv_out, E_sv_out, N_sv_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int nk_debug_trace(nk_ctx* ctx, uint64_t* out8) {
+    cudaSetDevice(ctx->device);
+    if (!ctx->P.trace) { ctx->err = "tracing is off (NK_TRACE=1 at nk_create)"; return -1; }
+    NK_CK(cudaStreamSynchronize(ctx->stream));
+    NK_CK(cudaMemcpy(out8, ctx->P.trace, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    NK_CK(cudaMemset(ctx->P.trace, 0, 8 * sizeof(uint64_t)));
+    return 0;
 }
 
 int nk_last_transfer_bytes(nk_ctx* ctx, int64_t* h2d, int64_t* d2h) {

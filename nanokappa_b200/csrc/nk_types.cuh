@@ -37,23 +37,29 @@ struct __align__(64) NkModeHot {
     double t[4];
 };
 
-struct NkDyn {                   // device-resident, mutated by kernels
-    long long n_slots;           // slots [0, n_slots) are live or on the free list
-    long long fr_head;           // free-slot ring: next entry to recycle
-    long long fr_tail;           //                 next entry to write (slots freed by absorption)
-    long long fr_snap;           //                 fr_tail at the end of the previous step (pop limit)
+struct alignas(128) NkDyn {      // device-resident, mutated by kernels
+    // line 0: fields touched once per block or once per step
+    long long fr_snap;           // free-slot ring: fr_tail at the end of the previous step (pop limit)
     long long n_alive;
     long long step;              // Population.current_timestep
-    unsigned int n_hits;         // particles whose collision falls inside this step
     unsigned int n_emit;         // emission-list entries of this step
-    unsigned int n_new;          // slots filled by emission in this step (newslots list)
     unsigned int last_hits;      // n_hits / n_new of the step that was closed last (dirty-slot list for host patches)
     unsigned int last_new;
-    unsigned int pad2;
     int relax_pending;           // lifetime_scattering of step-1 still to be applied to `occ`
     int error;                   // sticky device-side error bits
     unsigned int blocks_done;    // last-block detection
-    unsigned int pad;
+    char pad0[128 - 3 * 8 - 6 * 4];
+    // the counters the rare path hammers with atomics get a 128-byte line (= an L2 slice queue) each
+    long long n_slots;           // slots [0, n_slots) are live or on the free list
+    char pad1[120];
+    long long fr_head;           // free-slot ring: next entry to recycle (may overshoot fr_snap inside a step; clamped by the finalize)
+    char pad2[120];
+    long long fr_tail;           //                 next entry to write (slots freed by absorption)
+    char pad3[120];
+    unsigned int n_hits;         // particles whose collision falls inside this step
+    char pad4[124];
+    unsigned int n_new;          // slots filled by emission in this step (newslots list)
+    char pad5[124];
 };
 
 #define NK_ERR_CAPACITY 1        // emission ran out of slots
@@ -96,6 +102,7 @@ struct NkP {
     int tau_i0;
     double Tg_inv_d;                  // 1 / (Tg[1]-Tg[0]) guess
     int nE; const double* Ea; const double* Ta;
+    double Ta_inv_d;                  // (nE-1)/(Ta[nE-1]-Ta[0]): index guess into the E(T) table
     double hbar, kb, V_uc, n_active, dens_norm;   // dens_norm = Q * V_uc
     // ---- population
     double dt, particle_density, eVpsa2_in_Wm2, a_in_m;
@@ -127,6 +134,7 @@ struct NkP {
     double* res_acc;                  // (R*4) E_bal + flux accumulated over the convergence window
     double* out;                      // results block, see NK_OUT_* offsets
     NkDyn* dyn;
+    unsigned long long* trace;        // NK_TRACE=1: %globaltimer marks of the last step (see nk_debug_trace), else null
     int rank, world;
     // ---- fused exchange of the accumulator vector over NVLink peer memory (nk_comm_*)
     int comm_on;                      // 1: the last block of k_rare all-reduces P.acc through the mailboxes
