@@ -125,3 +125,30 @@ def test_binary_checkpoint_continues_exactly(tmp_path):
     assert np.allclose(p["occupation"], q["occupation"], rtol=1e-12, atol=0)
     assert np.allclose(pop.subvol_temperature, pop2.subvol_temperature, rtol=1e-13, atol=0)
     assert np.array_equal(pop.engine.res_counter(), pop2.engine.res_counter())
+
+
+def test_converged_film_matches_reference(tmp_path, golden_dir):
+    """Converged run, independent random draws: kappa, the temperature profile, the heat flux and the particle count
+    of a short cross-plane film must agree with what the REFERENCE ITSELF produced (tests/golden/converged_film.json,
+    written by oracle/gen_converged.py executing /root/reference) within the combined block-averaged standard
+    errors (4 sigma; the error estimates themselves come from 10 blocks, i.e. are known to ~25 %)."""
+    import json
+    from oracle import gen_converged as gc
+    ref = json.load(open(os.path.join(golden_dir, "converged_film.json")))
+    args, geo, ph, pop = _population(ref["params"], tmp_path, seed=5)
+    kappa, T, flux, N = [], [], [], []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for k in range(1, ref["steps"] + 1):
+            pop.run_timestep(geo, ph)
+            if k % 10 == 0 and k > ref["discard"]:
+                kappa.append(float(pop.kappa)); T.append(pop.subvol_temperature.copy())
+                flux.append(pop.subvol_heat_flux[:, 0].copy()); N.append(float(pop.N_p))
+    got = gc.summarise(kappa, T, flux, N)
+    assert len(kappa) == ref["rows"]
+    for name in ("kappa", "T", "flux_x", "N_p"):
+        g, r = got[name], ref[name]
+        gm, ge, rm, re_ = (np.asarray(x, dtype=float) for x in (g["mean"], g["stderr"], r["mean"], r["stderr"]))
+        band = 4.0 * np.sqrt(ge ** 2 + re_ ** 2)
+        assert (np.abs(gm - rm) <= band).all(), f"{name}: gpu {gm} +- {ge} vs reference {rm} +- {re_}"
+    # and the error bars are small enough for the comparison to mean something: 0.2 % on kappa
+    assert 4.0 * np.hypot(got["kappa"]["stderr"], ref["kappa"]["stderr"]) < 2e-3 * ref["kappa"]["mean"] * 2
