@@ -67,7 +67,7 @@ def workload(n_total, mesh):
     if CASE["name"] == "c1":      # parameters_test.txt geometry (configs[0]): rough walls + linear T interpolation -> general kernel path
         text = PARAMS_C1.format(mat="/nonexistent_material_folder/", mesh=mesh, n=int(n_total), eta=CASE.get("eta", 0))
     else:
-        text = PARAMS.format(mat="/nonexistent_material_folder/", mesh=mesh, n=int(n_total))
+        text = PARAMS.format(mat="/nonexistent_material_folder/", mesh=mesh, n=int(n_total)).replace("--subvolumes slice 20 0", "--subvolumes slice {} 0".format(int(CASE.get("slices", 20))))
     args = ap.initialise_parser(False).parse_args(text.split())
     args.results_folder = "/tmp"
     with contextlib.redirect_stdout(io.StringIO()):
@@ -236,11 +236,11 @@ def reference_arm(a):
 
 
 def config_dict(a, n_per_gpu, where):
-    wl = ("si_thin_film_crossplane: box (2e4 A)^3, T 302/298 K on x faces, periodic sides, 20 slice SVs, nearest T, dt 1 ps "
+    wl = ("si_thin_film_crossplane: box (2e4 A)^3, T 302/298 K on x faces, periodic sides, {} slice SVs, nearest T, dt 1 ps ".format(int(CASE.get("slices", 20))) +
           "(BASELINE configs[1] geometry at configs[4] scale)") if CASE["name"] == "c2" else \
          (f"parameters_test geometry: box 5e3x1e3x1e3 A, T/T/R/R/P, eta {CASE.get('eta', 0)} A, 10 slice SVs, linear T (BASELINE configs[0] scaled up; diagnostic)")
     return {"workload": wl,
-            "particles_per_gpu": int(n_per_gpu), "mode_table": f"synthetic {a.mesh}^3 x 6", "subvolumes": 20 if CASE["name"] == "c2" else 10,
+            "particles_per_gpu": int(n_per_gpu), "mode_table": f"synthetic {a.mesh}^3 x 6", "subvolumes": int(CASE.get("slices", 20)) if CASE["name"] == "c2" else 10,
             "particle_order": "tiled modes (as initialised)" if getattr(a, "no_sort", False) else "sorted by mode at set-up",
             "l2_policy": "inputs larger than L2 (no flush)" if n_per_gpu * 44 > 2.6e8 else "state fits L2; L2 flushed between timed steps",
             "parallelism": f"particle shards x{a.gpus}, per-step all-reduce of the per-SV vectors ({getattr(a, 'exchange', '?')})" if a.gpus > 1 else "single GPU"}
@@ -492,8 +492,9 @@ def main():
     p.add_argument("--no-sort", action="store_true", help="keep the tiled mode order of Population.initialise_modes")
     p.add_argument("--case", default="c2", choices=["c2", "c1"], help="c2: README cross-plane film (headline); c1: parameters_test.txt geometry (diagnostic)")
     p.add_argument("--eta", type=float, default=0.0, help="roughness of the R facets in --case c1")
+    p.add_argument("--slices", type=int, default=20, help="slice subvolumes of --case c2 (20 = README case; 100 = the configs[2] layout, diagnostic)")
     a = p.parse_args()
-    CASE["name"] = a.case; CASE["eta"] = a.eta
+    CASE["name"] = a.case; CASE["eta"] = a.eta; CASE["slices"] = a.slices
     if a.impl == "reference":
         reference_arm(a)
     else:

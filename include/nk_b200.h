@@ -210,9 +210,13 @@ int nk_energy_table(int device, int n_modes, const double* omega, const uint8_t*
  * The host arrays are the caller's copy of Population's particle arrays (Population.py:1724-1800 reads and writes
  * self.positions, self.n_timesteps, self.occupation, self.modes, ... in place); on return they hold the state after
  * the step(s).  For one step of >= 2^20 particles the call is pipelined: slots are cut into chunks, chunk c+1 is
- * uploaded while chunk c streams through the kernel and chunk c-1's positions/clocks are downloaded; arrays the
- * streaming kernel never writes come back as a packed patch of the slots the rare path touched (NK_HOST_PIPELINE=0
- * selects the plain upload-all / step / download-all sequence; both leave identical host arrays). */
+ * uploaded while chunk c streams through the kernel and chunk c-1's positions/clocks are downloaded.  Only the fields the
+ * streaming kernel reads travel densely; collision facet / position and ids go up as a sparse patch for the particles
+ * that collide in this step (found by a host scan of tc < 1) and come back as a sparse patch of the slots the rare path
+ * touched.  During the call the device arrays are a scratch image of the host arrays: do not mix this entry point with
+ * device-resident stepping (nk_step) on the same ctx without re-uploading the state.  NK_HOST_SPARSE=0 uploads the cold
+ * arrays densely, NK_HOST_PIPELINE=0 selects the plain upload-all / step / download-all sequence; all three leave
+ * identical host arrays. */
 int nk_advance_host(nk_ctx* ctx, int64_t n_in, int n_steps,
                     double* px, double* py, double* pz, double* tc, double* occ,
                     int32_t* mode, int32_t* omode, int32_t* cfacet,

@@ -1267,7 +1267,7 @@ __global__ void __launch_bounds__(256) k_flush_relax(NkP P) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         int md = P.mode[i];
         if (md < 0) continue;
-        int om = P.omode[i];
+        const int om = P.has_rough ? P.omode[i] : md;      // as the streaming kernel: without rough facets omode == mode
         double4 ma, mt;
         nk_ld256(&P.mhot[md].omega, ma);
         nk_ld256(&P.mhot[md].t[0], mt);
@@ -1284,16 +1284,32 @@ struct NkPatch {                  // structure of arrays, `cap` records each
     int *slot, *mode, *omode, *cfacet; long long* pid;
     double *x, *y, *z, *tc, *cx, *cy, *cz;
 };
-__global__ void __launch_bounds__(256) k_pack_dirty(NkP P, NkPatch out, long long cap, unsigned int* count) {
+__global__ void __launch_bounds__(256) k_pack_dirty(NkP P, NkPatch out, long long cap, long long offset, unsigned int* count) {
     const unsigned int nh = P.dyn->last_hits, nn = P.dyn->last_new;
-    const unsigned long long total = (unsigned long long)nh + nn;
+    const long long total = (long long)nh + nn;
     if (blockIdx.x == 0 && threadIdx.x == 0) { count[0] = nh; count[1] = nn; }
-    if ((long long)total > cap || (long long)nn > P.newslots_cap) return;       // host falls back to a full download
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+    if ((long long)nn > P.newslots_cap) return;              // the list of new slots is incomplete: the host decides
+    const long long hi = min(total, offset + cap);           // this round packs entries [offset, hi) of hits ++ new slots
+    for (long long i = offset + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
         const int s = i < nh ? P.hitlist[i] : P.newslots[i - nh];
-        out.slot[i] = s; out.mode[i] = P.mode[s]; out.omode[i] = P.omode[s]; out.cfacet[i] = P.cfacet[s]; out.pid[i] = P.pid[s];
-        out.x[i] = P.px[s]; out.y[i] = P.py[s]; out.z[i] = P.pz[s]; out.tc[i] = P.tc[s];
-        out.cx[i] = P.cx[s]; out.cy[i] = P.cy[s]; out.cz[i] = P.cz[s];
+        const long long o = i - offset;
+        out.slot[o] = s; out.mode[o] = P.mode[s]; out.omode[o] = P.omode[s]; out.cfacet[o] = P.cfacet[s]; out.pid[o] = P.pid[s];
+        out.x[o] = P.px[s]; out.y[o] = P.py[s]; out.z[o] = P.pz[s]; out.tc[o] = P.tc[s];
+        out.cx[o] = P.cx[s]; out.cy[o] = P.cy[s]; out.cz[o] = P.cz[s];
+    }
+}
+
+// Host-buffer pipeline, upload side: the streaming kernel never reads collision facet / position or the particle id,
+// the rare path reads them only for particles whose collision falls inside the step (tc < 1 on entry).  The host
+// finds those (a scan of `tc`), packs their cold fields and this kernel scatters them into the device arrays.
+struct NkCold {                   // structure of arrays, `cap` records each
+    int *slot, *cfacet, *omode; long long* pid; double *cx, *cy, *cz;
+};
+__global__ void __launch_bounds__(256) k_unpack_cold(NkP P, NkCold in, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int s = in.slot[i];
+        P.cfacet[s] = in.cfacet[i]; P.omode[s] = in.omode[i]; P.pid[s] = in.pid[i];
+        P.cx[s] = in.cx[i]; P.cy[s] = in.cy[i]; P.cz[s] = in.cz[i];
     }
 }
 
@@ -1325,6 +1341,9 @@ struct nk_ctx {
     std::vector<cudaEvent_t> ev_in, ev_k;
     void* patch_dev = nullptr; void* patch_host = nullptr; long long patch_cap = 0;
     unsigned int* patch_count_dev = nullptr;
+    void* cold_dev = nullptr; void* cold_host = nullptr; long long cold_cap = 0;
+    cudaEvent_t ev_cold = nullptr;
+    bool sparse_cold = true;       // NK_HOST_SPARSE=0: upload the cold arrays densely
     bool use_pipeline = true;      // NK_HOST_PIPELINE=0 disables it
     long long xfer_h2d = 0, xfer_d2h = 0;   // bytes of the last nk_advance_host call
     void* comm_block = nullptr;    // flags + mailboxes of the fused exchange
@@ -1398,6 +1417,7 @@ int nk_create(int device, nk_ctx** out) {
     ctx->P.world = 1;
     ctx->P.slot_lo = 0; ctx->P.slot_hi = 0x7fffffffffffffffLL; ctx->P.scan_emit = 1;
     if (const char* e = getenv("NK_HOST_PIPELINE")) ctx->use_pipeline = strcmp(e, "0") != 0;
+    if (const char* e = getenv("NK_HOST_SPARSE")) ctx->sparse_cold = strcmp(e, "0") != 0;
     ctx->P.trace = nullptr;
     if (const char* e = getenv("NK_TRACE")) {
         if (strcmp(e, "0") != 0 && cudaMalloc(&ctx->P.trace, 8 * sizeof(unsigned long long)) == cudaSuccess)
@@ -1423,6 +1443,9 @@ void nk_destroy(nk_ctx* ctx) {
     if (ctx->s_in) { cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out); }
     if (ctx->patch_dev) cudaFree(ctx->patch_dev);
     if (ctx->patch_host) cudaFreeHost(ctx->patch_host);
+    if (ctx->cold_dev) cudaFree(ctx->cold_dev);
+    if (ctx->cold_host) cudaFreeHost(ctx->cold_host);
+    if (ctx->ev_cold) cudaEventDestroy(ctx->ev_cold);
     if (ctx->patch_count_dev) cudaFree(ctx->patch_count_dev);
     delete ctx;
 }
@@ -1615,7 +1638,7 @@ int nk_set_reservoirs(nk_ctx* ctx, int R, const int32_t* res_facet, const double
     NK_UP(dd, double, enter_prob, (size_t)R * P.M); P.enter_prob = dd;
     NK_UP(dd, double, res_counter, (size_t)R * P.M); P.res_counter = dd;
     int2* de; NK_UP(de, int2, (const int2*)nullptr, (size_t)std::max(R, 1) * P.M); P.emitlist = de;
-    P.newslots_cap = (long long)std::max(R, 1) * P.M * 2;
+    P.newslots_cap = std::max<long long>((long long)std::max(R, 1) * P.M * 2, 1 << 20);
     int* dn; NK_UP(dn, int, (const int*)nullptr, (size_t)P.newslots_cap); P.newslots = dn;
     // emission-mode extras (nk_set_reservoir_mode): initial N_leaving (Population.py:344), roulette of one_to_one (:465-466)
     P.res_gen = NK_RESGEN_CONSTANT;
@@ -1665,7 +1688,7 @@ int nk_set_boundary_luts(nk_ctx* ctx, int Fr, const double* spec, const uint8_t*
     NK_UP(du, unsigned char, ts, n); P.true_spec = du;
     NK_UP(di, int, so, n); P.spec_out = di;
     NK_UP(dd, double, rou, n); P.roulette = dd;
-    ctx->has_rough = Fr > 0;
+    ctx->has_rough = Fr > 0; P.has_rough = Fr > 0;
     return 0;
 }
 
@@ -1873,6 +1896,7 @@ int nk_init_collisions(nk_ctx* ctx) {
     return 0;
 }
 
+#define NK_TAB_MAX_ENTRIES (6LL << 20)      // 96 MB of {n0, decay} pairs
 static size_t nk_step_smem(const NkP& P) { return (nk_sv_smem_doubles(P.S) + 8 * (size_t)P.S) * 8 + ((size_t)P.S + 2) * 4 + nk_hot_smem_bytes(P.S) + 32; }
 
 // chunked launch of the streaming kernel for the host-buffer pipeline: chunk c waits for its upload event and
@@ -1880,7 +1904,8 @@ static size_t nk_step_smem(const NkP& P) { return (nk_sv_smem_doubles(P.S) + 8 *
 struct NkChunkPlan { int n; long long chunk, total; cudaEvent_t* ev_in; cudaEvent_t* ev_k; };
 
 // kernels of one step; fuse_finalize: the last block of k_rare closes the step (no collective in between)
-static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* plan = nullptr) {
+// phase 0: whole step; 1: streaming part only (chunks of the host pipeline); 2: rare path + closing of a step started with 1
+static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* plan = nullptr, int phase = 0) {
     cudaSetDevice(ctx->device);
     if (nk_check_ready(ctx)) return -1;
     const NkP& P = ctx->P;
@@ -1891,9 +1916,14 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     const bool relax = ctx->h_relax_pending;
     const bool flux = ((ctx->h_step + 1) % P.n_dt_to_conv) == 0;
     int variant = ctx->step_variant;                          // 0: 2 particles/thread LDG.128, 1: TMA pipeline, 2: 1 particle/thread
+    if (phase == 2) variant = ctx->last_variant;
+    else {
     if (variant == 1 && (P.cap % NK_TILE) != 0) variant = 0;
     // per-(mode, subvolume) tables pay off once there are a few particles per table entry
-    if (variant == 0 && ctx->use_tab && fast && P.hot_tab && (ctx->force_tab || ctx->h_slots_hint >= 2 * (long long)P.M * P.S)) variant = 4;
+    // ... and while the table (16 B per entry, rebuilt every step) stays L2-sized: at S = 100 x 1.8e5 modes (286 MB) the
+    // rebuild costs what the leaner inner loop saves (profiles/README.md)
+    if (variant == 0 && ctx->use_tab && fast && P.hot_tab &&
+        (ctx->force_tab || (ctx->h_slots_hint >= 2 * (long long)P.M * P.S && (long long)P.M * P.S <= NK_TAB_MAX_ENTRIES))) variant = 4;
     if (variant == 4 && ctx->tab_dirty) {
         k_mode_tables<<<ctx->n_sm * 8, 256, nk_hot_smem_bytes(P.S), ctx->stream>>>(P);
         NK_CK(cudaGetLastError());
@@ -1930,6 +1960,9 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     }
     NK_CK(cudaGetLastError());
     nk_prof_mark(ctx);
+    ctx->last_variant = variant;
+    }
+    if (phase == 1) return 0;
     const size_t fin_smem = (3 * (size_t)P.S + nk_acc_len(P.S, P.R)) * 8;
     if (fuse_finalize) k_rare<true><<<ctx->n_sm * 16, NK_RARE_THREADS, fin_smem, ctx->stream>>>(P);
     else k_rare<false><<<ctx->n_sm * 16, NK_RARE_THREADS, fin_smem, ctx->stream>>>(P);
@@ -2126,10 +2159,14 @@ static int nk_advance_host_pipelined(nk_ctx* ctx, int64_t n_in, double* px, doub
     NK_CK(cudaStreamSynchronize(ctx->s_in));
     if (nk_set_slot_count(ctx, n_in)) return -1;
     lap("census");
-    // 2. uploads, chunk by chunk
+    // 2. uploads, chunk by chunk: only what the streaming kernel reads (48 of the 84 bytes per particle)
     long long chunk = ((long long)n_in + NK_PIPE_CHUNKS - 1) / NK_PIPE_CHUNKS;
     chunk = (chunk + 511) / 512 * 512;
     const int nc = (int)(((long long)n_in + chunk - 1) / chunk);
+    const bool sparse = ctx->sparse_cold;
+    // without rough facets nothing separates the omega-carrying mode from the mode: the kernels do not read `omode` then,
+    // except the rare path for the particles it handles (it travels with the cold record)
+    const bool dense_omode = ctx->has_rough || !sparse;
     for (int c = 0; c < nc; ++c) {
         const size_t lo = (size_t)c * chunk, len = std::min<size_t>(chunk, n - lo);
         NK_CK(cudaMemcpyAsync(P.px + lo, px + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
@@ -2137,17 +2174,12 @@ static int nk_advance_host_pipelined(nk_ctx* ctx, int64_t n_in, double* px, doub
         NK_CK(cudaMemcpyAsync(P.pz + lo, pz + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
         NK_CK(cudaMemcpyAsync(P.tc + lo, tc + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
         NK_CK(cudaMemcpyAsync(P.occ + lo, occ + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
-        NK_CK(cudaMemcpyAsync(P.omode + lo, omode + lo, len * 4, cudaMemcpyHostToDevice, ctx->s_in));
-        NK_CK(cudaMemcpyAsync(P.cfacet + lo, cfacet + lo, len * 4, cudaMemcpyHostToDevice, ctx->s_in));
-        NK_CK(cudaMemcpyAsync(P.cx + lo, cx + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
-        NK_CK(cudaMemcpyAsync(P.cy + lo, cy + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
-        NK_CK(cudaMemcpyAsync(P.cz + lo, cz + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
-        NK_CK(cudaMemcpyAsync(P.pid + lo, pid + lo, len * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        if (dense_omode) NK_CK(cudaMemcpyAsync(P.omode + lo, omode + lo, len * 4, cudaMemcpyHostToDevice, ctx->s_in));
         NK_CK(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
     }
-    // 3. streaming kernel per chunk + rare path + finalize on the ctx stream
+    // 3. the streaming kernel per chunk on the ctx stream, as soon as the chunk has arrived
     NkChunkPlan plan{nc, chunk, (long long)n_in, ctx->ev_in.data(), ctx->ev_k.data()};
-    if (nk_step_kernels(ctx, true, &plan)) return -1;
+    if (nk_step_kernels(ctx, true, &plan, 1)) return -1;
     // 4. positions and clocks of every chunk go back as soon as its kernel is done (stale for the few slots the
     //    rare path rewrites afterwards: the patch below overrides them)
     for (int c = 0; c < nc; ++c) {
@@ -2158,9 +2190,94 @@ static int nk_advance_host_pipelined(nk_ctx* ctx, int64_t n_in, double* px, doub
         NK_CK(cudaMemcpyAsync(pz + lo, P.pz + lo, len * 8, cudaMemcpyDeviceToHost, ctx->s_out));
         NK_CK(cudaMemcpyAsync(tc + lo, P.tc + lo, len * 8, cudaMemcpyDeviceToHost, ctx->s_out));
     }
+    lap("enq hot");
+    // 4b. cold fields (collision facet / position, id): only the rare path reads them, and only for particles whose
+    //     collision falls inside this step (tc - 1 < 0 <=> tc < 1, exact in IEEE).  While the DMA engines are busy with the
+    //     chunks, host threads scan `tc` for those particles and pack their cold fields; NaN clocks are included (harmless).
+    long long n_cold = -1;
+    if (sparse) {
+        const long long want_cold = std::max<long long>(1 << 16, P.cap / 32);
+        if (ctx->cold_cap != want_cold) {
+            if (ctx->cold_dev) cudaFree(ctx->cold_dev);
+            if (ctx->cold_host) cudaFreeHost(ctx->cold_host);
+            ctx->cold_dev = ctx->cold_host = nullptr; ctx->cold_cap = 0;
+            NK_CK(cudaMalloc(&ctx->cold_dev, (size_t)want_cold * 44));
+            NK_CK(cudaMallocHost(&ctx->cold_host, (size_t)want_cold * 44));
+            ctx->cold_cap = want_cold;
+        }
+        if (!ctx->ev_cold) NK_CK(cudaEventCreateWithFlags(&ctx->ev_cold, cudaEventDisableTiming));
+        const long long ccap = ctx->cold_cap;
+        auto carve_cold = [&](void* base) {
+            NkCold q; char* b = (char*)base;
+            q.cx = (double*)b; q.cy = q.cx + ccap; q.cz = q.cy + ccap; q.pid = (long long*)(q.cz + ccap);
+            q.slot = (int*)(q.pid + ccap); q.cfacet = q.slot + ccap; q.omode = q.cfacet + ccap;
+            return q;
+        };
+        const NkCold cd = carve_cold(ctx->cold_dev), ch = carve_cold(ctx->cold_host);
+        const unsigned hw = std::thread::hardware_concurrency();
+        const int nt = (int)std::max(1u, std::min(16u, hw ? hw : 1u));
+        std::vector<std::vector<int>> found(nt);
+        {
+            std::vector<std::thread> th;
+            for (int k = 0; k < nt; ++k)
+                th.emplace_back([&, k]() {
+                    const long long i0 = (long long)n_in * k / nt, i1 = (long long)n_in * (k + 1) / nt;
+                    std::vector<int>& v = found[k];
+                    for (long long i = i0; i < i1; ++i)
+                        if (!(tc[i] >= 1.0) && mode[i] >= 0) v.push_back((int)i);
+                });
+            for (auto& t : th) t.join();
+        }
+        std::vector<long long> off(nt + 1, 0);
+        for (int k = 0; k < nt; ++k) off[k + 1] = off[k] + (long long)found[k].size();
+        if (off[nt] <= ccap) {
+            n_cold = off[nt];
+            std::vector<std::thread> th;
+            for (int k = 0; k < nt; ++k)
+                th.emplace_back([&, k]() {
+                    long long o = off[k];
+                    for (int i : found[k]) {
+                        ch.slot[o] = i; ch.cfacet[o] = cfacet[i]; ch.omode[o] = omode[i]; ch.pid[o] = pid[i];
+                        ch.cx[o] = cx[i]; ch.cy[o] = cy[i]; ch.cz[o] = cz[i];
+                        ++o;
+                    }
+                });
+            for (auto& t : th) t.join();
+            const size_t k = (size_t)n_cold;
+            if (k) {
+                NK_CK(cudaMemcpyAsync(cd.cx, ch.cx, k * 8, cudaMemcpyHostToDevice, ctx->s_in));
+                NK_CK(cudaMemcpyAsync(cd.cy, ch.cy, k * 8, cudaMemcpyHostToDevice, ctx->s_in));
+                NK_CK(cudaMemcpyAsync(cd.cz, ch.cz, k * 8, cudaMemcpyHostToDevice, ctx->s_in));
+                NK_CK(cudaMemcpyAsync(cd.pid, ch.pid, k * 8, cudaMemcpyHostToDevice, ctx->s_in));
+                NK_CK(cudaMemcpyAsync(cd.slot, ch.slot, k * 4, cudaMemcpyHostToDevice, ctx->s_in));
+                NK_CK(cudaMemcpyAsync(cd.cfacet, ch.cfacet, k * 4, cudaMemcpyHostToDevice, ctx->s_in));
+                NK_CK(cudaMemcpyAsync(cd.omode, ch.omode, k * 4, cudaMemcpyHostToDevice, ctx->s_in));
+            }
+            NK_CK(cudaEventRecord(ctx->ev_cold, ctx->s_in));
+            NK_CK(cudaStreamWaitEvent(st, ctx->ev_cold, 0));
+            if (k) {
+                k_unpack_cold<<<ctx->n_sm * 2, 256, 0, st>>>(P, cd, n_cold);
+                NK_CK(cudaGetLastError());
+            }
+        }
+        lap("cold scan");
+    }
+    if (n_cold < 0) {             // dense upload of the cold arrays (NK_HOST_SPARSE=0, or more candidates than the staging holds)
+        NK_CK(cudaMemcpyAsync(P.cfacet, cfacet, n * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.cx, cx, n * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.cy, cy, n * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.cz, cz, n * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        NK_CK(cudaMemcpyAsync(P.pid, pid, n * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        if (!dense_omode) NK_CK(cudaMemcpyAsync(P.omode, omode, n * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        if (!ctx->ev_cold) NK_CK(cudaEventCreateWithFlags(&ctx->ev_cold, cudaEventDisableTiming));
+        NK_CK(cudaEventRecord(ctx->ev_cold, ctx->s_in));
+        NK_CK(cudaStreamWaitEvent(st, ctx->ev_cold, 0));
+    }
+    // 4c. rare path + closing of the step
+    if (nk_step_kernels(ctx, true, nullptr, 2)) return -1;
     // 5. tail: flush the deferred relaxation, pack the dirty slots
     if (nk_flush_relaxation(ctx)) return -1;
-    k_pack_dirty<<<ctx->n_sm * 4, 256, 0, st>>>(P, pd, cap, ctx->patch_count_dev);
+    k_pack_dirty<<<ctx->n_sm * 4, 256, 0, st>>>(P, pd, cap, 0, ctx->patch_count_dev);
     NK_CK(cudaGetLastError());
     unsigned int cnt[2] = {0, 0};
     NK_CK(cudaMemcpyAsync(cnt, ctx->patch_count_dev, sizeof(cnt), cudaMemcpyDeviceToHost, st));
@@ -2171,18 +2288,43 @@ static int nk_advance_host_pipelined(nk_ctx* ctx, int64_t n_in, double* px, doub
     if (nk_get_slot_count(ctx, &ns, &na)) return -1;
     const size_t m = (size_t)ns;
     const long long nd = (long long)cnt[0] + cnt[1];
-    const bool patch_ok = nd <= cap && (long long)cnt[1] <= P.newslots_cap;
-    // the (small) patch first, on s_out; the occupations follow on the ctx stream while the host applies the patch
-    if (patch_ok) {
-        const size_t k = (size_t)nd;
+    const bool patch_ok = (long long)cnt[1] <= P.newslots_cap;
+    if (!patch_ok && n_cold >= 0) {
+        // the new-slot list overflowed AND the device holds the cold arrays only for the touched slots: neither a patch
+        // nor a full download can rebuild the host arrays
+        ctx->err = "nk_advance_host: more emitted particles than the new-slot list holds; rerun with NK_HOST_SPARSE=0 or NK_HOST_PIPELINE=0";
+        return -1;
+    }
+    auto fetch_patch = [&](size_t k, cudaStream_t q) -> int {
         double* const dsrc[7] = {pd.x, pd.y, pd.z, pd.tc, pd.cx, pd.cy, pd.cz};
         double* const ddst[7] = {ph.x, ph.y, ph.z, ph.tc, ph.cx, ph.cy, ph.cz};
-        for (int a = 0; a < 7; ++a) NK_CK(cudaMemcpyAsync(ddst[a], dsrc[a], k * 8, cudaMemcpyDeviceToHost, ctx->s_out));
-        NK_CK(cudaMemcpyAsync(ph.pid, pd.pid, k * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        for (int a = 0; a < 7; ++a) NK_CK(cudaMemcpyAsync(ddst[a], dsrc[a], k * 8, cudaMemcpyDeviceToHost, q));
+        NK_CK(cudaMemcpyAsync(ph.pid, pd.pid, k * 8, cudaMemcpyDeviceToHost, q));
         int* const isrc[4] = {pd.slot, pd.mode, pd.omode, pd.cfacet};
         int* const idst[4] = {ph.slot, ph.mode, ph.omode, ph.cfacet};
-        for (int a = 0; a < 4; ++a) NK_CK(cudaMemcpyAsync(idst[a], isrc[a], k * 4, cudaMemcpyDeviceToHost, ctx->s_out));
-    }
+        for (int a = 0; a < 4; ++a) NK_CK(cudaMemcpyAsync(idst[a], isrc[a], k * 4, cudaMemcpyDeviceToHost, q));
+        return 0;
+    };
+    // scattered writes, latency-bound on one core: a few host threads (a slot listed twice carries the same values)
+    auto apply_patch = [&](long long cntp) {
+        auto apply = [&](long long i0, long long i1) {
+            for (long long i = i0; i < i1; ++i) {
+                const int s = ph.slot[i];
+                px[s] = ph.x[i]; py[s] = ph.y[i]; pz[s] = ph.z[i]; tc[s] = ph.tc[i];
+                cx[s] = ph.cx[i]; cy[s] = ph.cy[i]; cz[s] = ph.cz[i];
+                mode[s] = ph.mode[i]; omode[s] = ph.omode[i]; cfacet[s] = ph.cfacet[i]; pid[s] = ph.pid[i];
+            }
+        };
+        const unsigned hw = std::thread::hardware_concurrency();
+        const int nt = cntp < 8192 ? 1 : (int)std::min<unsigned>(8, hw ? hw : 1);
+        if (nt <= 1) { apply(0, cntp); return; }
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; ++k) th.emplace_back(apply, cntp * k / nt, cntp * (k + 1) / nt);
+        for (auto& t : th) t.join();
+    };
+    // the first round of the (small) patch on s_out; the occupations follow on the ctx stream while the host applies it
+    const long long first = std::min(nd, cap);
+    if (patch_ok && fetch_patch((size_t)first, ctx->s_out)) return -1;
     NK_CK(cudaMemcpyAsync(occ, P.occ, m * 8, cudaMemcpyDeviceToHost, st));
     if (!patch_ok) {
         NK_CK(cudaStreamSynchronize(ctx->s_out));    // the chunk downloads write the same host arrays
@@ -2201,30 +2343,22 @@ static int nk_advance_host_pipelined(nk_ctx* ctx, int64_t n_in, double* px, doub
     NK_CK(cudaStreamSynchronize(ctx->s_out));    // all chunk downloads (enqueued before the patch) and the patch
     lap("d2h patch");
     if (patch_ok) {
-        // scattered writes, latency-bound on one core: a few host threads (a slot listed twice carries the same values)
-        auto apply = [&](long long i0, long long i1) {
-            for (long long i = i0; i < i1; ++i) {
-                const int s = ph.slot[i];
-                px[s] = ph.x[i]; py[s] = ph.y[i]; pz[s] = ph.z[i]; tc[s] = ph.tc[i];
-                cx[s] = ph.cx[i]; cy[s] = ph.cy[i]; cz[s] = ph.cz[i];
-                mode[s] = ph.mode[i]; omode[s] = ph.omode[i]; cfacet[s] = ph.cfacet[i]; pid[s] = ph.pid[i];
-            }
-        };
-        const unsigned hw = std::thread::hardware_concurrency();
-        const int nt = nd < 8192 ? 1 : (int)std::min<unsigned>(8, hw ? hw : 1);
-        if (nt <= 1) apply(0, nd);
-        else {
-            std::vector<std::thread> th;
-            for (int k = 0; k < nt; ++k) th.emplace_back(apply, nd * k / nt, nd * (k + 1) / nt);
-            for (auto& t : th) t.join();
+        apply_patch(first);
+        for (long long off = cap; off < nd; off += cap) {       // more dirty slots than one staging buffer holds: further rounds
+            const long long k = std::min(cap, nd - off);
+            k_pack_dirty<<<ctx->n_sm * 4, 256, 0, ctx->s_out>>>(P, pd, cap, off, ctx->patch_count_dev);
+            NK_CK(cudaGetLastError());
+            if (fetch_patch((size_t)k, ctx->s_out)) return -1;
+            NK_CK(cudaStreamSynchronize(ctx->s_out));
+            apply_patch(k);
         }
     }
     lap("patched");
     NK_CK(cudaStreamSynchronize(st));
     lap("d2h occ");
-    ctx->xfer_h2d = (long long)n * 84;
+    ctx->xfer_h2d = (long long)n * (dense_omode ? 48 : 44) + (n_cold >= 0 ? n_cold * 44 : (long long)n * (dense_omode ? 36 : 40));
     ctx->xfer_d2h = (long long)n * 32 + (long long)m * 8 + 8 + (patch_ok ? nd * 80 : (long long)m * 76);
-    if (trace) fprintf(stderr, "[nk pipe] patch entries %lld (hits %u, new %u)\n", nd, cnt[0], cnt[1]);
+    if (trace) fprintf(stderr, "[nk pipe] patch entries %lld (hits %u, new %u), cold records uploaded %lld\n", nd, cnt[0], cnt[1], n_cold);
     if (n_out) *n_out = ns;
     return 0;
 }

@@ -116,6 +116,7 @@ struct NkP {
     const double* res_roulette;       // (R, M) cumsum(enter_prob[r]) / max (one_to_one)
     double* res_nleave;               // (R) particles absorbed per reservoir in the previous step (one_to_one)
     // ---- rough-wall LUTs (Fr, M)
+    int has_rough;                    // 0: no rough facet, the omega-carrying mode is always the mode itself (omode == mode)
     int Fr; const double* specularity; const unsigned char* true_spec; const int* spec_out; const double* roulette;
     // ---- particles (borrowed)
     long long cap;

@@ -23,7 +23,7 @@ PARAMS = """
 """
 
 
-def _run(tmp, seed, steps, env=None, monkeypatch=None):
+def _run(tmp, seed, steps, env=None, monkeypatch=None, params=None):
     from nanokappa_b200.classes.Geometry import Geometry
     from nanokappa_b200.classes.Phonon import Phonon
     from nanokappa_b200.classes.Population import Population
@@ -32,7 +32,7 @@ def _run(tmp, seed, steps, env=None, monkeypatch=None):
             monkeypatch.delenv(k, raising=False)
         for k, v in (env or {}).items():
             monkeypatch.setenv(k, v)
-    args = ap.initialise_parser(False).parse_args(PARAMS.split())
+    args = ap.initialise_parser(False).parse_args((params or PARAMS).split())
     args.results_folder = str(tmp)
     with contextlib.redirect_stdout(io.StringIO()):
         geo = Geometry(args)
@@ -79,7 +79,19 @@ def test_readme_case_properties(tmp_path, monkeypatch):
     assert np.array_equal(a["collision_facets"], b["collision_facets"]) and np.array_equal(a["positions"], b["positions"])
 
 
-def test_host_buffer_call_pipelined_equals_simple(tmp_path, monkeypatch):
+# two populations above the 2^20-particle threshold of the pipelined host-buffer call: the cross-plane film (no rough
+# facet: `omode` travels sparsely) and a rough-walled bar with linear temperature interpolation (general kernel path)
+PIPE_CASES = {
+    "film": PARAMS.replace("--particles total 1e6", "--particles total 1.2e6"),
+    "rough_bar": PARAMS.replace("--particles total 1e6", "--particles total 1.2e6").replace("--dimensions 20e3 20e3 20e3", "--dimensions 5e3 1e3 1e3")
+                       .replace("--bound_pos relative -0.1 0.5 0.5 1.1 0.5 0.5 --bound_cond T T P", "--bound_pos relative -0.1 0.5 0.5 1.1 0.5 0.5 0.5 0.5 -0.1 0.5 0.5 1.1 --bound_cond T T R R P")
+                       .replace("--connect_pos relative 0.5 -0.1 0.5 0.5 1.1 0.5 0.5 0.5 -0.1 0.5 0.5 1.1 --bound_values 302 298", "--connect_pos relative 0.5 -0.1 0.5 0.5 1.1 0.5 --bound_values 302 298 5 5")
+                       .replace("--temp_interp nearest", "--temp_interp linear").replace("synthetic:11", "synthetic:7"),
+}
+
+
+@pytest.mark.parametrize("case", sorted(PIPE_CASES))
+def test_host_buffer_call_pipelined_equals_simple(case, tmp_path, monkeypatch):
     """nk_advance_host (host SoA in, one timestep, host SoA out): the chunked pipeline (H2D / kernel / D2H overlapped,
     cold arrays returned as a patch of the rewritten slots) must hand back exactly what the plain
     upload-step-download version does, call after call."""
@@ -87,11 +99,14 @@ def test_host_buffer_call_pipelined_equals_simple(tmp_path, monkeypatch):
     from nanokappa_b200._lib import check
     out = {}
     for label, env in (("pipelined", {"NK_HOST_PIPELINE": "1"}), ("simple", {"NK_HOST_PIPELINE": "0"}),
-                       ("patch_overflow", {"NK_HOST_PIPELINE": "1", "NK_PIPE_PATCH_CAP": "64"})):
+                       ("patch_overflow", {"NK_HOST_PIPELINE": "1", "NK_PIPE_PATCH_CAP": "64"}),
+                       ("dense_cold", {"NK_HOST_PIPELINE": "1", "NK_HOST_SPARSE": "0"})):
         monkeypatch.delenv("NK_PIPE_PATCH_CAP", raising=False)
-        geo, pop, _ = _run(tmp_path / label, 3, 0, dict(env, NK_STEP_TAB="0"), monkeypatch)
+        monkeypatch.delenv("NK_HOST_SPARSE", raising=False)
+        geo, pop, _ = _run(tmp_path / label, 3, 0, dict(env, NK_STEP_TAB="0"), monkeypatch, params=PIPE_CASES[case])
         eng = pop.engine
         n, _ = eng.slot_count()
+        assert n >= 1 << 20, "below the threshold of the pipelined call: the test would compare the simple path with itself"
         names = ("px", "py", "pz", "tc", "occ", "mode", "omode", "cfacet", "cx", "cy", "cz", "pid")
         host = {k: torch.empty(eng.cap, dtype=eng.t[k].dtype, pin_memory=True) for k in names}
         for k in names:
@@ -100,7 +115,15 @@ def test_host_buffer_call_pipelined_equals_simple(tmp_path, monkeypatch):
         S = eng.S
         Tsv = np.zeros(S); Esv = np.zeros(S); Nsv = np.zeros(S, dtype=np.int64)
         hp = lambda k: C.c_void_p(host[k].data_ptr())
-        for _ in range(4):
+        for call in range(6):
+            if call == 4:
+                # the host arrays are the state: reorder them between calls (ordered by id, so every variant does the
+                # same), which makes whatever the device still holds from the previous call wrong for almost every slot
+                # -- a hit particle whose cold fields were not uploaded would show up below
+                key = torch.where(host["mode"][:n] >= 0, host["pid"][:n], torch.full((n,), 2 ** 63 - 1, dtype=torch.int64))
+                perm = torch.argsort(key, stable=True).flip(0)
+                for k in names:
+                    host[k][:n] = host[k][:n][perm]
             n_out = C.c_int64()
             check(eng.ctx, eng.L.nk_advance_host(eng.ctx, n, 1, *[hp(k) for k in names], C.byref(n_out),
                                                  Tsv.ctypes.data_as(C.c_void_p), Esv.ctypes.data_as(C.c_void_p), Nsv.ctypes.data_as(C.c_void_p)),
@@ -110,7 +133,7 @@ def test_host_buffer_call_pipelined_equals_simple(tmp_path, monkeypatch):
         order = np.argsort(host["pid"][:n].numpy()[live])
         out[label] = ({k: host[k][:n].numpy()[live][order] for k in names}, Tsv.copy(), Nsv.copy(), n)
     b = out["simple"]
-    for label in ("pipelined", "patch_overflow"):
+    for label in ("pipelined", "patch_overflow", "dense_cold"):
         a = out[label]
         assert np.array_equal(a[2], b[2]) and int(a[2].sum()) == a[0]["pid"].shape[0]
         for k in a[0]:
