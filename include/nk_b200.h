@@ -193,7 +193,11 @@ int nk_get_results(nk_ctx* ctx, double* T_sv, double* E_sv, int64_t* N_sv, doubl
                    double* kappa_sv, double* kappa, double* res_E_bal, double* res_flux,
                    int64_t* N_leaving, double* total_energy);
 
-/* Population.contains_check (Population.py:1712-1722): not yet on the GPU path. */
+/* Population.contains_check (Population.py:1712-1722), detection half: the slots of the live particles that lie outside
+ * the mesh bounding box by more than tol (upstream: 1e-10) are written to slots_dev (device, capacity `cap`; unordered),
+ * their number to *n_found (may exceed cap: call again with a larger buffer).  The caller re-draws those particles
+ * (Mesh.sample_volume) and gives them a first collision through nk_find_boundary. */
+int nk_outside_slots(nk_ctx* ctx, double tol, int32_t* slots_dev, int64_t cap, int64_t* n_found);
 
 /* ---- set-up helper (no ctx) ------------------------------------------------------------------------------------ */
 

@@ -63,6 +63,7 @@ SIGNATURES = {
     "nk_advance_host": (C.c_int, [VP, C.c_int64, C.c_int] + [VP] * 12 + [c_lp, VP, VP, VP]),
     "nk_last_transfer_bytes": (C.c_int, [VP, c_lp, c_lp]),
     "nk_debug_trace": (C.c_int, [VP, VP]),
+    "nk_outside_slots": (C.c_int, [VP, C.c_double, VP, C.c_int64, c_lp]),
     "nk_set_rank": (C.c_int, [VP, C.c_int, C.c_int]),
     "nk_acc_buffer": (C.c_int, [VP, C.POINTER(VP), c_lp]),
     "nk_step_local": (C.c_int, [VP]),

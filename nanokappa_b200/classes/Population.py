@@ -606,16 +606,20 @@ class Population(PopulationSetup):
         n, _ = eng.slot_count()
         if n == 0:
             return
+        import ctypes as C
         import torch
+        from ..engine import _dp
+        from .._lib import check
         t = eng.t
-        lo = torch.as_tensor(geometry.bounds[0] - 1e-10, device=eng.device)
-        hi = torch.as_tensor(geometry.bounds[1] + 1e-10, device=eng.device)
-        live = t['mode'][:n] >= 0
-        out = live & ((t['px'][:n] < lo[0]) | (t['py'][:n] < lo[1]) | (t['pz'][:n] < lo[2]) |
-                      (t['px'][:n] > hi[0]) | (t['py'][:n] > hi[1]) | (t['pz'][:n] > hi[2]))
-        idx = out.nonzero().squeeze(1)
-        if idx.numel() == 0:
+        buf = torch.empty(4096, dtype=torch.int32, device=eng.device)
+        found = C.c_int64()
+        check(eng.ctx, eng.L.nk_outside_slots(eng.ctx, 1e-10, _dp(buf), buf.numel(), C.byref(found)), 'nk_outside_slots')
+        if found.value > buf.numel():
+            buf = torch.empty(found.value, dtype=torch.int32, device=eng.device)
+            check(eng.ctx, eng.L.nk_outside_slots(eng.ctx, 1e-10, _dp(buf), buf.numel(), C.byref(found)), 'nk_outside_slots')
+        if found.value == 0:
             return
+        idx = torch.sort(buf[:found.value].long()).values
         new = geometry.mesh.sample_volume(int(idx.numel()))
         md = t['mode'][idx].cpu().numpy().astype(int)
         v = self.engine.tb['group_vel'].reshape(-1, 3)[md]

@@ -1299,6 +1299,21 @@ __global__ void __launch_bounds__(256) k_pack_dirty(NkP P, NkPatch out, long lon
     }
 }
 
+// Population.contains_check (Population.py:1712-1722): live particles outside the bounding box +- tol
+__global__ void __launch_bounds__(256) k_outside_slots(NkP P, double tol, int* out, long long cap, unsigned int* count) {
+    const long long n = P.dyn->n_slots;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (P.mode[i] < 0) continue;
+        const double x = P.px[i], y = P.py[i], z = P.pz[i];
+        const bool outside = x < P.blo[0] - tol || y < P.blo[1] - tol || z < P.blo[2] - tol ||
+                             x > P.bhi[0] + tol || y > P.bhi[1] + tol || z > P.bhi[2] + tol;
+        if (outside) {
+            const unsigned int k = nk_agg_inc(count);
+            if ((long long)k < cap) out[k] = (int)i;
+        }
+    }
+}
+
 // Host-buffer pipeline, upload side: the streaming kernel never reads collision facet / position or the particle id,
 // the rare path reads them only for particles whose collision falls inside the step (tc < 1 on entry).  The host
 // finds those (a scan of `tc`), packs their cold fields and this kernel scatters them into the device arrays.
@@ -2376,6 +2391,20 @@ int nk_advance_host(nk_ctx* ctx, int64_t n_in, int n_steps, double* px, double* 
                   : nk_advance_host_simple(ctx, n_in, n_steps, px, py, pz, tc, occ, mode, omode, cfacet, cx, cy, cz, pid, n_out);
     if (rc) return rc;
     return nk_get_results(ctx, T_sv_out, E_sv_out, N_sv_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int nk_outside_slots(nk_ctx* ctx, double tol, int32_t* slots_dev, int64_t cap, int64_t* n_found) {
+    cudaSetDevice(ctx->device);
+    if (nk_check_ready(ctx)) return -1;
+    if (!ctx->patch_count_dev) NK_CK(cudaMalloc(&ctx->patch_count_dev, 2 * sizeof(unsigned int)));
+    NK_CK(cudaMemsetAsync(ctx->patch_count_dev, 0, 2 * sizeof(unsigned int), ctx->stream));
+    k_outside_slots<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(ctx->P, tol, slots_dev, cap, ctx->patch_count_dev);
+    NK_CK(cudaGetLastError());
+    unsigned int c = 0;
+    NK_CK(cudaMemcpyAsync(&c, ctx->patch_count_dev, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    NK_CK(cudaStreamSynchronize(ctx->stream));
+    if (n_found) *n_found = (int64_t)c;
+    return 0;
 }
 
 int nk_debug_trace(nk_ctx* ctx, uint64_t* out8) {

@@ -152,3 +152,40 @@ def test_converged_film_matches_reference(tmp_path, golden_dir):
         assert (np.abs(gm - rm) <= band).all(), f"{name}: gpu {gm} +- {ge} vs reference {rm} +- {re_}"
     # and the error bars are small enough for the comparison to mean something: 0.2 % on kappa
     assert 4.0 * np.hypot(got["kappa"]["stderr"], ref["kappa"]["stderr"]) < 2e-3 * ref["kappa"]["mean"] * 2
+
+
+def test_contains_check_puts_escaped_particles_back(tmp_path):
+    """Population.contains_check (Population.py:1712-1722) through nk_outside_slots: particles pushed outside the
+    bounding box are found on the device, re-drawn inside the mesh and given a fresh first collision; the others
+    are not touched."""
+    args, geo, ph, pop = _population(gen_golden.PARAMS_C1.format(eta=5, n=20000), tmp_path, seed=4)
+    eng = pop.engine
+    before = eng.particles(flush=False)
+    t = eng.t
+    n_slots, _ = eng.slot_count()
+    victims = np.array([3, 777, 15000, n_slots - 1])
+    assert (t["mode"][victims] >= 0).all()
+    victim_ids = t["pid"][victims].cpu().numpy()
+    t["px"][3] = float(geo.bounds[1, 0] + 5.0)
+    t["py"][777] = float(geo.bounds[1, 1] + 6.0)
+    t["px"][15000] = float(geo.bounds[0, 0] - 7.0)
+    t["pz"][n_slots - 1] = float(geo.bounds[0, 2] - 1e-3)
+    np.random.seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        pop.contains_check(geo)
+    after = eng.particles(flush=False)
+    assert np.array_equal(after["ids"], before["ids"])
+    moved = np.nonzero((after["positions"] != before["positions"]).any(axis=1))[0]
+    assert np.array_equal(np.sort(before["ids"][moved]), np.sort(victim_ids))
+    x = after["positions"][moved]
+    assert geo.mesh.contains(x).all()
+    assert (after["n_timesteps"][moved] > 0).all() and (after["collision_facets"][moved] >= 0).all()
+    xc, tc, fc = eng.find_boundary(x, ph.group_vel[after["modes"][moved][:, 0], after["modes"][moved][:, 1], :])
+    assert np.array_equal(fc, after["collision_facets"][moved])
+    keep = np.setdiff1d(np.arange(before["ids"].shape[0]), moved)
+    for f in ("positions", "n_timesteps", "collision_facets", "collision_positions", "occupation"):
+        assert np.array_equal(after[f][keep], before[f][keep], equal_nan=True), f
+    with contextlib.redirect_stdout(io.StringIO()):
+        pop.contains_check(geo)          # nothing left outside: a no-op
+    again = eng.particles(flush=False)
+    assert np.array_equal(again["positions"], after["positions"])
