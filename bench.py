@@ -380,7 +380,7 @@ def gpu_arm(a):
                 "kernel_share_of_step": {k: v / max(sum(prof.values()), 1e-12) for k, v in prof.items()}}
 
     # ---- end to end through host buffers (pinned): full particle state H2D, one timestep, state + per-SV results D2H
-    e2e = e2e_run(a, eng, n, world, rank, one_step, dev)
+    e2e = e2e_run(a, eng, n, world, rank, one_step, dev, fused)
 
     if world > 1:
         e2e_t = torch.tensor([e2e["seconds"]], device=dev, dtype=torch.float64)
@@ -413,10 +413,11 @@ def gpu_arm(a):
         dist.destroy_process_group()
 
 
-def e2e_run(a, eng, n, world, rank, one_step, dev):
+def e2e_run(a, eng, n, world, rank, one_step, dev, fused=False):
     """One public-API call per step with HOST particle arrays: upload the state, advance one timestep,
     download the state and the per-subvolume results.  N=1 goes through the C-ABI host-buffer entry
-    point nk_advance_host; N>1 composes the same copies around step_local / all-reduce / finalize."""
+    point nk_advance_host (also for N>1 when the per-SV sums are exchanged inside the kernel); with the NCCL all-reduce
+    between the step halves the same copies are composed around step_local / all-reduce / finalize."""
     import torch
     import torch.distributed as dist
     from nanokappa_b200._lib import check
@@ -438,7 +439,7 @@ def e2e_run(a, eng, n, world, rank, one_step, dev):
 
     def one_call():
         n_cur = state["n"]
-        if world == 1:
+        if world == 1 or fused:
             n_out = C.c_int64()
             hp = lambda k: C.c_void_p(host[k].data_ptr())
             check(eng.ctx, eng.L.nk_advance_host(eng.ctx, n_cur, 1, hp("px"), hp("py"), hp("pz"), hp("tc"), hp("occ"), hp("mode"),
@@ -473,7 +474,7 @@ def e2e_run(a, eng, n, world, rank, one_step, dev):
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
     return {"seconds": sec, "updates_global": updates, "h2d": int(state["h2d"]), "d2h": int(state["d2h"]),
-            "calls": calls, "api": "nk_advance_host (C ABI, pinned host SoA)" if world == 1 else "Engine host-buffer step (torch pinned copies + step_local/all_reduce/finalize)"}
+            "calls": calls, "api": "nk_advance_host (C ABI, pinned host SoA)" if (world == 1 or fused) else "Engine host-buffer step (torch pinned copies + step_local/all_reduce/finalize)"}
 
 
 def main():

@@ -2385,7 +2385,7 @@ int nk_advance_host(nk_ctx* ctx, int64_t n_in, int n_steps, double* px, double* 
     if (nk_check_ready(ctx)) return -1;
     NkP& P = ctx->P;
     if (n_in > P.cap) { ctx->err = "n_in exceeds bound capacity"; return -1; }
-    const bool pipe = ctx->use_pipeline && n_steps == 1 && P.world == 1 && n_in >= (1 << 20) && !ctx->profiling &&
+    const bool pipe = ctx->use_pipeline && n_steps == 1 && (P.world == 1 || P.comm_on) && n_in >= (1 << 20) && !ctx->profiling &&
                       (ctx->step_variant == 0);
     int rc = pipe ? nk_advance_host_pipelined(ctx, n_in, px, py, pz, tc, occ, mode, omode, cfacet, cx, cy, cz, pid, n_out)
                   : nk_advance_host_simple(ctx, n_in, n_steps, px, py, pz, tc, occ, mode, omode, cfacet, cx, cy, cz, pid, n_out);
