@@ -241,6 +241,8 @@ __device__ __forceinline__ NkSvHot nk_load_hot(const NkP& P, void* mem) {
         int it = nk_T_index(P, T);
         double t0 = P.Tg[it], t1 = P.Tg[it + 1];
         h.tw[i] = nk_div(nk_sub(T, t0), nk_sub(t1, t0));
+        if (P.is_slice && P.interp == NK_INTERP_LINEAR)        // the linear rule has no per-slice tau weight: reuse the slot
+            h.tw[i] = i > 0 ? nk_div(1.0, nk_sub(P.sv_axis[i], P.sv_axis[i - 1])) : 0.0;
         int r = it - P.tau_i0;
         h.tr[i] = (r >= 0 && r <= 2) ? r : -1;
         h.ti[i] = it;
@@ -277,8 +279,31 @@ __device__ __forceinline__ double nk_relax_particle(const NkP& P, const NkSvSmem
         }
         tau = nk_add(nk_mul(lo, nk_sub(1.0, w)), nk_mul(hi, w));
     } else {
-        const double Ti = nk_particle_T(P, s.svc, s.sv_axis, s.sv_mid, s.T_sv, x, y, z, -1);
-        tau = nk_tau(P, Ti, mode);
+        // general rule (linear interpolation between slices, nearest centre / RBF of grid and voronoi subvolumes).  The
+        // temperature only feeds occupations, so reciprocals replace IEEE divisions (1e-16 relative), and the lifetime
+        // comes from the tau slabs of the mode record already in registers whenever T lies inside them.
+        double Ti;
+        if (P.is_slice && P.interp == NK_INTERP_LINEAR && P.S > 1) {
+            const double xa = P.axis == 0 ? x : (P.axis == 1 ? y : z);
+            int idx = nk_searchsorted_left(s.sv_axis, P.S, xa, P.sv_inv_dx);
+            idx = max(1, min(idx, P.S - 1));
+            const double xl = s.sv_axis[idx - 1], xh = s.sv_axis[idx];
+            const double inv = h.tw[idx];                                              // 1 / (xh - xl), see nk_load_hot
+            Ti = ((xa - xl) * inv) * s.T_sv[idx] + ((xh - xa) * inv) * s.T_sv[idx - 1];
+        } else {
+            Ti = nk_particle_T(P, s.svc, s.sv_axis, s.sv_mid, s.T_sv, x, y, z, -1);
+        }
+        const int it = nk_T_index(P, Ti);
+        const double t0 = __ldg(P.Tg + it), t1 = __ldg(P.Tg + it + 1);
+        const double w = (Ti - t0) * nk_rcp(t1 - t0);
+        const int r = it - P.tau_i0;
+        double lo = r == 0 ? mt.x : (r == 1 ? mt.y : mt.z);
+        double hi = r == 0 ? mt.y : (r == 1 ? mt.z : mt.w);
+        if (r < 0 || r > 2) {
+            lo = __ldg(P.tau + (size_t)it * P.M + mode);
+            hi = __ldg(P.tau + (size_t)(it + 1) * P.M + mode);
+        }
+        tau = nk_add(nk_mul(lo, nk_sub(1.0, w)), nk_mul(hi, w));
         be0 = nk_bose_fast(a, omega, Ti > 0.0 ? nk_rcp(nk_mul(Ti, P.kb)) : 0.0);
         g0 = -1;
     }
