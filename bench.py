@@ -486,7 +486,7 @@ def main():
     p.add_argument("--particles", type=float, default=1e8, help="particles per GPU")
     p.add_argument("--mesh", type=int, default=31, help="q-mesh of the synthetic mode table (31 -> 29791 x 6 modes)")
     p.add_argument("--cpu-particles", type=float, default=2e5)
-    p.add_argument("--cpu-steps", type=int, default=20)
+    p.add_argument("--cpu-steps", type=int, default=100)
     p.add_argument("--e2e-calls", type=int, default=3)
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--nccl", action="store_true", help="multi-GPU: use the NCCL all-reduce between the step halves instead of the fused exchange")
