@@ -286,3 +286,43 @@ def test_energy_table_on_device_matches_numpy(golden_dir):
     rc = L.nk_energy_table(0, om.shape[0], p(om), p(act), T.shape[0], p(T), tb["hbar"], tb["kb"], Q * tb["volume_unitcell"], zero, p(out))
     assert rc == 0, L.nk_last_error(None)
     _close("E(T) table", out, tb["energy_array"], 1e-13)
+
+
+def test_error_conventions_of_the_c_abi(golden_dir):
+    """Every entry point returns 0 / <0 and leaves the message in nk_last_error (the Python layer raises NkError with
+    it, as upstream raises bare Exception('...')): calls out of order, bad arguments, capacity violations."""
+    import ctypes as C
+    from nanokappa_b200._lib import lib, NkError
+    from nanokappa_b200.engine import Engine
+    L = lib()
+    msg = lambda ctx: L.nk_last_error(ctx).decode()
+    ctx = C.c_void_p()
+    assert L.nk_create(10 ** 6, C.byref(ctx)) != 0 and "device" in L.nk_last_error(None).decode()
+    assert L.nk_create(0, C.byref(ctx)) == 0
+    assert L.nk_step(ctx, 1) != 0 and "bound" in msg(ctx)                      # nothing set up yet
+    c3 = (C.c_double * 9)(*range(9)); v3 = (C.c_double * 3)(1, 1, 1)
+    assert L.nk_set_subvols(ctx, 0, c3, v3, 0, 0, 0) != 0 and "n_subvols" in msg(ctx)
+    assert L.nk_set_subvols(ctx, 3, c3, v3, 0, 0, 1) != 0 and "slice" in msg(ctx)       # linear needs slices
+    assert L.nk_set_subvols(ctx, 3, c3, v3, 1, 0, 2) != 0 and "radial" in msg(ctx)      # radial on slices is singular upstream
+    assert L.nk_set_subvols(ctx, 3, c3, v3, 0, 0, 7) != 0
+    assert L.nk_set_subvols(ctx, 3, c3, v3, 0, 0, 0) == 0
+    assert L.nk_set_rbf(ctx, 3, (C.c_int32 * 3)(0, 1, 2), v3, v3, c3) != 0 and "RADIAL" in msg(ctx)
+    assert L.nk_set_reservoir_mode(ctx, 1, None) != 0 and "nk_set_reservoirs" in msg(ctx)
+    assert L.nk_set_rank(ctx, 2, 2) != 0
+    out8 = (C.c_uint64 * 8)()
+    assert L.nk_debug_trace(ctx, out8) != 0 and "NK_TRACE" in msg(ctx)
+    L.nk_destroy(ctx)
+
+    tb, st, _ = _load("c2_crossplane", golden_dir)
+    eng = _engine(tb, st)
+    names = ("px", "py", "pz", "tc", "occ", "mode", "omode", "cfacet", "cx", "cy", "cz", "pid")
+    bufs = [C.c_void_p(eng.t[k].data_ptr()) for k in names]                    # never dereferenced: the size check comes first
+    n_out = C.c_int64()
+    assert L.nk_advance_host(eng.ctx, eng.cap + 1, 1, *bufs, C.byref(n_out), None, None, None) != 0
+    assert "capacity" in msg(eng.ctx)
+    assert L.nk_bind_particles(eng.ctx, 3, *bufs) != 0 and "capacity" in msg(eng.ctx)      # must be even and >= 2
+    assert L.nk_set_reservoir_mode(eng.ctx, 9, None) != 0 and "unknown" in msg(eng.ctx)
+    h2d, d2h = C.c_int64(-1), C.c_int64(-1)
+    assert L.nk_last_transfer_bytes(eng.ctx, C.byref(h2d), C.byref(d2h)) == 0 and h2d.value == 0 and d2h.value == 0
+    eng.step(2)                                                                # the context is still usable afterwards
+    assert eng.timestep() == 2
