@@ -2255,7 +2255,8 @@ static int nk_advance_host_pipelined(nk_ctx* ctx, int64_t n_in, double* px, doub
         };
         const NkCold cd = carve_cold(ctx->cold_dev), ch = carve_cold(ctx->cold_host);
         const unsigned hw = std::thread::hardware_concurrency();
-        const int nt = (int)std::max(1u, std::min(16u, hw ? hw : 1u));
+        const unsigned share = (hw ? hw : 1u) / (unsigned)std::max(1, P.world);          // the ranks of a box share its cores
+        const int nt = (int)std::max(2u, std::min(16u, share));
         std::vector<std::vector<int>> found(nt);
         {
             std::vector<std::thread> th;
