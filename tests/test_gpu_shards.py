@@ -42,7 +42,7 @@ def _acc(eng):
     return torch.as_tensor(_A(), device=eng.device)
 
 
-@pytest.mark.parametrize("name", ["c2_crossplane", "c1_mixed"])
+@pytest.mark.parametrize("name", ["c2_crossplane", "c1_mixed", "c5_box_grid_radial", "c7_fixed_rate", "c8_one_to_one"])
 def test_two_shards_equal_one_context(name, golden_dir):
     tb, st, _ = gen_golden.load_fixture(os.path.join(golden_dir, name + ".npz"))
     n = st.positions.shape[0]
