@@ -1216,49 +1216,53 @@ __global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(Nk
     G.faces = P.faces; G.bc = P.facet_bc; G.partner = P.facet_partner; G.res = P.facet_res; G.rough = P.facet_rough;
     G.normal = P.facet_normal; G.centroid = P.facet_centroid;
     NK_TRACE_MARK_FIRST(P, 2);
-    if (P.F <= NK_RARE_FACES) {
-        const double* src = reinterpret_cast<const double*>(P.faces);
-        double* dst = reinterpret_cast<double*>(sfaces);
-        for (int k = threadIdx.x; k < P.F * (int)(sizeof(NkFace) / 8); k += blockDim.x) dst[k] = src[k];
-        G.faces = sfaces;
-    }
-    if (P.nf <= NK_RARE_FACETS) {
-        for (int k = threadIdx.x; k < P.nf; k += blockDim.x) {
-            sfi[k] = P.facet_bc[k]; sfi[NK_RARE_FACETS + k] = P.facet_partner[k];
-            sfi[2 * NK_RARE_FACETS + k] = P.facet_res[k]; sfi[3 * NK_RARE_FACETS + k] = P.facet_rough[k];
+    // blocks beyond the work list (most of them when few particles hit a wall) go straight to the closing protocol
+    const bool has_work = (unsigned long long)blockIdx.x * blockDim.x < (unsigned long long)P.dyn->n_hits + P.dyn->n_emit;
+    if (has_work) {
+        if (P.F <= NK_RARE_FACES) {
+            const double* src = reinterpret_cast<const double*>(P.faces);
+            double* dst = reinterpret_cast<double*>(sfaces);
+            for (int k = threadIdx.x; k < P.F * (int)(sizeof(NkFace) / 8); k += blockDim.x) dst[k] = src[k];
+            G.faces = sfaces;
         }
-        for (int k = threadIdx.x; k < 3 * P.nf; k += blockDim.x) { sfd[k] = P.facet_normal[k]; sfd[3 * NK_RARE_FACETS + k] = P.facet_centroid[k]; }
-        G.bc = sfi; G.partner = sfi + NK_RARE_FACETS; G.res = sfi + 2 * NK_RARE_FACETS; G.rough = sfi + 3 * NK_RARE_FACETS;
-        G.normal = sfd; G.centroid = sfd + 3 * NK_RARE_FACETS;
-    }
-    // block-private accumulators: thousands of items would otherwise hammer the same ~40 global addresses
-    double* racc = sm_fin + 3 * P.S;
-    const int nacc = nk_acc_len(P.S, P.R);
-    for (int k = threadIdx.x; k < nacc; k += blockDim.x) racc[k] = 0.0;
-    __syncthreads();
-    const unsigned int nh = P.dyn->n_hits, ne = P.dyn->n_emit;
-    const long long step = P.dyn->step;
-    const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
-    for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < nh + ne; w += gridDim.x * blockDim.x) {
-        if (w < nh) {
-            nk_hit_entry(P, G, racc, P.hitlist[w], step, with_flux);
-        } else {
-            if (P.res_gen == NK_RESGEN_ONE_TO_ONE) {
-                nk_emit_one_to_one(P, G, racc, (long long)(w - nh), step, with_flux);
+        if (P.nf <= NK_RARE_FACETS) {
+            for (int k = threadIdx.x; k < P.nf; k += blockDim.x) {
+                sfi[k] = P.facet_bc[k]; sfi[NK_RARE_FACETS + k] = P.facet_partner[k];
+                sfi[2 * NK_RARE_FACETS + k] = P.facet_res[k]; sfi[3 * NK_RARE_FACETS + k] = P.facet_rough[k];
+            }
+            for (int k = threadIdx.x; k < 3 * P.nf; k += blockDim.x) { sfd[k] = P.facet_normal[k]; sfd[3 * NK_RARE_FACETS + k] = P.facet_centroid[k]; }
+            G.bc = sfi; G.partner = sfi + NK_RARE_FACETS; G.res = sfi + 2 * NK_RARE_FACETS; G.rough = sfi + 3 * NK_RARE_FACETS;
+            G.normal = sfd; G.centroid = sfd + 3 * NK_RARE_FACETS;
+        }
+        // block-private accumulators: thousands of items would otherwise hammer the same ~40 global addresses
+        double* racc = sm_fin + 3 * P.S;
+        const int nacc = nk_acc_len(P.S, P.R);
+        for (int k = threadIdx.x; k < nacc; k += blockDim.x) racc[k] = 0.0;
+        __syncthreads();
+        const unsigned int nh = P.dyn->n_hits, ne = P.dyn->n_emit;
+        const long long step = P.dyn->step;
+        const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
+        for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < nh + ne; w += gridDim.x * blockDim.x) {
+            if (w < nh) {
+                nk_hit_entry(P, G, racc, P.hitlist[w], step, with_flux);
             } else {
-                const int2 e = P.emitlist[w - nh];
-                nk_emit_entry(P, G, racc, e.x >> 8, e.y, e.x & 0xff, step, with_flux);
+                if (P.res_gen == NK_RESGEN_ONE_TO_ONE) {
+                    nk_emit_one_to_one(P, G, racc, (long long)(w - nh), step, with_flux);
+                } else {
+                    const int2 e = P.emitlist[w - nh];
+                    nk_emit_entry(P, G, racc, e.x >> 8, e.y, e.x & 0xff, step, with_flux);
+                }
             }
         }
-    }
-    __syncthreads();
-    NK_TRACE_MARK_MAX(P, 3);
-    for (int k = threadIdx.x; k < nacc; k += blockDim.x)
-        if (racc[k] != 0.0) atomicAdd(P.acc + k, racc[k]);
-    if (threadIdx.x == 0) {
-        // live count: + particles that got a slot (emitted - absorbed on arrival) - absorbed
-        const double d = racc[NK_ACC_NEMIT(P.S, P.R)] - racc[NK_ACC_NABS(P.S, P.R)];
-        if (d != 0.0) atomicAdd((unsigned long long*)&P.dyn->n_alive, (unsigned long long)(long long)d);
+        __syncthreads();
+        NK_TRACE_MARK_MAX(P, 3);
+        for (int k = threadIdx.x; k < nacc; k += blockDim.x)
+            if (racc[k] != 0.0) atomicAdd(P.acc + k, racc[k]);
+        if (threadIdx.x == 0) {
+            // live count: + particles that got a slot (emitted - absorbed on arrival) - absorbed
+            const double d = racc[NK_ACC_NEMIT(P.S, P.R)] - racc[NK_ACC_NABS(P.S, P.R)];
+            if (d != 0.0) atomicAdd((unsigned long long*)&P.dyn->n_alive, (unsigned long long)(long long)d);
+        }
     }
     if (FUSE) {
         __syncthreads();
@@ -2004,8 +2008,12 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     }
     if (phase == 1) return 0;
     const size_t fin_smem = (3 * (size_t)P.S + nk_acc_len(P.S, P.R)) * 8;
-    if (fuse_finalize) k_rare<true><<<ctx->n_sm * 16, NK_RARE_THREADS, fin_smem, ctx->stream>>>(P);
-    else k_rare<false><<<ctx->n_sm * 16, NK_RARE_THREADS, fin_smem, ctx->stream>>>(P);
+    // one item per thread; the number of items is known on the device only, so size the grid for ~5 % of the slots
+    // (hits + emission are 0.2-2 % of the particles per step; more items are covered by the grid-stride loop)
+    const long long want_blocks = (ctx->h_slots_hint / 20 + NK_RARE_THREADS - 1) / NK_RARE_THREADS;
+    const int rare_blocks = (int)std::min<long long>((long long)ctx->n_sm * 16, std::max<long long>(ctx->n_sm, want_blocks));
+    if (fuse_finalize) k_rare<true><<<rare_blocks, NK_RARE_THREADS, fin_smem, ctx->stream>>>(P);
+    else k_rare<false><<<rare_blocks, NK_RARE_THREADS, fin_smem, ctx->stream>>>(P);
     NK_CK(cudaGetLastError());
     nk_prof_mark(ctx);
     if (fuse_finalize) {
