@@ -250,7 +250,8 @@ int nk_step_finalize(nk_ctx* ctx);   /* accumulators -> T_sv, results; closes th
  * mailbox, waits (bounded) for the peers' and adds them in rank order.  One box, <= 8 ranks. */
 int nk_comm_export(nk_ctx* ctx, void* handle_out_64B);
 int nk_comm_import(nk_ctx* ctx, int peer_rank, const void* handle_64B);
-int nk_comm_enable(nk_ctx* ctx, int enable);
+int nk_comm_enable(nk_ctx* ctx, int enable);   /* enable = 0 also unmaps the peers' mailboxes: do it on every rank
+                                                  (then synchronise the ranks) before any rank calls nk_destroy */
 
 #ifdef __cplusplus
 }

@@ -1391,7 +1391,8 @@ struct nk_ctx {
     bool use_pipeline = true;      // NK_HOST_PIPELINE=0 disables it
     long long xfer_h2d = 0, xfer_d2h = 0;   // bytes of the last nk_advance_host call
     void* comm_block = nullptr;    // flags + mailboxes of the fused exchange
-    unsigned int comm_imported = 0;    // slot count at the last nk_set_slot_count
+    unsigned int comm_imported = 0;
+    std::vector<void*> ipc_open;   // peer mailboxes mapped with cudaIpcOpenMemHandle    // slot count at the last nk_set_slot_count
     bool profiling = false;
     long long h_step = 0;          // host mirror of NkDyn::step
     bool h_relax_pending = false;  // host mirror of NkDyn::relax_pending
@@ -1480,6 +1481,7 @@ void nk_destroy(nk_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    for (void* p : ctx->ipc_open) cudaIpcCloseMemHandle(p);
     for (void* p : ctx->owned) cudaFree(p);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
@@ -2529,7 +2531,9 @@ int nk_comm_export(nk_ctx* ctx, void* handle_out) {
     if (!ctx->comm_block) {
         const size_t flag_bytes = 256;
         const size_t bytes = flag_bytes + 2 * (size_t)P.world * nk_acc_len(P.S, P.R) * sizeof(double);
-        NK_CK(cudaMalloc(&ctx->comm_block, bytes));
+        // an allocation of its own (>= 2 MB): IPC handles name the underlying allocation, and small blocks of several
+        // contexts of one process would share one -- a peer cannot map the same allocation twice
+        NK_CK(cudaMalloc(&ctx->comm_block, std::max<size_t>(bytes, (size_t)2 << 20)));
         NK_CK(cudaMemset(ctx->comm_block, 0, bytes));
         ctx->owned.push_back(ctx->comm_block);
         P.flags_local = reinterpret_cast<unsigned long long*>(ctx->comm_block);
@@ -2552,6 +2556,7 @@ int nk_comm_import(nk_ctx* ctx, int peer, const void* handle) {
         cudaIpcMemHandle_t h;
         memcpy(&h, handle, sizeof(h));
         NK_CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipc_open.push_back(base);
     }
     P.peer_flags[peer] = reinterpret_cast<unsigned long long*>(base);
     P.peer_mbox[peer] = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + 256);
@@ -2565,7 +2570,13 @@ int nk_comm_enable(nk_ctx* ctx, int enable) {
         if (P.world > 1 && ctx->comm_imported != (1u << P.world) - 1u) { ctx->err = "not every peer mailbox has been imported"; return -1; }
         P.comm_on = P.world > 1 ? 1 : 0;
     } else {
+        // also unmap the peers' mailboxes, so that every rank can release them before any rank frees its own block
         P.comm_on = 0;
+        cudaSetDevice(ctx->device);
+        NK_CK(cudaStreamSynchronize(ctx->stream));
+        for (void* p : ctx->ipc_open) cudaIpcCloseMemHandle(p);
+        ctx->ipc_open.clear();
+        ctx->comm_imported = 0;
     }
     return 0;
 }

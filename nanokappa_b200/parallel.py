@@ -79,6 +79,7 @@ class ShardedEngine:
         self.acc = torch.as_tensor(_Acc(), device=engine.device)
 
         self.fused = False
+        self.fused_error = None
         self._synced = False
 
     def enable_fused_exchange(self):
@@ -99,14 +100,27 @@ class ShardedEngine:
                 check(eng.ctx, eng.L.nk_comm_import(eng.ctx, r, buf), "nk_comm_import")
             check(eng.ctx, eng.L.nk_comm_enable(eng.ctx, 1), "nk_comm_enable")
             ok = 1
-        except Exception:
+            self.fused_error = None
+        except Exception as e:              # e.g. no peer access between the GPUs: keep the NCCL all-reduce
             ok = 0
+            self.fused_error = str(e)
         flag = torch.tensor([ok], device=eng.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)      # all ranks or none
         self.fused = bool(flag.item())
         if not self.fused:
             eng.L.nk_comm_enable(eng.ctx, 0)
         return self.fused
+
+    def close(self):
+        """Collective: unmap the peers' mailboxes on every rank, then destroy the context (a rank must not free its
+        mailbox while a peer still has it mapped)."""
+        if self.fused:
+            torch.cuda.synchronize(self.engine.device)
+            self.engine.L.nk_comm_enable(self.engine.ctx, 0)
+            self.fused = False
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self.engine.close()
 
     def step(self, n=1):
         if self.fused and not self._synced:

@@ -50,6 +50,7 @@ def main():
                 assert sh.enable_fused_exchange(), "peer mailboxes could not be mapped"
             sh.step(STEPS)
             runs[mode] = (sh.engine.particles(), sh.engine.results())
+            sh.close()
         (pn, rn), (pf, rf) = runs["nccl"], runs["fused"]
         for k in ("ids", "modes", "collision_facets", "positions", "n_timesteps"):
             ok &= bool(np.array_equal(pn[k], pf[k], equal_nan=True))
@@ -73,7 +74,7 @@ def main():
         cut = [0] + [int(n_all * (0.7 + 0.3 * r / (world - 1))) for r in range(world)]
         cut[-1] = n_all
         sh = ShardedEngine(make(tb, st, slice(cut[rank], cut[rank + 1]), local), rank, world)
-        assert sh.enable_fused_exchange()
+        assert sh.enable_fused_exchange(), sh.fused_error
         sh.step(STEPS // 2)
         before = sh.live_counts()
         moved = sh.rebalance(tolerance=0.01)
@@ -91,6 +92,7 @@ def main():
             ok &= bool(np.array_equal(rr["subvol_N_p"], rs["subvol_N_p"]))
             ok &= bool(np.allclose(rr["subvol_temperature"], rs["subvol_temperature"], rtol=1e-12, atol=0))
             print(f"[{name}] rebalance {before} -> {after}: {ok}", flush=True)
+        sh.close()
     flag = torch.tensor([int(ok)], device=torch.device("cuda", local))
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
