@@ -30,6 +30,47 @@ __device__ __forceinline__ unsigned long long nk_globaltimer() {
 #define NK_TRACE_MARK_FIRST(P, slot) do { if ((P).trace && threadIdx.x == 0 && blockIdx.x == 0) (P).trace[slot] = nk_globaltimer(); } while (0)
 #define NK_TRACE_MARK_MAX(P, slot)   do { if ((P).trace && threadIdx.x == 0) atomicMax((P).trace + (slot), nk_globaltimer()); } while (0)
 
+// Block-private per-subvolume sums.  On sm_100 shared-memory atomicAdd is native only for 32-bit integers
+// (ATOMS.ADD / ATOMS.POPC.INC); the f64 and the 64-bit integer versions are compare-and-swap loops
+// (ATOMS.CAST.SPIN.64) and were a quarter of the streaming kernel's stall samples (and 9-12 us of the rare path).  Terms
+// are therefore accumulated in 64-bit FIXED POINT built from two native 32-bit adds: the low word's returned old value
+// tells this add whether it wrapped, and the carry rides on the high word's add (two's complement, so signed terms
+// just work, and the result does not depend on the order of the adds).  Quantum: 2^-46 eV for energies
+// (1.4e-14 eV, the size of the f64 rounding noise of the reference's own sum), 2^-38 for flux terms
+// (|v e| is at most ~0.03 eV A/ps for a few K of temperature difference, so 1e-8 of a single typical term).  A
+// term outside the fixed-point range (|q| >= 2^40; never for physical occupations) or non-finite goes to
+// an f64 side bin.  A block adds at most a few million terms: |sum| < 2^62.
+#define NK_QE 70368744177664.0          // 2^46
+#define NK_QF 274877906944.0            // 2^38
+__device__ __forceinline__ void nk_bin_add(long long* q, double* side, double v, double scale) {
+    const double t = v * scale;
+    if (fabs(t) < 1099511627776.0) {
+        const long long i = __double2ll_rn(t);
+        const unsigned int lo = (unsigned int)i, hi = (unsigned int)(i >> 32);
+        unsigned int* w = reinterpret_cast<unsigned int*>(q);            // little endian: w[0] low, w[1] high
+        const unsigned int old = atomicAdd(w, lo);
+        atomicAdd(w + 1, hi + ((old + lo) < old ? 1u : 0u));
+    } else {
+        atomicAdd(side, v);
+    }
+}
+
+// The rare path's block-private copy of the accumulator vector: `acc` (double, the side bins) is followed by the
+// fixed-point halves of the same entries.  Energies / reservoir balances use NK_QE, fluxes NK_QF, counters are integers.
+#define NK_RACC_Q(P, acc, idx) (reinterpret_cast<long long*>((acc) + nk_acc_len((P).S, (P).R)) + (idx))
+#define NK_RACC_E(P, acc, idx, v) nk_bin_add(NK_RACC_Q(P, acc, idx), (acc) + (idx), (v), NK_QE)
+#define NK_RACC_F(P, acc, idx, v) nk_bin_add(NK_RACC_Q(P, acc, idx), (acc) + (idx), (v), NK_QF)
+#define NK_RACC_N(P, acc, idx) nk_bin_add(NK_RACC_Q(P, acc, idx), (acc) + (idx), 1.0, 1.0)
+__device__ __forceinline__ double nk_racc_inv_scale(int S, int R, int k) {
+    if (k < S) return 1.0 / NK_QE;                                        // sum e
+    if (k < 2 * S) return 1.0;                                            // count
+    if (k < 5 * S) return 1.0 / NK_QF;                                    // sum v e
+    if (k < 5 * S + R) return 1.0;                                        // N_leaving
+    if (k < 5 * S + 2 * R) return 1.0 / NK_QE;                            // reservoir energy balance
+    if (k < 5 * S + 5 * R) return 1.0 / NK_QF;                            // reservoir flux
+    return 1.0;                                                           // emitted, absorbed
+}
+
 #define NK_STREAM_EMIT_A 0u
 #define NK_STREAM_EMIT_B 1u
 #define NK_STREAM_ROUGH0 2u          // + index of the boundary event within the step
@@ -312,11 +353,11 @@ __device__ __forceinline__ void nk_boundary_events(const NkP& P, const NkGeo& G,
                     double e = nk_mul(nk_mul(P.hbar, p.omega), nk_sub(p.occ, nk_bose(P, P.res_T[r], p.omega)));
                     const double* n = G.normal + 3 * cfi;
                     double vn = dot3(p.vx, p.vy, p.vz, n[0], n[1], n[2]);
-                    atomicAdd(acc + NK_ACC_NLEAVE(P.S, P.R) + r, 1.0);
-                    atomicAdd(acc + NK_ACC_EBAL(P.S, P.R) + r, -e);
-                    atomicAdd(acc + NK_ACC_RFLUX(P.S, P.R) + 3 * r + 0, nk_div(nk_mul(e, p.vx), vn));
-                    atomicAdd(acc + NK_ACC_RFLUX(P.S, P.R) + 3 * r + 1, nk_div(nk_mul(e, p.vy), vn));
-                    atomicAdd(acc + NK_ACC_RFLUX(P.S, P.R) + 3 * r + 2, nk_div(nk_mul(e, p.vz), vn));
+                    NK_RACC_N(P, acc, NK_ACC_NLEAVE(P.S, P.R) + r);
+                    NK_RACC_E(P, acc, NK_ACC_EBAL(P.S, P.R) + r, -e);
+                    NK_RACC_F(P, acc, NK_ACC_RFLUX(P.S, P.R) + 3 * r + 0, nk_div(nk_mul(e, p.vx), vn));
+                    NK_RACC_F(P, acc, NK_ACC_RFLUX(P.S, P.R) + 3 * r + 1, nk_div(nk_mul(e, p.vy), vn));
+                    NK_RACC_F(P, acc, NK_ACC_RFLUX(P.S, P.R) + 3 * r + 2, nk_div(nk_mul(e, p.vz), vn));
                 }
                 p.alive = false;
                 return;

@@ -361,30 +361,7 @@ __device__ __forceinline__ void nk_emit_scan(const NkP& P) {
     }
 }
 
-// Block-private per-subvolume sums.  On sm_100 shared-memory atomicAdd is native only for 32-bit integers
-// (ATOMS.ADD / ATOMS.POPC.INC); the f64 and the 64-bit integer versions are compare-and-swap loops
-// (ATOMS.CAST.SPIN.64) and were a quarter of the kernel's stall samples.  Terms are therefore accumulated
-// in 64-bit FIXED POINT built from two native 32-bit adds: the low word's returned old value tells this
-// add whether it wrapped, and the carry rides on the high word's add (two's complement, so signed terms
-// just work, and the result does not depend on the order of the adds).  Quantum: 2^-46 eV for energies
-// (1.4e-14 eV, the size of the f64 rounding noise of the reference's own sum), 2^-38 for flux terms
-// (|v e| is at most ~0.03 eV A/ps for a few K of temperature difference, so 1e-8 of a single typical term).  A
-// term outside the fixed-point range (|q| >= 2^40; never for physical occupations) or non-finite goes to
-// an f64 side bin.  A block adds at most a few million terms: |sum| < 2^62.
-#define NK_QE 70368744177664.0          // 2^46
-#define NK_QF 274877906944.0            // 2^38
-__device__ __forceinline__ void nk_bin_add(long long* q, double* side, double v, double scale) {
-    const double t = v * scale;
-    if (fabs(t) < 1099511627776.0) {
-        const long long i = __double2ll_rn(t);
-        const unsigned int lo = (unsigned int)i, hi = (unsigned int)(i >> 32);
-        unsigned int* w = reinterpret_cast<unsigned int*>(q);            // little endian: w[0] low, w[1] high
-        const unsigned int old = atomicAdd(w, lo);
-        atomicAdd(w + 1, hi + ((old + lo) < old ? 1u : 0u));
-    } else {
-        atomicAdd(side, v);
-    }
-}
+// (block-private fixed-point bins: nk_bin_add in nk_device.cuh)
 
 // one live particle: deferred relaxation -> drift -> (if no collision this step) subvolume + energy bins.
 // Returns true when the particle's collision falls inside this step (it then goes to the hit list).
@@ -913,12 +890,12 @@ __device__ __forceinline__ void nk_store_particle(const NkP& P, long long i, con
 __device__ __forceinline__ void nk_accumulate(const NkP& P, double* acc, const NkParticle& p, bool with_flux) {
     int sv = nk_classify(P, P.svc, P.sv_mid, p.x, p.y, p.z);
     double e = nk_mul(nk_mul(P.hbar, p.omega), nk_sub(p.occ, nk_bose(P, P.T_sv[sv], p.omega)));
-    atomicAdd(acc + NK_ACC_E(P.S, P.R) + sv, e);
-    atomicAdd(acc + NK_ACC_CNT(P.S, P.R) + sv, 1.0);
+    NK_RACC_E(P, acc, NK_ACC_E(P.S, P.R) + sv, e);
+    NK_RACC_N(P, acc, NK_ACC_CNT(P.S, P.R) + sv);
     if (with_flux) {
-        atomicAdd(acc + NK_ACC_FLUX(P.S, P.R) + 3 * sv, nk_mul(p.vx, e));
-        atomicAdd(acc + NK_ACC_FLUX(P.S, P.R) + 3 * sv + 1, nk_mul(p.vy, e));
-        atomicAdd(acc + NK_ACC_FLUX(P.S, P.R) + 3 * sv + 2, nk_mul(p.vz, e));
+        NK_RACC_F(P, acc, NK_ACC_FLUX(P.S, P.R) + 3 * sv, nk_mul(p.vx, e));
+        NK_RACC_F(P, acc, NK_ACC_FLUX(P.S, P.R) + 3 * sv + 1, nk_mul(p.vy, e));
+        NK_RACC_F(P, acc, NK_ACC_FLUX(P.S, P.R) + 3 * sv + 2, nk_mul(p.vz, e));
     }
 }
 
@@ -929,7 +906,7 @@ __device__ __forceinline__ void nk_kill(const NkP& P, double* acc, long long i) 
     P.mode[i] = -1;
     unsigned long long k = nk_agg_inc((unsigned long long*)&P.dyn->fr_tail);
     P.freelist[k % (unsigned long long)P.cap] = (int)i;
-    atomicAdd(acc + NK_ACC_NABS(P.S, P.R), 1.0);
+    NK_RACC_N(P, acc, NK_ACC_NABS(P.S, P.R));
 }
 __device__ __forceinline__ long long nk_take_slot(const NkP& P) {
     // claims beyond fr_snap are not returned: the finalize clamps fr_head back to fr_snap
@@ -972,9 +949,9 @@ __device__ __forceinline__ void nk_emit_particle(const NkP& P, const NkGeo& G, d
     p.x = nk_add(x0, nk_mul(p.vx, dt_in)); p.y = nk_add(y0, nk_mul(p.vy, dt_in)); p.z = nk_add(z0, nk_mul(p.vz, dt_in));
     p.occ = nk_bose(P, P.res_T[r], p.omega);
     p.alive = true;
-    atomicAdd(acc + NK_ACC_NEMIT(P.S, P.R), 1.0);
+    NK_RACC_N(P, acc, NK_ACC_NEMIT(P.S, P.R));
     if (p.tc < 0.0) nk_boundary_events(P, G, p, step, acc);
-    if (!p.alive) { atomicAdd(acc + NK_ACC_NABS(P.S, P.R), 1.0); return; }   // crossed the whole domain within the step
+    if (!p.alive) { NK_RACC_N(P, acc, NK_ACC_NABS(P.S, P.R)); return; }   // crossed the whole domain within the step
     const long long slot = nk_take_slot(P);
     if (slot < 0) return;
     nk_store_particle(P, slot, p);
@@ -1237,7 +1214,8 @@ __global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(Nk
         // block-private accumulators: thousands of items would otherwise hammer the same ~40 global addresses
         double* racc = sm_fin + 3 * P.S;
         const int nacc = nk_acc_len(P.S, P.R);
-        for (int k = threadIdx.x; k < nacc; k += blockDim.x) racc[k] = 0.0;
+        long long* rq = reinterpret_cast<long long*>(racc + nacc);      // fixed-point halves of the same entries (nk_racc_*)
+        for (int k = threadIdx.x; k < nacc; k += blockDim.x) { racc[k] = 0.0; rq[k] = 0; }
         __syncthreads();
         const unsigned int nh = P.dyn->n_hits, ne = P.dyn->n_emit;
         const long long step = P.dyn->step;
@@ -1257,10 +1235,13 @@ __global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(Nk
         __syncthreads();
         NK_TRACE_MARK_MAX(P, 3);
         for (int k = threadIdx.x; k < nacc; k += blockDim.x)
-            if (racc[k] != 0.0) atomicAdd(P.acc + k, racc[k]);
+        {
+            const double v = (double)rq[k] * nk_racc_inv_scale(P.S, P.R, k) + racc[k];
+            if (v != 0.0) atomicAdd(P.acc + k, v);
+        }
         if (threadIdx.x == 0) {
             // live count: + particles that got a slot (emitted - absorbed on arrival) - absorbed
-            const double d = racc[NK_ACC_NEMIT(P.S, P.R)] - racc[NK_ACC_NABS(P.S, P.R)];
+            const double d = (double)(rq[NK_ACC_NEMIT(P.S, P.R)] - rq[NK_ACC_NABS(P.S, P.R)]);
             if (d != 0.0) atomicAdd((unsigned long long*)&P.dyn->n_alive, (unsigned long long)(long long)d);
         }
     }
@@ -2009,7 +1990,7 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     ctx->last_variant = variant;
     }
     if (phase == 1) return 0;
-    const size_t fin_smem = (3 * (size_t)P.S + nk_acc_len(P.S, P.R)) * 8;
+    const size_t fin_smem = (3 * (size_t)P.S + 2 * (size_t)nk_acc_len(P.S, P.R)) * 8;
     // one item per thread; the number of items is known on the device only, so size the grid for ~5 % of the slots
     // (hits + emission are 0.2-2 % of the particles per step; more items are covered by the grid-stride loop)
     const long long want_blocks = (ctx->h_slots_hint / 20 + NK_RARE_THREADS - 1) / NK_RARE_THREADS;
