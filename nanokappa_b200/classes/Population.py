@@ -719,12 +719,17 @@ class Population(PopulationSetup):
     def write_final_state(self, geometry):
         """particle_data.txt / subvolumes.txt / subvol_connections.txt (Population.py:2071-2151)."""
         time = datetime.now().strftime('%Y-%m-%dT%H:%M:%S.%f')
-        p = self._particles()
-        header = 'Particles final state data \n' + 'Date and time: {}\n'.format(time) + \
-                 'hdf file = {}, POSCAR file = {}\n'.format(self.args.hdf_file, self.args.poscar_file) + \
-                 'q-point, branch, pos x [angs], pos y [angs], pos z [angs], occupation'
-        data = np.hstack((p['modes'], p['positions'], p['occupation'].reshape(-1, 1)))
-        np.savetxt(os.path.join(self.results_folder_name, 'particle_data.txt'), data, '%d, %d, %.3f, %.3f, %.3f, %.6e', delimiter=',', header=header)
+        # the reference dumps ~60 bytes of text per particle every 100 steps (0.5 s per 1e5 particles, 6 GB at 1e8): above
+        # NK_TEXT_DUMP_MAX particles the exact binary checkpoint (also a valid restart point) replaces it
+        if self.N_p > float(os.environ.get('NK_TEXT_DUMP_MAX', 5e6)):
+            self.save_checkpoint(os.path.join(self.results_folder_name, 'particle_data.npz'))
+        else:
+            p = self._particles()
+            header = 'Particles final state data \n' + 'Date and time: {}\n'.format(time) + \
+                     'hdf file = {}, POSCAR file = {}\n'.format(self.args.hdf_file, self.args.poscar_file) + \
+                     'q-point, branch, pos x [angs], pos y [angs], pos z [angs], occupation'
+            data = np.hstack((p['modes'], p['positions'], p['occupation'].reshape(-1, 1)))
+            np.savetxt(os.path.join(self.results_folder_name, 'particle_data.txt'), data, '%d, %d, %.3f, %.3f, %.3f, %.6e', delimiter=',', header=header)
         if self.current_timestep > 0 and hasattr(self.view, 'mean_T'):
             v = self.view
             S = self.n_of_subvols

@@ -221,3 +221,18 @@ def test_population_runs_the_other_configurations(name, tmp_path):
     assert pop.view.timestep.tolist() == list(range(0, 61, 10)) and np.isfinite(pop.view.T).all()
     if geo.subvol_type != "slice":
         assert pop.svcon_kappa.shape == (geo.n_of_subvol_con,) and np.isfinite(pop.svcon_kappa).all()
+
+
+def test_large_populations_dump_the_binary_checkpoint(tmp_path, monkeypatch):
+    """Above NK_TEXT_DUMP_MAX particles write_final_state stores particle_data.npz (exact, restartable) instead of the
+    reference's 60-bytes-per-particle text file."""
+    monkeypatch.setenv("NK_TEXT_DUMP_MAX", "1000")
+    args, geo, ph, pop = _population(gen_golden.PARAMS_C2.format(n=5000), tmp_path, seed=2)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(10):
+            pop.run_timestep(geo, ph)
+        pop.write_final_state(geo)
+    assert not os.path.exists(os.path.join(tmp_path, "particle_data.txt"))
+    z = np.load(os.path.join(tmp_path, "particle_data.npz"))
+    assert z["positions"].shape == (pop.N_p, 3) and int(z["current_timestep"]) == 10
+    assert np.array_equal(z["positions"], pop.positions)
