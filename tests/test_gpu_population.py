@@ -236,3 +236,27 @@ def test_large_populations_dump_the_binary_checkpoint(tmp_path, monkeypatch):
     z = np.load(os.path.join(tmp_path, "particle_data.npz"))
     assert z["positions"].shape == (pop.N_p, 3) and int(z["current_timestep"]) == 10
     assert np.array_equal(z["positions"], pop.positions)
+
+
+def test_command_line_driver_end_to_end(tmp_path):
+    """`python nanokappa.py -ff parameters.txt` as a user of the reference runs it (nanokappa.py:71-107 upstream):
+    a parameters file in the reference's format, 200 iterations, results folder with the reference's files."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    params = tmp_path / "parameters.txt"
+    text = gen_golden.PARAMS_C1.format(eta=2, n=8000).replace("kappa-m313131.hdf5", "synthetic:5") \
+        .replace("--mat_folder test_material/Si/", "--mat_folder /nonexistent/").replace("--iterations 1000", "--iterations 200") \
+        .replace("--results_folder x", "--results_folder {}".format(tmp_path / "run"))
+    params.write_text("\n".join(l for l in text.splitlines() if l.strip()) + "\n")
+    out = subprocess.run([sys.executable, os.path.join(root, "nanokappa.py"), "-ff", str(params)], cwd=tmp_path,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Total time" in out.stdout and "Timestep   100" in out.stdout
+    folders = [d for d in os.listdir(tmp_path) if d.startswith("run")]
+    assert len(folders) == 1
+    run = tmp_path / folders[0]
+    for f in ("arguments.txt", "convergence.txt", "particle_data.txt", "residue.txt", "subvolumes.txt"):
+        assert (run / f).is_file(), f
+    rows = [l for l in (run / "convergence.txt").read_text().splitlines() if l and not l.startswith("#")]
+    assert len(rows) >= 21                                                   # row 0 + one per 10 steps
