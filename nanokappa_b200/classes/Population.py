@@ -527,7 +527,7 @@ class Population(PopulationSetup):
         if self.current_timestep == 0:
             print('Simulating...')
         if (self.current_timestep % 100) == 0:
-            self.write_final_state(geometry)
+            self.write_final_state(geometry, final=False)
             self.view.postprocess(verbose=False)
             self.update_residue(geometry)
             self.contains_check(geometry)
@@ -716,12 +716,18 @@ class Population(PopulationSetup):
         self.f.writelines(line.replace('\n', ' ') + '\n')
         self.f.close()
 
-    def write_final_state(self, geometry):
-        """particle_data.txt / subvolumes.txt / subvol_connections.txt (Population.py:2071-2151)."""
+    def write_final_state(self, geometry, final=True):
+        """particle_data.txt / subvolumes.txt / subvol_connections.txt (Population.py:2071-2151).  `final=False` marks the
+        every-100-steps call of run_timestep."""
         time = datetime.now().strftime('%Y-%m-%dT%H:%M:%S.%f')
-        # the reference dumps ~60 bytes of text per particle every 100 steps (0.5 s per 1e5 particles, 6 GB at 1e8): above
-        # NK_TEXT_DUMP_MAX particles the exact binary checkpoint (also a valid restart point) replaces it
-        if self.N_p > float(os.environ.get('NK_TEXT_DUMP_MAX', 5e6)):
+        # the reference dumps ~60 bytes of text per particle every 100 steps (0.5 s per 1e5 particles -- a thousand times the
+        # cost of the 100 timesteps themselves here -- and 6 GB at 1e8): the exact binary checkpoint (also a valid restart
+        # point) replaces the text file above NK_TEXT_DUMP_MAX particles, and above NK_TEXT_DUMP_PERIODIC_MAX for the
+        # periodic dumps; the dump at the end of a run keeps the reference's format up to NK_TEXT_DUMP_MAX
+        limit = float(os.environ.get('NK_TEXT_DUMP_MAX', 5e6))
+        if not final:
+            limit = min(limit, float(os.environ.get('NK_TEXT_DUMP_PERIODIC_MAX', 2e5)))
+        if self.N_p > limit:
             self.save_checkpoint(os.path.join(self.results_folder_name, 'particle_data.npz'))
         else:
             p = self._particles()

@@ -287,6 +287,9 @@ NK_DEVI void nk_ray_faces(const NkFace* faces, int F, double x, double y, double
         const NkFace& T = faces[f];
         double num = nk_add(dot3(x, y, z, T.nx, T.ny, T.nz), T.k);
         double den = dot3(vx, vy, vz, T.nx, T.ny, T.nz);
+        // t = -num/den can only reach the tolerance when num and den have opposite signs (0, inf and NaN quotients are
+        // rejected below anyway): skip the IEEE division for the planes the ray moves away from -- half of a convex mesh
+        if (!((num < 0.0 && den > 0.0) || (num > 0.0 && den < 0.0))) continue;
         double t = -nk_div(num, den);
         if (!(t >= NK_TOL) || isinf(t)) continue;                 // also rejects NaN
         if (!(t < tbest)) continue;                               // cannot become the first minimum
