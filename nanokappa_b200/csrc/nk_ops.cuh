@@ -1,0 +1,118 @@
+// nk_ops.cuh -- shared-memory subvolume tables and the operator kernels behind the reference's method seams
+// Part of the single translation unit nk_kernels.cu (included in this order: nk_ops.cuh, nk_stream.cuh,
+// nk_stream_variants.cuh, nk_rare.cuh, nk_hostpipe.cuh); see DESIGN.md section 4.
+#pragma once
+
+// =================================================================================================
+// kernels
+// =================================================================================================
+
+// ---- shared-memory copy of the subvolume tables used by the streaming kernels --------------------
+struct NkSvSmem {
+    double* svc; double* sv_axis; double* sv_mid; double* T_sv;
+};
+__device__ __forceinline__ NkSvSmem nk_load_sv(const NkP& P, double* sm) {
+    NkSvSmem s;
+    s.svc = sm; s.sv_axis = sm + 3 * P.S; s.sv_mid = s.sv_axis + P.S; s.T_sv = s.sv_mid + P.S;
+    for (int i = threadIdx.x; i < 3 * P.S; i += blockDim.x) s.svc[i] = P.svc[i];
+    for (int i = threadIdx.x; i < P.S; i += blockDim.x) {
+        s.sv_axis[i] = P.sv_axis[i];
+        s.T_sv[i] = P.T_sv[i];
+        if (i < P.S - 1) s.sv_mid[i] = P.sv_mid[i];
+    }
+    return s;
+}
+__host__ __device__ static inline size_t nk_sv_smem_doubles(int S) { return (size_t)6 * S; }
+
+// Mesh.find_boundary operator seam: one ray per thread, triangles staged through shared memory.
+#define NK_FACE_TILE 256
+__global__ void __launch_bounds__(256) k_find_boundary(NkP P, long long n, const double* __restrict__ x,
+                                                        const double* __restrict__ v, double* __restrict__ xc,
+                                                        double* __restrict__ tc, int* __restrict__ fc) {
+    __shared__ NkFace sf[NK_FACE_TILE];
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0;
+    if (i < n) { px = x[3 * i]; py = x[3 * i + 1]; pz = x[3 * i + 2]; vx = v[3 * i]; vy = v[3 * i + 1]; vz = v[3 * i + 2]; }
+    double tbest = CUDART_INF; int fbest = -1;
+    for (int f0 = 0; f0 < P.F; f0 += NK_FACE_TILE) {
+        int nt = min(NK_FACE_TILE, P.F - f0);
+        __syncthreads();
+        const double* src = reinterpret_cast<const double*>(P.faces + f0);
+        double* dst = reinterpret_cast<double*>(sf);
+        for (int k = threadIdx.x; k < nt * (int)(sizeof(NkFace) / 8); k += blockDim.x) dst[k] = src[k];
+        __syncthreads();
+        if (i < n) nk_ray_faces(sf, nt, px, py, pz, vx, vy, vz, tbest, fbest);
+    }
+    if (i < n) {
+        tc[i] = tbest; fc[i] = fbest;
+        xc[3 * i] = nk_add(px, nk_mul(tbest, vx)); xc[3 * i + 1] = nk_add(py, nk_mul(tbest, vy)); xc[3 * i + 2] = nk_add(pz, nk_mul(tbest, vz));
+    }
+}
+
+// first collision of every live slot (Population.py:308-316)
+__global__ void __launch_bounds__(256) k_init_collisions(NkP P) {
+    __shared__ NkFace sf[NK_FACE_TILE];
+    const long long n = P.dyn->n_slots;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
+        long long i = base + threadIdx.x;
+        bool live = i < n && P.mode[i] >= 0;
+        double px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0;
+        if (live) { NkMode m = P.mprop[P.mode[i]]; px = P.px[i]; py = P.py[i]; pz = P.pz[i]; vx = m.vx; vy = m.vy; vz = m.vz; }
+        double tbest = CUDART_INF; int fbest = -1;
+        for (int f0 = 0; f0 < P.F; f0 += NK_FACE_TILE) {
+            int nt = min(NK_FACE_TILE, P.F - f0);
+            __syncthreads();
+            const double* src = reinterpret_cast<const double*>(P.faces + f0);
+            double* dst = reinterpret_cast<double*>(sf);
+            for (int k = threadIdx.x; k < nt * (int)(sizeof(NkFace) / 8); k += blockDim.x) dst[k] = src[k];
+            __syncthreads();
+            if (live) nk_ray_faces(sf, nt, px, py, pz, vx, vy, vz, tbest, fbest);
+        }
+        if (live) {
+            P.tc[i] = nk_div(tbest, P.dt); P.cfacet[i] = fbest;
+            P.cx[i] = nk_add(px, nk_mul(tbest, vx)); P.cy[i] = nk_add(py, nk_mul(tbest, vy)); P.cz[i] = nk_add(pz, nk_mul(tbest, vz));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_classify(NkP P, long long n, const double* __restrict__ x, int* __restrict__ sv,
+                                                   unsigned long long* __restrict__ counts) {
+    extern __shared__ double sm[];
+    NkSvSmem s = nk_load_sv(P, sm);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(sm + nk_sv_smem_doubles(P.S));
+    for (int i = threadIdx.x; i < P.S; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int r = nk_classify(P, s.svc, s.sv_mid, x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+        sv[i] = r;
+        if (counts) atomicAdd(hist + r, 1u);
+    }
+    __syncthreads();
+    if (counts) for (int i = threadIdx.x; i < P.S; i += blockDim.x) if (hist[i]) atomicAdd(counts + i, (unsigned long long)hist[i]);
+}
+
+__global__ void k_occupation(NkP P, long long n, const double* T, const double* omega, double* occ) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        occ[i] = nk_bose(P, T[i], omega[i]);
+}
+__global__ void k_lifetime(NkP P, long long n, const double* T, const int* mode, double* tau) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        tau[i] = nk_tau(P, T[i], mode[i]);
+}
+__global__ void k_table(NkP P, long long n, const double* in, double* out, int e_to_t) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = e_to_t ? nk_interp_table(P.Ea, P.Ta, P.nE, in[i], P.Ta[0], P.Ta[P.nE - 1])
+                        : nk_interp_table(P.Ta, P.Ea, P.nE, in[i], P.Ea[0], P.Ea[P.nE - 1]);
+}
+__global__ void k_particle_T(NkP P, long long n, const double* x, double* T) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        T[i] = nk_particle_T(P, P.svc, P.sv_axis, P.sv_mid, P.T_sv, x[3 * i], x[3 * i + 1], x[3 * i + 2], -1);
+}
+
+// ---- lifetime_scattering of one particle (Population.py:1701-1710) ---------------------------------
+__device__ __forceinline__ double nk_relax(const NkP& P, double T, int mode, double omega, double occ) {
+    double tau = nk_tau(P, T, mode);
+    double n0 = nk_bose(P, T, omega);
+    if (tau > 0.0) return nk_add(n0, nk_mul(nk_sub(occ, n0), exp(nk_div(-P.dt, tau))));
+    return n0;
+}

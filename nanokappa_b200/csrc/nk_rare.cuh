@@ -1,0 +1,412 @@
+// nk_rare.cuh -- the rare path of a timestep (boundary events, emission), the closing block, the in-kernel exchange, the relaxation flush
+// Part of the single translation unit nk_kernels.cu (included in this order: nk_ops.cuh, nk_stream.cuh,
+// nk_stream_variants.cuh, nk_rare.cuh, nk_hostpipe.cuh); see DESIGN.md section 4.
+#pragma once
+
+// ---- helpers shared by the rare-path code ------------------------------------------------------------------
+__device__ __forceinline__ void nk_store_particle(const NkP& P, long long i, const NkParticle& p) {
+    P.px[i] = p.x; P.py[i] = p.y; P.pz[i] = p.z; P.tc[i] = p.tc; P.occ[i] = p.occ;
+    P.mode[i] = p.mode; P.omode[i] = p.omode; P.cfacet[i] = p.cf; P.cx[i] = p.cx; P.cy[i] = p.cy; P.cz[i] = p.cz;
+}
+// refresh_temperatures contribution of one particle handled outside k_step; `acc` is the block-private
+// (shared memory) copy of the accumulator vector
+__device__ __forceinline__ void nk_accumulate(const NkP& P, double* acc, const NkParticle& p, bool with_flux) {
+    int sv = nk_classify(P, P.svc, P.sv_mid, p.x, p.y, p.z);
+    double e = nk_mul(nk_mul(P.hbar, p.omega), nk_sub(p.occ, nk_bose(P, P.T_sv[sv], p.omega)));
+    NK_RACC_E(P, acc, NK_ACC_E(P.S, P.R) + sv, e);
+    NK_RACC_N(P, acc, NK_ACC_CNT(P.S, P.R) + sv);
+    if (with_flux) {
+        NK_RACC_F(P, acc, NK_ACC_FLUX(P.S, P.R) + 3 * sv, nk_mul(p.vx, e));
+        NK_RACC_F(P, acc, NK_ACC_FLUX(P.S, P.R) + 3 * sv + 1, nk_mul(p.vy, e));
+        NK_RACC_F(P, acc, NK_ACC_FLUX(P.S, P.R) + 3 * sv + 2, nk_mul(p.vz, e));
+    }
+}
+
+// Free slots live in a ring: absorbed particles push at `fr_tail`, emission pops at `fr_head` but only
+// entries pushed in EARLIER steps (below `fr_snap`, advanced by the finalize), so that pushes and pops
+// of the same launch never touch the same entry.
+__device__ __forceinline__ void nk_kill(const NkP& P, double* acc, long long i) {
+    P.mode[i] = -1;
+    unsigned long long k = nk_agg_inc((unsigned long long*)&P.dyn->fr_tail);
+    P.freelist[k % (unsigned long long)P.cap] = (int)i;
+    NK_RACC_N(P, acc, NK_ACC_NABS(P.S, P.R));
+}
+__device__ __forceinline__ long long nk_take_slot(const NkP& P) {
+    // claims beyond fr_snap are not returned: the finalize clamps fr_head back to fr_snap
+    long long old = (long long)nk_agg_inc((unsigned long long*)&P.dyn->fr_head);
+    if (old < P.dyn->fr_snap) return P.freelist[old % P.cap];
+    long long slot = (long long)nk_agg_inc((unsigned long long*)&P.dyn->n_slots);      // nothing recyclable: append
+    if (slot >= P.cap) {
+        atomicAdd((unsigned long long*)&P.dyn->n_slots, (unsigned long long)(-1LL));
+        atomicOr(&P.dyn->error, NK_ERR_CAPACITY);
+        return -1;
+    }
+    return slot;
+}
+
+// One emission-list entry: n_new copies of mode m entering through reservoir r (Population.py:385-406,
+// :491-508, add_reservoir_particles :525-552, Mesh.sample_surface Mesh.py:923-951).
+// One new particle of reservoir r in mode m entering the domain dt_in before the end of the step
+// (Population.fill_reservoirs :491-508 + add_reservoir_particles :525-552 + Mesh.sample_surface :923-951).
+__device__ __forceinline__ void nk_emit_particle(const NkP& P, const NkGeo& G, double* acc, int r, int m, long long id, double dt_in,
+                                                 double uface, double us, double ur, long long step, bool with_flux) {
+    const double dt = P.dt;
+    const NkMode mp = P.mprop[m];
+    NkParticle p;
+    p.id = id;
+    // face ~ area: searchsorted(cdf, u, side='right') as np.random.choice does
+    const int f0 = P.res_face_ptr[r], f1 = P.res_face_ptr[r + 1];
+    int lo = f0, hi = f1;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (P.res_face_cdf[mid] <= uface) lo = mid + 1; else hi = mid; }
+    const int face = P.res_faces[min(lo, f1 - 1)];
+    const double* V = P.face_vertices + 9 * (size_t)face;
+    const double rs = sqrt(us);
+    const double a0 = nk_sub(1.0, rs), a1 = nk_mul(nk_sub(1.0, ur), rs), a2 = nk_mul(ur, rs);
+    const double x0 = nk_add(nk_add(nk_mul(a0, V[0]), nk_mul(a1, V[3])), nk_mul(a2, V[6]));
+    const double y0 = nk_add(nk_add(nk_mul(a0, V[1]), nk_mul(a1, V[4])), nk_mul(a2, V[7]));
+    const double z0 = nk_add(nk_add(nk_mul(a0, V[2]), nk_mul(a1, V[5])), nk_mul(a2, V[8]));
+    p.mode = m; p.omode = m; p.omega = mp.omega; p.vx = mp.vx; p.vy = mp.vy; p.vz = mp.vz;
+    double t;
+    nk_find_boundary_1(P, G.faces, x0, y0, z0, p.vx, p.vy, p.vz, p.cx, p.cy, p.cz, t, p.cf);
+    p.tc = nk_sub(nk_div(t, dt), nk_div(dt_in, dt));
+    p.x = nk_add(x0, nk_mul(p.vx, dt_in)); p.y = nk_add(y0, nk_mul(p.vy, dt_in)); p.z = nk_add(z0, nk_mul(p.vz, dt_in));
+    p.occ = nk_bose(P, P.res_T[r], p.omega);
+    p.alive = true;
+    NK_RACC_N(P, acc, NK_ACC_NEMIT(P.S, P.R));
+    if (p.tc < 0.0) nk_boundary_events(P, G, p, step, acc);
+    if (!p.alive) { NK_RACC_N(P, acc, NK_ACC_NABS(P.S, P.R)); return; }   // crossed the whole domain within the step
+    const long long slot = nk_take_slot(P);
+    if (slot < 0) return;
+    nk_store_particle(P, slot, p);
+    P.pid[slot] = p.id;
+    {
+        const unsigned int k = nk_agg_inc(&P.dyn->n_new);
+        if ((long long)k < P.newslots_cap) P.newslots[k] = (int)slot;
+    }
+    nk_accumulate(P, acc, p, with_flux);
+}
+
+// One emission-list entry (constant / fixed_rate): n_new copies of mode m from reservoir r.
+__device__ __forceinline__ void nk_emit_entry(const NkP& P, const NkGeo& G, double* acc, int r, int m, int n_new, long long step, bool with_flux) {
+    const double dt = P.dt;
+    const size_t idx = (size_t)r * P.M + m;
+    const double prob = P.enter_prob[idx];
+    // numerator of the first copy's entry time: the counter after this step's update, or this step's dice
+    const double lead = P.res_gen == NK_RESGEN_FIXED_RATE ? P.emit_u[idx] : P.res_counter[idx];
+    for (int c = n_new; c >= 1; --c) {
+        const long long id = NK_EMIT_ID_BASE + (((step * P.R + r) * (long long)P.M + m) * NK_EMIT_CMAX + (c - 1));
+        double ua, uface, us, ur;
+        nk_uniforms(P, id, step, NK_STREAM_EMIT_A, ua, uface);
+        nk_uniforms(P, id, step, NK_STREAM_EMIT_B, us, ur);
+        const double dt_in = (c == 1) ? nk_mul(dt, nk_sub(1.0, nk_div(lead, prob)))
+                                      : nk_mul(dt, nk_sub(1.0, nk_div(nk_add((double)(c - 1), ua), prob)));
+        nk_emit_particle(P, G, acc, r, m, id, dt_in, uface, us, ur, step, with_flux);
+    }
+}
+
+// One re-emitted particle of the one_to_one mode: k-th particle of reservoir r (Population.py:457-489).
+__device__ __forceinline__ void nk_emit_one_to_one(const NkP& P, const NkGeo& G, double* acc, long long e, long long step, bool with_flux) {
+    int r = 0;
+    for (; r < P.R; ++r) {
+        const long long share = nk_one_to_one_share(P, r);
+        if (e < share) break;
+        e -= share;
+    }
+    if (r >= P.R) return;
+    const long long k = P.rank + e * P.world;
+    const long long id = NK_EMIT_ID_BASE + (step * P.R + r) * ((long long)P.M * NK_EMIT_CMAX) + k;
+    double ua, uface, us, ur, umode, udt;
+    nk_uniforms(P, id, step, NK_STREAM_EMIT_A, ua, uface);
+    nk_uniforms(P, id, step, NK_STREAM_EMIT_B, us, ur);
+    nk_uniforms(P, id, step, NK_STREAM_EMIT_C, umode, udt);
+    const double* rou = P.res_roulette + (size_t)r * P.M;
+    int lo = 0, hi = P.M;                                    // searchsorted left
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (rou[mid] < umode) lo = mid + 1; else hi = mid; }
+    nk_emit_particle(P, G, acc, r, min(lo, P.M - 1), id, nk_mul(P.dt, udt), uface, us, ur, step, with_flux);
+}
+
+// One hit-list entry: the boundary event loop of an existing particle.
+__device__ __forceinline__ void nk_hit_entry(const NkP& P, const NkGeo& G, double* acc, long long i, long long step, bool with_flux) {
+    NkParticle p;
+    p.x = P.px[i]; p.y = P.py[i]; p.z = P.pz[i]; p.tc = P.tc[i]; p.occ = P.occ[i];
+    p.mode = P.mode[i]; p.omode = P.omode[i];
+    const NkMode m = P.mprop[p.mode];
+    p.vx = m.vx; p.vy = m.vy; p.vz = m.vz;
+    p.omega = (p.omode == p.mode) ? m.omega : P.mprop[p.omode].omega;
+    p.cf = P.cfacet[i]; p.cx = P.cx[i]; p.cy = P.cy[i]; p.cz = P.cz[i];
+    p.id = P.pid[i]; p.alive = true;
+    nk_boundary_events(P, G, p, step, acc);
+    if (p.alive) {
+        nk_store_particle(P, i, p);
+        nk_accumulate(P, acc, p, with_flux);
+    } else {
+        nk_kill(P, acc, i);
+    }
+}
+
+// coef = rbf_w . T (T may live in shared memory); all threads of the block take rows
+__device__ __forceinline__ void nk_rbf_refresh(const NkP& P, const double* T) {
+    const int rows = P.S + P.rbf_nd + 1;
+    for (int j = threadIdx.x; j < rows; j += blockDim.x) {
+        const double* w = P.rbf_w + (size_t)j * P.S;
+        double a = 0.0;
+        for (int s = 0; s < P.S; ++s) a += w[s] * T[s];
+        P.rbf_coef[j] = a;
+    }
+}
+
+// ---- close the step: calculate_energy normalisation, temperature_function, heat flux, kappa,
+//      reservoir balances (Population.py:704-728, :692, :730-788, :1685-1699).  One block. -----------------------
+__device__ void nk_finalize_block(const NkP& P, double* sm) {
+    const int S = P.S, R = P.R;
+    double* sT = sm;             // new T_sv
+    double* sPhi = sm + S;       // flux along the slice axis
+    double* sN = sm + 2 * S;     // counts
+    double* acc = P.acc; double* out = P.out;
+    const long long step_done = P.dyn->step + 1;
+    const bool conv = (step_done % P.n_dt_to_conv) == 0;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        double cnt = __ldcg(acc + NK_ACC_CNT(S, R) + s);
+        double esum = __ldcg(acc + NK_ACC_E(S, R) + s);
+        double norm;
+        if (P.norm_mean) { norm = nk_div(P.n_active, cnt); if (norm != norm) norm = 0.0; }
+        else norm = nk_div(P.n_active, nk_mul(P.particle_density, P.sv_volume[s]));
+        double Tprev = P.T_sv[s];
+        // both tables share the index of the (uniform) temperature grid, and T moves little per step: start the bracket
+        // searches at the previous temperature's index
+        const int ig = P.nE > 1 ? (int)((Tprev - P.Ta[0]) * P.Ta_inv_d) : 0;
+        double ref = nk_interp_table_from(P.Ta, P.Ea, P.nE, Tprev, P.Ea[0], P.Ea[P.nE - 1], ig);
+        double E = nk_add(nk_div(nk_mul(esum, norm), P.dens_norm), ref);
+        double Tn = nk_interp_table_from(P.Ea, P.Ta, P.nE, E, P.Ta[0], P.Ta[P.nE - 1], ig);
+        sT[s] = Tn; sN[s] = cnt;
+        out[NK_OUT_T(S, R) + s] = Tn;
+        out[NK_OUT_E(S, R) + s] = E;
+        out[NK_OUT_N(S, R) + s] = cnt;
+        if (conv) {
+            double f[3];
+            for (int k = 0; k < 3; ++k) {
+                f[k] = nk_mul(nk_div(nk_mul(__ldcg(acc + NK_ACC_FLUX(S, R) + 3 * s + k), norm), P.dens_norm), P.eVpsa2_in_Wm2);
+                out[NK_OUT_FLUX(S, R) + 3 * s + k] = f[k];
+            }
+            sPhi[s] = f[P.axis];
+        }
+    }
+    __syncthreads();
+    // reservoirs: accumulate this step, normalise on convergence steps
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        out[NK_OUT_NLEAVE(S, R) + r] = __ldcg(acc + NK_ACC_NLEAVE(S, R) + r);
+        P.res_nleave[r] = __ldcg(acc + NK_ACC_NLEAVE(S, R) + r);
+        double eb = nk_add(P.res_acc[r], __ldcg(acc + NK_ACC_EBAL(S, R) + r));
+        double fx[3];
+        for (int k = 0; k < 3; ++k) fx[k] = nk_add(P.res_acc[R + 3 * r + k], __ldcg(acc + NK_ACC_RFLUX(S, R) + 3 * r + k));
+        if (conv) {
+            double area = P.facet_area[P.res_facet[r]];
+            double den = nk_mul(nk_mul(nk_mul(P.particle_density, P.dt), (double)P.n_dt_to_conv), area);
+            double cf = nk_div(P.n_active, den);
+            for (int k = 0; k < 3; ++k) out[NK_OUT_RFLUX(S, R) + 3 * r + k] = nk_mul(nk_div(nk_mul(fx[k], cf), P.dens_norm), P.eVpsa2_in_Wm2);
+            double ce = nk_div(P.n_active, nk_mul(nk_mul(P.particle_density, P.dt), (double)P.n_dt_to_conv));
+            out[NK_OUT_REBAL(S, R) + r] = nk_div(nk_mul(eb, ce), P.dens_norm);
+            eb = 0.0; fx[0] = fx[1] = fx[2] = 0.0;
+        }
+        P.res_acc[r] = eb;
+        for (int k = 0; k < 3; ++k) P.res_acc[R + 3 * r + k] = fx[k];
+    }
+    if (threadIdx.x == 0) {
+        double np = 0.0, et = 0.0;
+        for (int s = 0; s < S; ++s) { np += sN[s]; et += __ldcg(acc + NK_ACC_E(S, R) + s); }
+        out[NK_OUT_NP(S, R)] = np;
+        out[NK_OUT_ETOT(S, R)] = et;
+        if (conv && P.is_slice && R == 2) {
+            // calculate_kappa, slice subvolumes (Population.py:750-771)
+            double L = nk_sub(P.bhi[P.axis], P.blo[P.axis]);
+            double dx = nk_div(nk_mul(nk_mul(2.0, L), P.a_in_m), (double)S);
+            double DX = nk_div(nk_mul(nk_mul(L, P.a_in_m), (double)(1 + S)), (double)S);
+            double T0 = P.res_T[0], T1 = P.res_T[1];
+            double sum = 0.0;
+            for (int s = 0; s < S; ++s) {
+                double Tm = s == 0 ? T0 : sT[s - 1];
+                double Tp = s == S - 1 ? T1 : sT[s + 1];
+                double k = nk_div(nk_mul(-sPhi[s], dx), nk_sub(Tp, Tm));
+                if (isinf(k)) k = 0.0;
+                out[NK_OUT_KSV(S, R) + s] = k;
+                sum += nk_mul(sPhi[s], sN[s]);
+            }
+            out[NK_OUT_KAPPA(S, R)] = nk_div(nk_mul(-sum, nk_div(DX, nk_sub(T1, T0))), np);
+        }
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < S; s += blockDim.x) P.T_sv[s] = sT[s];
+    if (P.interp == NK_INTERP_RADIAL) nk_rbf_refresh(P, sT);
+    for (int i = threadIdx.x; i < nk_acc_len(S, R); i += blockDim.x) acc[i] = 0.0;
+    if (threadIdx.x == 0) {
+        NkDyn* d = P.dyn;
+        d->step = step_done;
+        d->relax_pending = 1;
+        d->last_hits = d->n_hits; d->last_new = d->n_new;
+        d->n_hits = 0;
+        d->n_emit = 0;
+        d->n_new = 0;
+        if (d->fr_head > d->fr_snap) d->fr_head = d->fr_snap;      // over-claims of an exhausted free list (nk_take_slot)
+        d->fr_snap = d->fr_tail;           // slots freed in this step become recyclable from the next one
+        d->blocks_done = 0;
+    }
+}
+
+// All-reduce (sum) of the accumulator vector across the ranks of one box, done by the block that closes the
+// step: every rank stores its vector straight into every peer's mailbox over NVLink (peer-mapped memory),
+// publishes a sequence number, waits for the peers' numbers and adds the world's vectors in rank order, so
+// all ranks get bit-identical sums without a separate collective launch.  Two mailbox parities: a rank can be
+// at most one step ahead of the slowest one.  The wait is bounded (~20 s): a missing peer raises NK_ERR_COMM
+// instead of hanging the GPU.
+__device__ void nk_exchange_sums(const NkP& P) {
+    const int len = nk_acc_len(P.S, P.R);
+    const int W = P.world;
+    const unsigned long long seq = (unsigned long long)(P.dyn->step + 1);
+    const int par = (int)(seq & 1ull);
+    for (int r = 0; r < W; ++r) {
+        double* dst = P.peer_mbox[r] + ((size_t)par * W + P.rank) * len;
+        for (int i = threadIdx.x; i < len; i += blockDim.x) dst[i] = __ldcg(P.acc + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < W) {
+        volatile unsigned long long* f = P.peer_flags[threadIdx.x] + (size_t)par * W + P.rank;
+        *f = seq;
+        __threadfence_system();
+        volatile unsigned long long* mine = P.flags_local + (size_t)par * W + threadIdx.x;
+        const long long t0 = clock64();
+        while (*mine != seq) {
+            if (clock64() - t0 > 40000000000LL) { atomicOr(&P.dyn->error, NK_ERR_COMM); break; }   // ~20 s
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        double sum = 0.0;
+        for (int r = 0; r < W; ++r) sum += *((volatile double*)(P.mbox_local + ((size_t)par * W + r) * len + i));
+        P.acc[i] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_finalize(NkP P) {
+    extern __shared__ double sm[];
+    nk_finalize_block(P, sm);
+}
+
+// ---- the rare path of a step: boundary events of the hit list + reservoir emission -----------------------------
+// Work items [0, n_hits) are existing particles whose collision falls inside the step, [n_hits, n_hits + n_emit)
+// are emission-list entries.  One thread per item; triangles staged in shared memory when they fit.  With
+// FUSE the last block to finish closes the step (single-GPU path: no collective between the two halves).
+#define NK_RARE_THREADS 128
+#define NK_RARE_FACES 128
+#define NK_RARE_FACETS 64
+template <bool FUSE>
+#ifndef NK_RARE_MIN_BLOCKS
+#define NK_RARE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(NkP P) {
+    __shared__ NkFace sfaces[NK_RARE_FACES];
+    __shared__ int sfi[4 * NK_RARE_FACETS];
+    __shared__ double sfd[6 * NK_RARE_FACETS];
+    extern __shared__ double sm_fin[];
+    __shared__ int s_last;
+    NkGeo G;
+    G.faces = P.faces; G.bc = P.facet_bc; G.partner = P.facet_partner; G.res = P.facet_res; G.rough = P.facet_rough;
+    G.normal = P.facet_normal; G.centroid = P.facet_centroid;
+    NK_TRACE_MARK_FIRST(P, 2);
+    // blocks beyond the work list (most of them when few particles hit a wall) go straight to the closing protocol
+    const bool has_work = (unsigned long long)blockIdx.x * blockDim.x < (unsigned long long)P.dyn->n_hits + P.dyn->n_emit;
+    if (has_work) {
+        if (P.F <= NK_RARE_FACES) {
+            const double* src = reinterpret_cast<const double*>(P.faces);
+            double* dst = reinterpret_cast<double*>(sfaces);
+            for (int k = threadIdx.x; k < P.F * (int)(sizeof(NkFace) / 8); k += blockDim.x) dst[k] = src[k];
+            G.faces = sfaces;
+        }
+        if (P.nf <= NK_RARE_FACETS) {
+            for (int k = threadIdx.x; k < P.nf; k += blockDim.x) {
+                sfi[k] = P.facet_bc[k]; sfi[NK_RARE_FACETS + k] = P.facet_partner[k];
+                sfi[2 * NK_RARE_FACETS + k] = P.facet_res[k]; sfi[3 * NK_RARE_FACETS + k] = P.facet_rough[k];
+            }
+            for (int k = threadIdx.x; k < 3 * P.nf; k += blockDim.x) { sfd[k] = P.facet_normal[k]; sfd[3 * NK_RARE_FACETS + k] = P.facet_centroid[k]; }
+            G.bc = sfi; G.partner = sfi + NK_RARE_FACETS; G.res = sfi + 2 * NK_RARE_FACETS; G.rough = sfi + 3 * NK_RARE_FACETS;
+            G.normal = sfd; G.centroid = sfd + 3 * NK_RARE_FACETS;
+        }
+        // block-private accumulators: thousands of items would otherwise hammer the same ~40 global addresses
+        double* racc = sm_fin + 3 * P.S;
+        const int nacc = nk_acc_len(P.S, P.R);
+        long long* rq = reinterpret_cast<long long*>(racc + nacc);      // fixed-point halves of the same entries (nk_racc_*)
+        for (int k = threadIdx.x; k < nacc; k += blockDim.x) { racc[k] = 0.0; rq[k] = 0; }
+        __syncthreads();
+        const unsigned int nh = P.dyn->n_hits, ne = P.dyn->n_emit;
+        const long long step = P.dyn->step;
+        const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
+        for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < nh + ne; w += gridDim.x * blockDim.x) {
+            if (w < nh) {
+                nk_hit_entry(P, G, racc, P.hitlist[w], step, with_flux);
+            } else {
+                if (P.res_gen == NK_RESGEN_ONE_TO_ONE) {
+                    nk_emit_one_to_one(P, G, racc, (long long)(w - nh), step, with_flux);
+                } else {
+                    const int2 e = P.emitlist[w - nh];
+                    nk_emit_entry(P, G, racc, e.x >> 8, e.y, e.x & 0xff, step, with_flux);
+                }
+            }
+        }
+        __syncthreads();
+        NK_TRACE_MARK_MAX(P, 3);
+        for (int k = threadIdx.x; k < nacc; k += blockDim.x)
+        {
+            const double v = (double)rq[k] * nk_racc_inv_scale(P.S, P.R, k) + racc[k];
+            if (v != 0.0) atomicAdd(P.acc + k, v);
+        }
+        if (threadIdx.x == 0) {
+            // live count: + particles that got a slot (emitted - absorbed on arrival) - absorbed
+            const double d = (double)(rq[NK_ACC_NEMIT(P.S, P.R)] - rq[NK_ACC_NABS(P.S, P.R)]);
+            if (d != 0.0) atomicAdd((unsigned long long*)&P.dyn->n_alive, (unsigned long long)(long long)d);
+        }
+    }
+    if (FUSE) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int t = atomicAdd(&P.dyn->blocks_done, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (P.comm_on) nk_exchange_sums(P);
+            if (P.trace && threadIdx.x == 0) P.trace[4] = nk_globaltimer();
+            nk_finalize_block(P, sm_fin);
+            __syncthreads();
+            if (P.trace && threadIdx.x == 0) P.trace[5] = nk_globaltimer();
+        }
+    }
+}
+
+// apply the deferred lifetime_scattering so that `occ` is what the reference holds after run_timestep
+// (same arithmetic as the head of k_step, so flushing between steps is bit-neutral)
+template <bool FAST>
+__global__ void __launch_bounds__(256) k_flush_relax(NkP P) {
+    extern __shared__ double sm[];
+    NkSvSmem s = nk_load_sv(P, sm);
+    NkSvHot h = nk_load_hot(P, sm + nk_sv_smem_doubles(P.S));
+    __syncthreads();
+    if (!P.dyn->relax_pending) return;
+    const long long n = P.dyn->n_slots;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int md = P.mode[i];
+        if (md < 0) continue;
+        const int om = P.has_rough ? P.omode[i] : md;      // as the streaming kernel: without rough facets omode == mode
+        double4 ma, mt;
+        nk_ld256(&P.mhot[md].omega, ma);
+        nk_ld256(&P.mhot[md].t[0], mt);
+        double omega = om == md ? ma.x : P.mhot[om].omega;
+        double be0; int g0;
+        P.occ[i] = nk_relax_particle<FAST>(P, s, h, P.px[i], P.py[i], P.pz[i], md, omega, nk_mul(P.hbar, omega), mt, P.occ[i], be0, g0);
+    }
+}
+__global__ void k_clear_relax(NkP P) { P.dyn->relax_pending = 0; }
