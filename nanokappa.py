@@ -23,7 +23,28 @@ def main(argv=None):
         warnings.simplefilter("ignore")
     print('\nNano-kappa (B200 particle loop). Running simulation, check the results folder for the current status.')
     args = read_args(debug_flag, argv)
-    args = generate_results_folder(args)
+    world, rank = int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('RANK', 0))
+    if world > 1:
+        # torchrun --nproc-per-node N nanokappa.py -ff parameters.txt: one rank per GPU, particles sharded.  The host
+        # set-up draws random numbers (voronoi centres, reservoir counters): all ranks must draw the same ones; rank 0
+        # owns the results folder, the others get a private sub-folder for their shard's dumps and keep quiet.
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get('LOCAL_RANK', 0))
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        if rank == 0:
+            args = generate_results_folder(args)
+        shared = [args.results_folder, int(np.random.randint(0, 2 ** 31 - 1))]
+        dist.broadcast_object_list(shared, src=0)
+        np.random.seed(shared[1])
+        if rank > 0:
+            args.results_folder = os.path.join(shared[0], 'rank{}'.format(rank))
+            os.makedirs(args.results_folder, exist_ok=True)
+            sys.stdout = open(os.path.join(args.results_folder, 'output.txt'), 'a')
+    else:
+        args = generate_results_folder(args)
     output = args.output[0] if isinstance(args.output, (list, tuple)) else args.output
     output_file = None
     if output == 'file':
@@ -48,9 +69,17 @@ def main(argv=None):
     flag = True
     while flag:
         pop.run_timestep(geo, phonons)
-        flag = (pop.current_timestep < args.iterations[0]) and not pop.finish_sim
+        flag = (pop.current_timestep < args.iterations[0]) and not pop.finish_sim       # the same on every rank
         if max_time.total_seconds() > 0:
-            flag = flag and datetime.now() - start_time < max_time
+            if world == 1:
+                flag = flag and datetime.now() - start_time < max_time
+            elif pop.current_timestep % 10 == 0:
+                # wall clocks differ between ranks: agree on the time limit (a rank that left alone would stall the others)
+                import torch
+                import torch.distributed as dist
+                go = torch.tensor([int(datetime.now() - start_time < max_time)], device='cuda')
+                dist.all_reduce(go, op=dist.ReduceOp.MIN)
+                flag = flag and bool(go.item())
     print('Saving end of run particle data...')
     pop.write_final_state(geo)
     pop.f.close()
@@ -64,6 +93,10 @@ def main(argv=None):
     if output_file is not None:
         sys.stdout = sys.__stdout__
         output_file.close()
+    if world > 1:
+        import torch.distributed as dist
+        pop.sharded.close()
+        dist.destroy_process_group()
     return pop
 
 

@@ -181,10 +181,23 @@ class Population(PopulationSetup):
         Constants.__init__(self)
         self.setup_host(arguments, geometry, phonon, seed)
 
-        # ---- device context
+        # ---- device context; under torchrun (WORLD_SIZE > 1) every rank owns a shard of the particles:
+        #      the host set-up above must be identical on all ranks (nanokappa.py seeds NumPy identically)
+        self.world, self.rank, self.sharded = 1, 0, None
         if engine is None:
+            self.world = int(os.environ.get('WORLD_SIZE', 1))
+            self.rank = int(os.environ.get('RANK', 0))
             if device is None:
                 device = int(os.environ.get('LOCAL_RANK', 0))
+            if self.world > 1:
+                import torch
+                import torch.distributed as dist
+                torch.cuda.set_device(device)
+                if not dist.is_initialized():
+                    dist.init_process_group('nccl', device_id=torch.device('cuda', device))
+                common = [self.seed, self.res_counter]
+                dist.broadcast_object_list(common, src=0)          # the Philox seed and the reservoir counters are global
+                self.seed, self.res_counter = int(common[0]), np.asarray(common[1])
             engine = Engine(device, seed=self.seed)
         self.engine = engine
         self.tables = build_tables(self.args, geometry, phonon, self)
@@ -194,6 +207,10 @@ class Population(PopulationSetup):
         self.engine.set_tables(self.tables, res_counter=self.res_counter, hot_T=hot)
         geometry.attach_engine(self.engine)
         phonon.attach_engine(self.engine)
+        if self.world > 1:
+            from ..parallel import ShardedEngine
+            self.sharded = ShardedEngine(self.engine, self.rank, self.world)
+            self.sharded.enable_fused_exchange()        # falls back to the NCCL all-reduce between the step halves
 
         print('Initialising population...')
         self.initialise_all_particles(geometry, phonon)
@@ -261,6 +278,14 @@ class Population(PopulationSetup):
             occupation = np.copy(data[:, 5])
         if occupation is None:
             modes = self.initialise_modes(phonon)
+        ids = None
+        if self.world > 1:
+            if occupation is not None:
+                raise Exception('Restarting from a particle file is a single-GPU feature; use the binary checkpoint per rank.')
+            from ..parallel import shard_bounds
+            lo_i, hi_i = shard_bounds(self.rank, self.world, positions.shape[0])       # every rank built the same arrays
+            positions, modes = positions[lo_i:hi_i], modes[lo_i:hi_i]
+            ids = np.arange(lo_i, hi_i, dtype=np.int64)
         self.N_p = positions.shape[0]
         J = phonon.number_of_branches
         flat = modes[:, 0] * J + modes[:, 1]
@@ -272,7 +297,7 @@ class Population(PopulationSetup):
         self.engine.allocate(cap)
         self.engine.set_sv_temperature(self.subvol_temperature)
         print('Getting first boundary collisions...')
-        self.engine.load_particles(positions, flat, occupation)
+        self.engine.load_particles(positions, flat, occupation, ids=ids)
         self.engine.set_timestep(0)
         if key not in ('random_domain', 'center_domain', 'random_subvol', 'center_subvol'):
             old = np.zeros(S)
@@ -282,7 +307,10 @@ class Population(PopulationSetup):
                     break
                 old = np.copy(self.subvol_temperature)
         print('Initialising local quantities...')
-        self._host_census(geometry, phonon)
+        if self.world > 1:
+            self._device_census(geometry, phonon)      # fresh populations start at equilibrium with their subvolume
+        else:
+            self._host_census(geometry, phonon)
 
     # ---- initialisation at scale: positions, modes and occupations created on the device ----
     def _can_init_on_device(self, geometry, key):
@@ -302,8 +330,10 @@ class Population(PopulationSetup):
         import torch
         eng = self.engine
         dev = eng.device
-        N, S, ax = int(self.N_p), self.n_of_subvols, self.slice_axis
-        g = torch.Generator(device=dev); g.manual_seed(self.seed)
+        from ..parallel import shard_bounds
+        lo_i, hi_i = shard_bounds(self.rank, self.world, int(self.N_p))
+        N, S, ax = hi_i - lo_i, self.n_of_subvols, self.slice_axis
+        g = torch.Generator(device=dev); g.manual_seed(self.seed + 7919 * self.rank)
         cap = int(N * float(os.environ.get('NK_CAPACITY_FACTOR', 1.25))) + 1024
         eng.allocate(cap)
         t = eng.t
@@ -320,11 +350,11 @@ class Population(PopulationSetup):
         print('Assigning modes...')
         act = torch.as_tensor(np.nonzero(~phonon.inactive_modes_mask.reshape(-1))[0].astype(np.int32), device=dev)
         if self.particles_pmps >= 1:
-            idx = torch.arange(N, device=dev, dtype=torch.int64) % act.numel()
+            idx = (torch.arange(N, device=dev, dtype=torch.int64) + lo_i) % act.numel()
         else:
             idx = torch.randint(0, act.numel(), (N,), generator=g, device=dev)
         t['mode'][:N] = act[idx]; t['omode'][:N] = act[idx]; t['mode'][N:] = -1
-        t['pid'][:N] = torch.arange(N, device=dev, dtype=torch.int64)
+        t['pid'][:N] = torch.arange(N, device=dev, dtype=torch.int64) + lo_i
         del idx
         _, self.subvol_temperature = self.assign_temperatures(np.zeros(1, dtype=int), geometry)
         eng.set_sv_temperature(self.subvol_temperature)
@@ -364,6 +394,9 @@ class Population(PopulationSetup):
         svt = torch.empty(n, dtype=torch.int32, device=eng.device)
         check(eng.ctx, eng.L.nk_classify(eng.ctx, n, _dp(pos), _dp(svt), _dp(counts)), 'nk_classify')
         eng.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(counts)
         self.subvol_N_p = counts.cpu().numpy()
         self.N_p = int(self.subvol_N_p.sum())
         self.subvol_energy = np.interp(self.subvol_temperature, phonon.T_array, phonon.energy_array)
@@ -535,7 +568,12 @@ class Population(PopulationSetup):
             for sv in range(self.n_of_subvols):
                 info += ' {:>7.3f}'.format(self.subvol_temperature[sv])
             print(info + ' ]')
-        self.engine.step(1)
+        if self.sharded is not None:
+            if self.current_timestep > 0 and (self.current_timestep % 100) == 0:
+                self.sharded.rebalance()               # live counts drift with position-dependent absorption
+            self.sharded.step(1)
+        else:
+            self.engine.step(1)
         self.current_timestep += 1
         self.t = self.current_timestep * self.dt
         if (self.current_timestep % self.n_dt_to_conv) == 0:
