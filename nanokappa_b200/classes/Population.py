@@ -560,7 +560,15 @@ class Population(PopulationSetup):
         if self.current_timestep == 0:
             print('Simulating...')
         if (self.current_timestep % 100) == 0:
-            self.write_final_state(geometry, final=False)
+            # particle dump: every 100 steps like the reference while it is the cheap text file; the binary checkpoint of a
+            # large population (1 GB per 1e7 particles, ~1 s) every NK_DUMP_EVERY steps (default 1000; 0 = only at the end)
+            every = 100
+            if self.N_p > float(os.environ.get('NK_TEXT_DUMP_PERIODIC_MAX', 2e5)):
+                every = int(os.environ.get('NK_DUMP_EVERY', 1000))
+            if every > 0 and (self.current_timestep % every) == 0:
+                self.write_final_state(geometry, final=False)
+            elif self.current_timestep > 0 and hasattr(self.view, 'mean_T'):
+                self.write_subvolume_state(geometry)
             self.view.postprocess(verbose=False)
             self.update_residue(geometry)
             self.contains_check(geometry)
@@ -775,27 +783,32 @@ class Population(PopulationSetup):
             data = np.hstack((p['modes'], p['positions'], p['occupation'].reshape(-1, 1)))
             np.savetxt(os.path.join(self.results_folder_name, 'particle_data.txt'), data, '%d, %d, %.3f, %.3f, %.3f, %.6e', delimiter=',', header=header)
         if self.current_timestep > 0 and hasattr(self.view, 'mean_T'):
-            v = self.view
-            S = self.n_of_subvols
-            head = 'subvols final state data \nDate and time: {}\nhdf file = {}, POSCAR file = {}\n'.format(time, self.args.hdf_file, self.args.poscar_file)
-            cols = [np.arange(S).reshape(-1, 1), geometry.subvol_center, self.subvol_volume.reshape(-1, 1), v.mean_T.reshape(-1, 1),
-                    v.std_T.reshape(-1, 1), v.mean_sv_phi.reshape(-1, 3), v.std_sv_phi.reshape(-1, 3)]
-            if geometry.subvol_type == 'slice':
-                cols += [v.mean_sv_k.reshape(-1, 1), v.std_sv_k.reshape(-1, 1)]
-                head += 'subvol id, subvol x, subvol y, subvol z, subvol volume, T [K], sigma T [K], HF x [W/m^2], HF y [W/m^2], HF z [W/m^2], sigma HF x [W/m^2], sigma HF y [W/m^2], sigma HF z [W/m^2], kappa [W/m K], sigma kappa [W/m K]'
-                fmt = '%d, %.3e, %.3e, %.3e, %.3e, %.3f, %.3e, %.3e, %.3e, %.3e, %.3e, %.3e, %.3e, %.3e, %.3e'
-            else:
-                head += 'subvol id, subvol position, subvol volume, T [K], sigma T [K], HF x [W/m^2], HF y [W/m^2], HF z [W/m^2], sigma HF x [W/m^2], sigma HF y [W/m^2], sigma HF z [W/m^2]'
-                fmt = '%d, %.3e, %.3e, %.3e, %.3e, %.3f, %.3e, %.3e, %.3e, %.3e, %.3e, %.3e, %.3e'
-            np.savetxt(os.path.join(self.results_folder_name, 'subvolumes.txt'), np.hstack(cols), fmt, delimiter=',', header=head)
-            if geometry.subvol_type != 'slice' and geometry.n_of_subvol_con > 0:
-                head = 'connections final state data \nDate and time: {}\nhdf file = {}, POSCAR file = {}\n'.format(time, self.args.hdf_file, self.args.poscar_file) + \
-                       'connection id, sv 1, sv 2, con dx, con dy, con dz, dT [K], sigma dT [K], HF [W/m^2], sigma HF [W/m^2], kappa [W/m K], sigma kappa [W/m K]'
-                data = np.hstack((np.arange(geometry.n_of_subvol_con).reshape(-1, 1), geometry.subvol_connections, geometry.subvol_con_vectors,
-                                  v.mean_con_dT.reshape(-1, 1), v.std_con_dT.reshape(-1, 1), v.mean_con_phi.reshape(-1, 1),
-                                  v.std_con_phi.reshape(-1, 1), v.mean_con_k.reshape(-1, 1), v.std_con_k.reshape(-1, 1)))
-                np.savetxt(os.path.join(self.results_folder_name, 'subvol_connections.txt'), data,
-                           '%d, %d, %d, %.3e, %.3e, %.3e, %.3f, %.3e, %.3e, %.3e, %.3e, %.3e', delimiter=',', header=head)
+            self.write_subvolume_state(geometry)
+
+    def write_subvolume_state(self, geometry):
+        """subvolumes.txt / subvol_connections.txt (Population.py:2093-2151)."""
+        time = datetime.now().strftime('%Y-%m-%dT%H:%M:%S.%f')
+        v = self.view
+        S = self.n_of_subvols
+        head = 'subvols final state data \nDate and time: {}\nhdf file = {}, POSCAR file = {}\n'.format(time, self.args.hdf_file, self.args.poscar_file)
+        cols = [np.arange(S).reshape(-1, 1), geometry.subvol_center, self.subvol_volume.reshape(-1, 1), v.mean_T.reshape(-1, 1),
+                v.std_T.reshape(-1, 1), v.mean_sv_phi.reshape(-1, 3), v.std_sv_phi.reshape(-1, 3)]
+        if geometry.subvol_type == 'slice':
+            cols += [v.mean_sv_k.reshape(-1, 1), v.std_sv_k.reshape(-1, 1)]
+            head += 'subvol id, subvol x, subvol y, subvol z, subvol volume, T [K], sigma T [K], HF x [W/m^2], HF y [W/m^2], HF z [W/m^2], sigma HF x [W/m^2], sigma HF y [W/m^2], sigma HF z [W/m^2], kappa [W/m K], sigma kappa [W/m K]'
+            fmt = '%d, %.3e, %.3e, %.3e, %.3e, %.3f, %.3e, %.3e, %.3e, %.3e, %.3e, %.3e, %.3e, %.3e, %.3e'
+        else:
+            head += 'subvol id, subvol position, subvol volume, T [K], sigma T [K], HF x [W/m^2], HF y [W/m^2], HF z [W/m^2], sigma HF x [W/m^2], sigma HF y [W/m^2], sigma HF z [W/m^2]'
+            fmt = '%d, %.3e, %.3e, %.3e, %.3e, %.3f, %.3e, %.3e, %.3e, %.3e, %.3e, %.3e, %.3e'
+        np.savetxt(os.path.join(self.results_folder_name, 'subvolumes.txt'), np.hstack(cols), fmt, delimiter=',', header=head)
+        if geometry.subvol_type != 'slice' and geometry.n_of_subvol_con > 0:
+            head = 'connections final state data \nDate and time: {}\nhdf file = {}, POSCAR file = {}\n'.format(time, self.args.hdf_file, self.args.poscar_file) + \
+                   'connection id, sv 1, sv 2, con dx, con dy, con dz, dT [K], sigma dT [K], HF [W/m^2], sigma HF [W/m^2], kappa [W/m K], sigma kappa [W/m K]'
+            data = np.hstack((np.arange(geometry.n_of_subvol_con).reshape(-1, 1), geometry.subvol_connections, geometry.subvol_con_vectors,
+                              v.mean_con_dT.reshape(-1, 1), v.std_con_dT.reshape(-1, 1), v.mean_con_phi.reshape(-1, 1),
+                              v.std_con_phi.reshape(-1, 1), v.mean_con_k.reshape(-1, 1), v.std_con_k.reshape(-1, 1)))
+            np.savetxt(os.path.join(self.results_folder_name, 'subvol_connections.txt'), data,
+                       '%d, %d, %d, %.3e, %.3e, %.3e, %.3f, %.3e, %.3e, %.3e, %.3e, %.3e', delimiter=',', header=head)
 
     def save_plot_real_time(self):
         """Called by nanokappa.py:105 but missing upstream (AttributeError after the results are
