@@ -314,7 +314,11 @@ def gpu_arm(a):
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    numa = None
     if world > 1:
+        from nanokappa_b200.parallel import bind_to_gpu_numa
+        if os.environ.get("NK_NUMA_BIND", "1") != "0":
+            numa = bind_to_gpu_numa(local)             # before any pinned allocation: host buffers next to the GPU
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -438,7 +442,7 @@ def gpu_arm(a):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(a, n, "gpu"),
             "clocks": clocks, "gpu_launches": int((2 + (1 if prof.get("k_finalize", 0.0) > 0 else 0)) * a.steps),
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                    "timesteps_per_call": 1, "calls": e2e["calls"], "api": e2e["api"]},
+                    "timesteps_per_call": 1, "calls": e2e["calls"], "api": e2e["api"], "numa_node_rank0": numa},
             "roofline": roofline, "cpu_baseline": cpu,
             "particles_alive": int(n_alive1),
         }

@@ -32,6 +32,8 @@ def main(argv=None):
         import torch
         import torch.distributed as dist
         local = int(os.environ.get('LOCAL_RANK', 0))
+        from nanokappa_b200.parallel import bind_to_gpu_numa
+        bind_to_gpu_numa(local)
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
         if rank == 0:

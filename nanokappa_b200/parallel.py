@@ -38,6 +38,33 @@ F64_FIELDS = ("px", "py", "pz", "tc", "occ", "cx", "cy", "cz", "pid")      # pid
 I32_FIELDS = ("mode", "omode", "cfacet")
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs), so that the host staging buffers it
+    allocates afterwards (first touch) and the threads that scan / patch them sit next to the GPU's PCIe root port.
+    With one rank per GPU and host-resident particle arrays, cross-socket DMA is otherwise the bottleneck.  Returns the
+    node, or None when the topology is not exposed (containers, single-node hosts): then nothing is changed."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = "{:04x}:{:02x}:{:02x}.0".format(getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def rebalance_plan(counts):
     """Deterministic transfer list [(src, dst, n)] that brings every rank to total // W (+1 for the first total % W ranks).
     Every rank computes the same plan from the all-gathered live counts."""
