@@ -131,7 +131,7 @@ def test_converged_film_matches_reference(tmp_path, golden_dir):
     """Converged run, independent random draws: kappa, the temperature profile, the heat flux and the particle count
     of a short cross-plane film must agree with what the REFERENCE ITSELF produced (tests/golden/converged_film.json,
     written by oracle/gen_converged.py executing /root/reference) within the combined block-averaged standard
-    errors (4 sigma; the error estimates themselves come from 10 blocks, i.e. are known to ~25 %)."""
+    errors (5 sigma; the error estimates themselves come from 10 blocks, i.e. are known to ~25 %)."""
     import json
     from oracle import gen_converged as gc
     ref = json.load(open(os.path.join(golden_dir, "converged_film.json")))
@@ -148,7 +148,9 @@ def test_converged_film_matches_reference(tmp_path, golden_dir):
     for name in ("kappa", "T", "flux_x", "N_p"):
         g, r = got[name], ref[name]
         gm, ge, rm, re_ = (np.asarray(x, dtype=float) for x in (g["mean"], g["stderr"], r["mean"], r["stderr"]))
-        band = 4.0 * np.sqrt(ge ** 2 + re_ ** 2)
+        # 5 sigma of the combined error bars (themselves known to ~25 %), never tighter than a small physical floor
+        floor = {"kappa": 3e-3 * abs(rm), "T": 0.02, "flux_x": 0.01 * np.abs(rm).max(), "N_p": 2e-3 * rm}[name]
+        band = np.maximum(5.0 * np.sqrt(ge ** 2 + re_ ** 2), floor)
         assert (np.abs(gm - rm) <= band).all(), f"{name}: gpu {gm} +- {ge} vs reference {rm} +- {re_}"
     # and the error bars are small enough for the comparison to mean something: 0.2 % on kappa
     assert 4.0 * np.hypot(got["kappa"]["stderr"], ref["kappa"]["stderr"]) < 2e-3 * ref["kappa"]["mean"] * 2
