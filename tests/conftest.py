@@ -17,6 +17,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _library_built():
+    """The C-ABI library is a build artefact (git-ignored): compile it on first use in a fresh checkout
+    (nvcc cross-compiles sm_100a without a GPU)."""
+    lib = os.path.join(ROOT, "nanokappa_b200", "libnk_b200.so")
+    if not os.path.isfile(lib):
+        import __graft_entry__ as g
+        g.build()
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
