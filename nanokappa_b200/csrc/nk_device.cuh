@@ -55,6 +55,23 @@ __device__ __forceinline__ void nk_bin_add(long long* q, double* side, double v,
     }
 }
 
+// Global merge of the block sums: the same fixed point one level up, 128 bits wide (two native 64-bit atomics with the
+// carry riding on the high word), so that neither the order in which blocks finish nor the number of particles can change
+// or overflow the sums: T_sv is a pure function of the particle set.
+__device__ __forceinline__ void nk_gacc_add(unsigned long long* q, long long v) {
+    if (v == 0) return;
+    const unsigned long long lo = (unsigned long long)v;
+    const unsigned long long hi = v < 0 ? ~0ull : 0ull;
+    const unsigned long long old = atomicAdd(q, lo);
+    atomicAdd(q + 1, hi + ((old + lo) < old ? 1ull : 0ull));
+}
+__device__ __forceinline__ double nk_gacc_value(const unsigned long long* q, double inv_scale) {
+    const unsigned long long lo = __ldcg(q);
+    const long long hi = (long long)__ldcg(q + 1);
+    if ((hi == 0 && (long long)lo >= 0) || (hi == -1 && (long long)lo < 0)) return (double)(long long)lo * inv_scale;
+    return ((double)hi * 18446744073709551616.0 + (double)lo) * inv_scale;
+}
+
 // The rare path's block-private copy of the accumulator vector: `acc` (double, the side bins) is followed by the
 // fixed-point halves of the same entries.  Energies / reservoir balances use NK_QE, fluxes NK_QF, counters are integers.
 #define NK_RACC_Q(P, acc, idx) (reinterpret_cast<long long*>((acc) + nk_acc_len((P).S, (P).R)) + (idx))
@@ -69,6 +86,16 @@ __device__ __forceinline__ double nk_racc_inv_scale(int S, int R, int k) {
     if (k < 5 * S + 2 * R) return 1.0 / NK_QE;                            // reservoir energy balance
     if (k < 5 * S + 5 * R) return 1.0 / NK_QF;                            // reservoir flux
     return 1.0;                                                           // emitted, absorbed
+}
+// One block, after every other block of the step has merged its sums: fixed point -> the f64 accumulator vector that the
+// closing block (and, between ranks, the exchange) reads; the side bins already sit in `acc`.
+__device__ __forceinline__ void nk_gacc_to_f64(const NkP& P) {
+    const int n = nk_acc_len(P.S, P.R);
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const double v = nk_gacc_value(P.acc_q + 2 * k, nk_racc_inv_scale(P.S, P.R, k));
+        P.acc[k] = v + __ldcg(P.acc + k);
+        P.acc_q[2 * k] = 0ull; P.acc_q[2 * k + 1] = 0ull;
+    }
 }
 
 #define NK_STREAM_EMIT_A 0u

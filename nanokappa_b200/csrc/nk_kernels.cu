@@ -343,6 +343,7 @@ static int nk_alloc_scratch(nk_ctx* ctx) {
     NkP& P = ctx->P;
     double* dd;
     NK_UP(dd, double, (const double*)nullptr, (size_t)nk_acc_len(P.S, P.R)); P.acc = dd;
+    { unsigned long long* dq; NK_UP(dq, unsigned long long, (const unsigned long long*)nullptr, (size_t)2 * nk_acc_len(P.S, P.R)); P.acc_q = dq; }
     NK_UP(dd, double, (const double*)nullptr, (size_t)4 * std::max(P.R, 1)); P.res_acc = dd;
     NK_UP(dd, double, (const double*)nullptr, (size_t)nk_out_len(P.S, P.R)); P.out = dd;
     P.hot_tab = nullptr;

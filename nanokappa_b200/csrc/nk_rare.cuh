@@ -359,8 +359,8 @@ __global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(Nk
         NK_TRACE_MARK_MAX(P, 3);
         for (int k = threadIdx.x; k < nacc; k += blockDim.x)
         {
-            const double v = (double)rq[k] * nk_racc_inv_scale(P.S, P.R, k) + racc[k];
-            if (v != 0.0) atomicAdd(P.acc + k, v);
+            nk_gacc_add(P.acc_q + 2 * k, rq[k]);
+            if (racc[k] != 0.0) atomicAdd(P.acc + k, racc[k]);
         }
         if (threadIdx.x == 0) {
             // live count: + particles that got a slot (emitted - absorbed on arrival) - absorbed
@@ -368,7 +368,8 @@ __global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(Nk
             if (d != 0.0) atomicAdd((unsigned long long*)&P.dyn->n_alive, (unsigned long long)(long long)d);
         }
     }
-    if (FUSE) {
+    {
+        // the last block to finish turns the fixed-point sums into the f64 accumulator vector; with FUSE it also closes the step
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -378,6 +379,10 @@ __global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(Nk
         __syncthreads();
         if (s_last) {
             __threadfence();
+            nk_gacc_to_f64(P);
+            __threadfence();
+            __syncthreads();
+            if (!FUSE) { if (threadIdx.x == 0) P.dyn->blocks_done = 0; return; }
             if (P.comm_on) nk_exchange_sums(P);
             if (P.trace && threadIdx.x == 0) P.trace[4] = nk_globaltimer();
             nk_finalize_block(P, sm_fin);

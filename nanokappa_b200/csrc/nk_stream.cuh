@@ -285,13 +285,17 @@ __device__ __forceinline__ void nk_flush_bins(const NkP& P, const long long* bin
                                               const unsigned int* binC) {
     const int S = P.S;
     double* acc = P.acc;
+    unsigned long long* q = P.acc_q;
     for (int i = threadIdx.x; i < S; i += blockDim.x) {
         if (binC[i]) {
-            atomicAdd(acc + NK_ACC_E(S, P.R) + i, (double)binE[i] * (1.0 / NK_QE) + binX[i]);
-            atomicAdd(acc + NK_ACC_CNT(S, P.R) + i, (double)binC[i]);
+            nk_gacc_add(q + 2 * (NK_ACC_E(S, P.R) + i), binE[i]);
+            if (binX[i] != 0.0) atomicAdd(acc + NK_ACC_E(S, P.R) + i, binX[i]);
+            nk_gacc_add(q + 2 * (NK_ACC_CNT(S, P.R) + i), (long long)binC[i]);
             if (FLUX) {
-                for (int k = 0; k < 3; ++k)
-                    atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i + k, (double)binF[3 * i + k] * (1.0 / NK_QF) + binX[S + 3 * i + k]);
+                for (int k = 0; k < 3; ++k) {
+                    nk_gacc_add(q + 2 * (NK_ACC_FLUX(S, P.R) + 3 * i + k), binF[3 * i + k]);
+                    if (binX[S + 3 * i + k] != 0.0) atomicAdd(acc + NK_ACC_FLUX(S, P.R) + 3 * i + k, binX[S + 3 * i + k]);
+                }
             }
         }
     }

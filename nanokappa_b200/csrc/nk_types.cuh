@@ -131,7 +131,8 @@ struct NkP {
     long long slot_lo, slot_hi;       // slot range the streaming kernel covers in this launch (chunked host pipeline)
     int scan_emit;                    // 1: this launch advances the reservoir counters
     double* T_sv;                     // (S) current subvolume temperatures
-    double* acc;                      // per-step accumulators, see layout below
+    double* acc;                      // per-step accumulators, see layout below (f64: the exchange vector + side bins)
+    unsigned long long* acc_q;        // the same entries in 128-bit fixed point {lo, hi}: order-independent block merges
     double* res_acc;                  // (R*4) E_bal + flux accumulated over the convergence window
     double* out;                      // results block, see NK_OUT_* offsets
     NkDyn* dyn;

@@ -77,6 +77,17 @@ def test_readme_case_properties(tmp_path, monkeypatch):
     a, b = pop.engine.particles(), pop2.engine.particles()
     assert np.array_equal(a["ids"], b["ids"]) and np.array_equal(a["modes"], b["modes"])
     assert np.array_equal(a["collision_facets"], b["collision_facets"]) and np.array_equal(a["positions"], b["positions"])
+    # same seed, same variant, again: block sums are merged in fixed point (order-independent), draws are keyed by particle,
+    # so a run is a pure function of its seed -- temperatures, energies and occupations repeat BIT FOR BIT although slot
+    # assignment and block scheduling differ from run to run
+    geo3, pop3, census3 = _run(tmp_path / "c", 5, 200, {"NK_STEP_TAB": "force"}, monkeypatch)
+    r3 = pop3.engine.results()
+    assert census3 == census
+    assert np.array_equal(r3["subvol_temperature"], T) and np.array_equal(r3["subvol_energy"], res["subvol_energy"])
+    assert np.array_equal(r3["subvol_heat_flux"], res["subvol_heat_flux"])
+    c = pop3.engine.particles()
+    assert np.array_equal(c["ids"], a["ids"]) and np.array_equal(c["occupation"], a["occupation"])
+    assert np.array_equal(c["positions"], a["positions"]) and np.array_equal(c["n_timesteps"], a["n_timesteps"])
 
 
 # two populations above the 2^20-particle threshold of the pipelined host-buffer call: the cross-plane film (no rough
