@@ -1214,7 +1214,7 @@ int nk_comm_export(nk_ctx* ctx, void* handle_out) {
     if (P.world < 1 || P.world > 8) { ctx->err = "fused exchange supports 1..8 ranks"; return -1; }
     if (!ctx->comm_block) {
         const size_t flag_bytes = 256;
-        const size_t bytes = flag_bytes + 2 * (size_t)P.world * nk_acc_len(P.S, P.R) * sizeof(double);
+        const size_t bytes = flag_bytes + 2 * (size_t)P.world * 3 * nk_acc_len(P.S, P.R) * sizeof(double);   // {lo, hi, side} per entry
         // an allocation of its own (>= 2 MB): IPC handles name the underlying allocation, and small blocks of several
         // contexts of one process would share one -- a peer cannot map the same allocation twice
         NK_CK(cudaMalloc(&ctx->comm_block, std::max<size_t>(bytes, (size_t)2 << 20)));

@@ -259,13 +259,18 @@ __device__ void nk_finalize_block(const NkP& P, double* sm) {
 // at most one step ahead of the slowest one.  The wait is bounded (~20 s): a missing peer raises NK_ERR_COMM
 // instead of hanging the GPU.
 __device__ void nk_exchange_sums(const NkP& P) {
+    // message of a rank: the 128-bit fixed-point sums {lo, hi} of every accumulator entry, then the f64 side bins.  The
+    // integer parts are added exactly, so the world totals -- and with them T_sv -- do not depend on how the particles
+    // are spread over the ranks: a sharded run repeats the single-GPU run bit for bit.
     const int len = nk_acc_len(P.S, P.R);
     const int W = P.world;
+    const size_t stride = 3 * (size_t)len;                       // 8-byte words per (parity, sender)
     const unsigned long long seq = (unsigned long long)(P.dyn->step + 1);
     const int par = (int)(seq & 1ull);
     for (int r = 0; r < W; ++r) {
-        double* dst = P.peer_mbox[r] + ((size_t)par * W + P.rank) * len;
-        for (int i = threadIdx.x; i < len; i += blockDim.x) dst[i] = __ldcg(P.acc + i);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.peer_mbox[r]) + ((size_t)par * W + P.rank) * stride;
+        for (int i = threadIdx.x; i < 2 * len; i += blockDim.x) dst[i] = __ldcg(P.acc_q + i);
+        for (int i = threadIdx.x; i < len; i += blockDim.x) dst[2 * len + i] = (unsigned long long)__double_as_longlong(__ldcg(P.acc + i));
     }
     __threadfence_system();
     __syncthreads();
@@ -281,10 +286,20 @@ __device__ void nk_exchange_sums(const NkP& P) {
     }
     __syncthreads();
     __threadfence_system();
+    const volatile unsigned long long* box = reinterpret_cast<const volatile unsigned long long*>(P.mbox_local) + (size_t)par * W * stride;
     for (int i = threadIdx.x; i < len; i += blockDim.x) {
-        double sum = 0.0;
-        for (int r = 0; r < W; ++r) sum += *((volatile double*)(P.mbox_local + ((size_t)par * W + r) * len + i));
-        P.acc[i] = sum;
+        unsigned long long lo = 0ull, hi = 0ull;
+        double side = 0.0;
+        for (int r = 0; r < W; ++r) {
+            const volatile unsigned long long* m = box + (size_t)r * stride;
+            const unsigned long long a = m[2 * i], b = m[2 * i + 1];
+            const unsigned long long s = lo + a;
+            hi += b + (s < lo ? 1ull : 0ull);
+            lo = s;
+            side += __longlong_as_double((long long)m[2 * len + i]);
+        }
+        P.acc_q[2 * i] = lo; P.acc_q[2 * i + 1] = hi;
+        P.acc[i] = side;
     }
     __threadfence();
     __syncthreads();
@@ -379,11 +394,11 @@ __global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(Nk
         __syncthreads();
         if (s_last) {
             __threadfence();
+            if (FUSE && P.comm_on) nk_exchange_sums(P);       // world totals, still in fixed point
             nk_gacc_to_f64(P);
             __threadfence();
             __syncthreads();
             if (!FUSE) { if (threadIdx.x == 0) P.dyn->blocks_done = 0; return; }
-            if (P.comm_on) nk_exchange_sums(P);
             if (P.trace && threadIdx.x == 0) P.trace[4] = nk_globaltimer();
             nk_finalize_block(P, sm_fin);
             __syncthreads();

@@ -5,7 +5,8 @@
 Every rank owns a block of the fixture's particles and a mode range of the reservoirs.  The same shards are
 stepped twice -- per-step NCCL all-reduce between nk_step_local / nk_step_finalize, and the fused in-kernel
 exchange over NVLink peer memory -- and both must agree with each other (integers identical, temperatures to
-1e-13) and, gathered on rank 0, with the single-context run of the whole population."""
+1e-13) and, gathered on rank 0, with the single-context run of the whole population; the fused run, whose exchange adds
+the ranks' fixed-point sums exactly, must reproduce the single-context temperatures and energies BIT FOR BIT."""
 import os
 import sys
 
@@ -68,7 +69,10 @@ def main():
             ok &= bool(np.array_equal(np.concatenate([g["collision_facets"] for g in gathered])[order], ps["collision_facets"]))
             ok &= bool(np.array_equal(rf["subvol_N_p"], rs["subvol_N_p"]))
             ok &= bool(np.allclose(rf["subvol_temperature"], rs["subvol_temperature"], rtol=1e-12, atol=0))
-            print(f"[{name}] world={world} fused==nccl==single: {ok}  N_p={rs['N_p']}", flush=True)
+            # the fused exchange adds the ranks' fixed-point sums exactly: the sharded run IS the single-GPU run
+            exact = bool(np.array_equal(rf["subvol_temperature"], rs["subvol_temperature"]) and np.array_equal(rf["subvol_energy"], rs["subvol_energy"]))
+            ok &= exact
+            print(f"[{name}] world={world} fused==nccl==single: {ok}  fused bit-identical to single: {exact}  N_p={rs['N_p']}", flush=True)
         # unbalanced shards (rank 0 owns 70 %), rebalanced by NCCL point-to-point migration half way: same union
         n_all = st.positions.shape[0]
         cut = [0] + [int(n_all * (0.7 + 0.3 * r / (world - 1))) for r in range(world)]
