@@ -71,6 +71,7 @@ struct nk_ctx {
     void* cold_dev = nullptr; void* cold_host = nullptr; long long cold_cap = 0;
     cudaEvent_t ev_cold = nullptr;
     bool sparse_cold = true;       // NK_HOST_SPARSE=0: upload the cold arrays densely
+    bool l2_persist = false, l2_window_set = false;      // NK_L2_PERSIST=1 (experiment)
     bool use_pipeline = true;      // NK_HOST_PIPELINE=0 disables it
     long long xfer_h2d = 0, xfer_d2h = 0;   // bytes of the last nk_advance_host call
     void* comm_block = nullptr;    // flags + mailboxes of the fused exchange
@@ -146,6 +147,7 @@ int nk_create(int device, nk_ctx** out) {
     ctx->P.slot_lo = 0; ctx->P.slot_hi = 0x7fffffffffffffffLL; ctx->P.scan_emit = 1;
     if (const char* e = getenv("NK_HOST_PIPELINE")) ctx->use_pipeline = strcmp(e, "0") != 0;
     if (const char* e = getenv("NK_HOST_SPARSE")) ctx->sparse_cold = strcmp(e, "0") != 0;
+    if (const char* e = getenv("NK_L2_PERSIST")) ctx->l2_persist = strcmp(e, "0") != 0;
     ctx->P.trace = nullptr;
     if (const char* e = getenv("NK_TRACE")) {
         if (strcmp(e, "0") != 0 && cudaMalloc(&ctx->P.trace, 8 * sizeof(unsigned long long)) == cudaSuccess)
@@ -661,6 +663,22 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     }
     if (variant == 1) smem = NK_STAGES * sizeof(NkTileSmem) + (NK_STAGES + 1) * 8 + nk_step_smem(P);
     if (variant == 3) smem = 2 * sizeof(NkPfStage) + nk_step_smem(P);
+    // experiment (NK_L2_PERSIST=1): keep the (mode, subvolume) table in the persisting part of the L2 while 8 GB of particle
+    // state stream through it
+    if (variant == 4 && ctx->l2_persist && !ctx->l2_window_set) {
+        cudaDeviceProp prop; cudaGetDeviceProperties(&prop, ctx->device);
+        const size_t bytes = (size_t)P.M * P.S * sizeof(double2);
+        const size_t win = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(win, (size_t)prop.persistingL2CacheMaxSize));
+        cudaStreamAttrValue attr; memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = P.hot_tab;
+        attr.accessPolicyWindow.num_bytes = win;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+        ctx->l2_window_set = true;
+    }
     nk_step_fn kern = nk_pick_step(variant, ctx->has_rough, fast, relax, flux);
     if (!ctx->step_blocks || ctx->step_blocks_variant != variant) {
         int per_sm = 0;
