@@ -137,7 +137,7 @@ class ClockSampler:
                 self.samples.append((float(sm), pw, int(rs)))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.001)
 
     def _read(self):
         for ln in self.proc.stdout:
@@ -523,7 +523,7 @@ def e2e_run(a, eng, n, world, rank, one_step, dev, fused=False):
 def main():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", 1)))
-    p.add_argument("--steps", type=int, default=100)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--particles", type=float, default=1e8, help="particles per GPU")

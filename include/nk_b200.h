@@ -134,6 +134,12 @@ int nk_bind_particles(nk_ctx* ctx, int64_t capacity,
                       double* cx, double* cy, double* cz, int64_t* pid);
 int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots);     /* slots [0, n_slots) are in use or free-listed */
 int nk_get_slot_count(nk_ctx* ctx, int64_t* n_slots, int64_t* n_alive);
+/* Optional, after the caller has ordered the particle arrays by mode (a set-up / maintenance choice that makes the mode-table
+ * gathers of neighbouring particles coalesce): first_slot_of_mode (n_modes, host) = index of the first slot holding each flat
+ * mode (insertion point for absent modes).  With NK_FREE_BUCKETS=1 emitted particles are then placed in free slots next to
+ * their own mode (experimental: it did not slow the erosion of the order measurably, profiles/README.md); by default the map
+ * is recorded and all free slots share one ring.  NULL forgets the map; nk_set_slot_count forgets it too. */
+int nk_set_mode_slots(nk_ctx* ctx, const int64_t* first_slot_of_mode);
 int nk_set_sv_temperature(nk_ctx* ctx, const double* T_sv_host);   /* Population.subvol_temperature */
 int nk_get_sv_temperature(nk_ctx* ctx, double* T_sv_host);
 int nk_set_timestep(nk_ctx* ctx, int64_t current_timestep);

@@ -42,6 +42,7 @@ SIGNATURES = {
     "nk_bind_particles": (C.c_int, [VP, C.c_int64] + [VP] * 12),
     "nk_set_slot_count": (C.c_int, [VP, C.c_int64]),
     "nk_get_slot_count": (C.c_int, [VP, c_lp, c_lp]),
+    "nk_set_mode_slots": (C.c_int, [VP, VP]),
     "nk_set_sv_temperature": (C.c_int, [VP, VP]),
     "nk_get_sv_temperature": (C.c_int, [VP, VP]),
     "nk_set_timestep": (C.c_int, [VP, C.c_int64]),

@@ -576,6 +576,13 @@ class Population(PopulationSetup):
             for sv in range(self.n_of_subvols):
                 info += ' {:>7.3f}'.format(self.subvol_temperature[sv])
             print(info + ' ]')
+        # maintenance: emitted particles reuse the slots of absorbed ones, which erodes the order by mode made at set-up and
+        # with it the locality of the mode-table gathers (+13 % per step after 100 steps at 1e8 particles, profiles/README.md);
+        # re-sorting costs about 12 steps' worth, so large populations are re-ordered every NK_RESORT_EVERY steps (0 = never)
+        every = int(os.environ.get('NK_RESORT_EVERY', 250))
+        if every > 0 and self.current_timestep > 0 and (self.current_timestep % every) == 0 and \
+                self.N_p >= float(os.environ.get('NK_RESORT_MIN', 1e6)):
+            self.engine.sort_by_mode()
         if self.sharded is not None:
             if self.current_timestep > 0 and (self.current_timestep % 100) == 0:
                 self.sharded.rebalance()               # live counts drift with position-dependent absorption

@@ -72,6 +72,7 @@ struct nk_ctx {
     cudaEvent_t ev_cold = nullptr;
     bool sparse_cold = true;       // NK_HOST_SPARSE=0: upload the cold arrays densely
     bool l2_persist = false, l2_window_set = false;      // NK_L2_PERSIST=1 (experiment)
+    int* mode_bucket_dev = nullptr;    // storage of NkP::mode_bucket
     bool use_pipeline = true;      // NK_HOST_PIPELINE=0 disables it
     long long xfer_h2d = 0, xfer_d2h = 0;   // bytes of the last nk_advance_host call
     void* comm_block = nullptr;    // flags + mailboxes of the fused exchange
@@ -93,6 +94,7 @@ static void nk_prof_mark(nk_ctx* ctx) {
 }
 
 static std::string g_create_err;
+static bool getenv_is_one(const char* name) { const char* e = getenv(name); return e && !strcmp(e, "1"); }
 
 #define NK_CK(call)                                                                          \
     do {                                                                                     \
@@ -436,7 +438,18 @@ int nk_bind_particles(nk_ctx* ctx, int64_t cap, double* px, double* py, double* 
     P.cx = cx; P.cy = cy; P.cz = cz; P.pid = (long long*)pid;
     int* di;
     NK_UP(di, int, (const int*)nullptr, (size_t)cap); P.hitlist = di;
-    NK_UP(di, int, (const int*)nullptr, (size_t)cap); P.freelist = di;
+    // free-slot rings (NkP::fr_*): one bucket ring per mode for the ordered region + the global ring of `cap` entries
+    {
+        // (experiment, off by default: NK_FREE_BUCKETS=1 -- measured no gain, see profiles/README.md; without it every slot
+        //  recycles through the global ring)
+        const char* e = getenv("NK_FREE_BUCKETS");
+        long long B = (e && !strcmp(e, "1")) ? std::max<long long>(1, std::min<long long>(P.M, cap)) : 1;
+        P.fr_B = (int)B;
+        P.fr_bsize = (int)((cap + B - 1) / B);
+        NK_UP(di, int, (const int*)nullptr, (size_t)P.fr_B * P.fr_bsize + (size_t)cap); P.freelist = di;
+        long long* dl; NK_UP(dl, long long, (const long long*)nullptr, 3 * ((size_t)P.fr_B + 1)); P.fr_ctr = dl;
+        P.mode_bucket = nullptr; P.fr_sorted = 0;          // until nk_set_mode_slots: every slot recycles through the global ring
+    }
     ctx->particles_bound = true;
     return 0;
 }
@@ -469,6 +482,8 @@ int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots) {
     ctx->h_slots_hint = n_slots;
     d.n_slots = n_slots; d.fr_head = d.fr_tail = d.fr_snap = 0; d.n_hits = 0; d.n_emit = 0; d.n_new = 0; d.last_hits = 0; d.last_new = 0; d.blocks_done = 0;
     if (nk_write_dyn(ctx, &d)) return -1;
+    NK_CK(cudaMemsetAsync(ctx->P.fr_ctr, 0, 3 * ((size_t)ctx->P.fr_B + 1) * sizeof(long long), ctx->stream));   // all free-slot rings empty
+    ctx->P.mode_bucket = nullptr; ctx->P.fr_sorted = 0;      // a new slot layout: the mode map (if any) must be published again
     unsigned long long* dc; NK_CK(cudaMalloc(&dc, 8)); NK_CK(cudaMemset(dc, 0, 8));
     k_count_alive<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->P, dc);
     unsigned long long hc = 0;
@@ -478,6 +493,27 @@ int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots) {
     if (nk_read_dyn(ctx, &d)) return -1;
     d.n_alive = (long long)hc;
     return nk_write_dyn(ctx, &d);
+}
+
+int nk_set_mode_slots(nk_ctx* ctx, const int64_t* first_slot_of_mode) {
+    cudaSetDevice(ctx->device);
+    NkP& P = ctx->P;
+    if (!ctx->particles_bound || P.M == 0) { ctx->err = "nk_set_phonon and nk_bind_particles first"; return -1; }
+    NK_CK(cudaStreamSynchronize(ctx->stream));
+    // pending free slots are dropped (they stay unused until the next compaction): the rings change meaning
+    NK_CK(cudaMemset(P.fr_ctr, 0, 3 * ((size_t)P.fr_B + 1) * sizeof(long long)));
+    if (!first_slot_of_mode || !getenv_is_one("NK_FREE_BUCKETS")) { P.mode_bucket = nullptr; P.fr_sorted = 0; return 0; }
+    NkDyn d; if (nk_read_dyn(ctx, &d)) return -1;
+    std::vector<int> mb(P.M);
+    for (int m = 0; m < P.M; ++m) {
+        long long b = first_slot_of_mode[m] / P.fr_bsize;
+        mb[m] = (int)std::max<long long>(0, std::min<long long>(b, P.fr_B - 1));
+    }
+    if (!ctx->mode_bucket_dev) { int* di; NK_UP(di, int, (const int*)nullptr, (size_t)P.M); ctx->mode_bucket_dev = di; }
+    NK_CK(cudaMemcpy(ctx->mode_bucket_dev, mb.data(), (size_t)P.M * sizeof(int), cudaMemcpyHostToDevice));
+    P.mode_bucket = ctx->mode_bucket_dev;
+    P.fr_sorted = d.n_slots;                   // the ordered region: everything in use right now
+    return 0;
 }
 
 int nk_get_slot_count(nk_ctx* ctx, int64_t* n_slots, int64_t* n_alive) {

@@ -22,19 +22,53 @@ __device__ __forceinline__ void nk_accumulate(const NkP& P, double* acc, const N
     }
 }
 
-// Free slots live in a ring: absorbed particles push at `fr_tail`, emission pops at `fr_head` but only
-// entries pushed in EARLIER steps (below `fr_snap`, advanced by the finalize), so that pushes and pops
-// of the same launch never touch the same entry.
+// Free slots live in rings (NkP::fr_*): absorbed particles push at the tail of the ring of their slot -- the bucket ring of an
+// ordered slot, the global ring otherwise -- and emission pops at the head of the bucket where the new particle's mode lives
+// (then its neighbours, then the global ring), but only entries pushed in EARLIER steps (below the ring's `snap`, advanced in
+// the prologue of the next streaming kernel), so that pushes and pops of the same launch never touch the same entry.  A bucket
+// ring only ever receives its own fr_bsize slots and the global ring holds cap entries: no ring can overflow.
 __device__ __forceinline__ void nk_kill(const NkP& P, double* acc, long long i) {
     P.mode[i] = -1;
-    unsigned long long k = nk_agg_inc((unsigned long long*)&P.dyn->fr_tail);
-    P.freelist[k % (unsigned long long)P.cap] = (int)i;
+    const bool ordered = i < P.fr_sorted;
+    const int b = ordered ? (int)(i / P.fr_bsize) : P.fr_B;
+    const unsigned long long size = ordered ? (unsigned long long)P.fr_bsize : (unsigned long long)P.cap;
+    long long* c = P.fr_ctr + 3 * (size_t)b;
+    const unsigned long long k = atomicAdd((unsigned long long*)(c + 1), 1ull);
+    P.freelist[(size_t)b * P.fr_bsize + (k % size)] = (int)i;
     NK_RACC_N(P, acc, NK_ACC_NABS(P.S, P.R));
 }
-__device__ __forceinline__ long long nk_take_slot(const NkP& P) {
-    // claims beyond fr_snap are not returned: the finalize clamps fr_head back to fr_snap
-    long long old = (long long)nk_agg_inc((unsigned long long*)&P.dyn->fr_head);
-    if (old < P.dyn->fr_snap) return P.freelist[old % P.cap];
+__device__ __forceinline__ long long nk_pop_ring(const NkP& P, int b, long long size) {
+    long long* c = P.fr_ctr + 3 * (size_t)b;
+    if (*(volatile long long*)c >= c[2]) return -1;                     // nothing recyclable here (cheap look before the atomic)
+    const long long old = (long long)atomicAdd((unsigned long long*)c, 1ull);
+    // a claim beyond the snapshot is not returned: the next prologue clamps the head back
+    return old < c[2] ? (long long)P.freelist[(size_t)b * P.fr_bsize + (old % size)] : -1;
+}
+__device__ __forceinline__ long long nk_take_slot(const NkP& P, int mode) {
+    if (P.mode_bucket && P.fr_sorted > 0) {
+        const int b0 = P.mode_bucket[mode];
+        for (int t = 0; t < 5; ++t) {
+            const int b = b0 + ((t & 1) ? (t + 1) / 2 : -(t / 2));      // b0, b0+1, b0-1, b0+2, b0-2
+            if (b < 0 || b >= P.fr_B) continue;
+            const long long s = nk_pop_ring(P, b, P.fr_bsize);
+            if (s >= 0) return s;
+        }
+    }
+    {
+        const long long s = nk_pop_ring(P, P.fr_B, P.cap);
+        if (s >= 0) return s;
+    }
+    if (P.mode_bucket && P.fr_sorted > 0) {
+        // the neighbourhood is exhausted (a rank of a sharded run emits only its share of the modes but absorbs all of them):
+        // take a free slot from anywhere rather than growing the slot range -- a few probes of pseudo-random buckets
+        unsigned int h = (unsigned int)clock64() * 2654435761u + (unsigned int)mode * 40503u + threadIdx.x;
+        const unsigned int used = (unsigned int)min((long long)P.fr_B, P.fr_sorted / P.fr_bsize + 1);
+        for (int t = 0; t < 8; ++t) {
+            h = h * 1664525u + 1013904223u;
+            const long long s = nk_pop_ring(P, (int)((h >> 8) % used), P.fr_bsize);
+            if (s >= 0) return s;
+        }
+    }
     long long slot = (long long)nk_agg_inc((unsigned long long*)&P.dyn->n_slots);      // nothing recyclable: append
     if (slot >= P.cap) {
         atomicAdd((unsigned long long*)&P.dyn->n_slots, (unsigned long long)(-1LL));
@@ -75,7 +109,7 @@ __device__ __forceinline__ void nk_emit_particle(const NkP& P, const NkGeo& G, d
     NK_RACC_N(P, acc, NK_ACC_NEMIT(P.S, P.R));
     if (p.tc < 0.0) nk_boundary_events(P, G, p, step, acc);
     if (!p.alive) { NK_RACC_N(P, acc, NK_ACC_NABS(P.S, P.R)); return; }   // crossed the whole domain within the step
-    const long long slot = nk_take_slot(P);
+    const long long slot = nk_take_slot(P, m);
     if (slot < 0) return;
     nk_store_particle(P, slot, p);
     P.pid[slot] = p.id;
@@ -246,8 +280,6 @@ __device__ void nk_finalize_block(const NkP& P, double* sm) {
         d->n_hits = 0;
         d->n_emit = 0;
         d->n_new = 0;
-        if (d->fr_head > d->fr_snap) d->fr_head = d->fr_snap;      // over-claims of an exhausted free list (nk_take_slot)
-        d->fr_snap = d->fr_tail;           // slots freed in this step become recyclable from the next one
         d->blocks_done = 0;
     }
 }

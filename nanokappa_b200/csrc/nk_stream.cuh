@@ -181,6 +181,13 @@ __device__ __forceinline__ long long nk_one_to_one_share(const NkP& P, int r) {
 }
 
 __device__ __forceinline__ void nk_emit_scan(const NkP& P) {
+    // free-slot rings: slots freed in the previous step become recyclable, over-claims of exhausted rings are dropped
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b <= P.fr_B; b += (long long)gridDim.x * blockDim.x) {
+        long long* c = P.fr_ctr + 3 * b;
+        const long long tail = c[1];
+        if (c[0] > c[2]) c[0] = c[2];
+        if (c[2] != tail) c[2] = tail;
+    }
     if (P.res_gen == NK_RESGEN_ONE_TO_ONE) {
         // one_to_one (Population.py:457-489): as many particles as the reservoir absorbed in the previous step; the
         // k-th of them belongs to rank k % world.  No table scan: k_rare decodes (reservoir, k) from the item index.

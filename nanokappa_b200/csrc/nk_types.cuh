@@ -126,6 +126,13 @@ struct NkP {
     long long* pid;
     // ---- scratch owned by the ctx
     int* hitlist; int* freelist;
+    // Free slots are kept in rings with counters {head, tail, snap} in fr_ctr: one global ring (index fr_B, entries
+    // freelist[fr_B * fr_bsize ...], capacity cap) and, once the host has ordered the particles by mode and published where
+    // each mode lives (nk_set_mode_slots), fr_B bucket rings of fr_bsize consecutive slots each (ring b = freelist[b * fr_bsize,
+    // (b + 1) * fr_bsize)) for the ordered region [0, fr_sorted).  A new particle of mode m takes a slot from the bucket of
+    // its mode (mode_bucket[m]) or a neighbour, so the mode order -- and with it the locality of the mode-table gathers --
+    // survives emission and absorption; slots beyond the ordered region recycle through the global ring.
+    long long* fr_ctr; int fr_B; int fr_bsize; const int* mode_bucket; long long fr_sorted;
     int2* emitlist;                   // (R*M) {reservoir << 8 | copies, mode} of the entries emitting this step
     int* newslots; long long newslots_cap;   // slots that received an emitted particle in this step
     long long slot_lo, slot_hi;       // slot range the streaming kernel covers in this launch (chunked host pipeline)

@@ -197,6 +197,10 @@ class Engine:
         t["mode"][n_live:n] = -1
         torch.cuda.synchronize(self.device)
         check(self.ctx, self.L.nk_set_slot_count(self.ctx, n_live), "nk_set_slot_count")
+        # where each mode lives now: emitted particles will be placed next to their own mode (nk_set_mode_slots)
+        first = torch.searchsorted(t["mode"][:n_live].contiguous(), torch.arange(self.M, device=self.device, dtype=torch.int32))
+        first = np.ascontiguousarray(first.cpu().numpy().astype(np.int64))
+        check(self.ctx, self.L.nk_set_mode_slots(self.ctx, first.ctypes.data_as(C.c_void_p)), "nk_set_mode_slots")
 
     def set_sv_temperature(self, T):
         T = _f64(T)

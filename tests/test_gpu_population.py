@@ -262,3 +262,24 @@ def test_command_line_driver_end_to_end(tmp_path):
         assert (run / f).is_file(), f
     rows = [l for l in (run / "convergence.txt").read_text().splitlines() if l and not l.startswith("#")]
     assert len(rows) >= 21                                                   # row 0 + one per 10 steps
+
+
+def test_maintenance_resort_does_not_change_the_physics(tmp_path, monkeypatch):
+    """Large populations are re-ordered by mode every NK_RESORT_EVERY steps (slot layout only).  Sums are merged in fixed
+    point and draws are keyed by particle, so the run with re-sorting must repeat the run without it BIT FOR BIT."""
+    text = gen_golden.PARAMS_C1.format(eta=2, n=15000)
+    out = []
+    for every in ("0", "7"):
+        monkeypatch.setenv("NK_RESORT_EVERY", every)
+        monkeypatch.setenv("NK_RESORT_MIN", "0")
+        args, geo, ph, pop = _population(text, tmp_path / every, seed=9)
+        with contextlib.redirect_stdout(io.StringIO()):
+            for _ in range(40):
+                pop.run_timestep(geo, ph)
+        p = pop.engine.particles()
+        out.append((pop.engine.results(), p))
+    (ra, pa), (rb, pb) = out
+    assert np.array_equal(ra["subvol_temperature"], rb["subvol_temperature"]) and np.array_equal(ra["subvol_N_p"], rb["subvol_N_p"])
+    assert np.array_equal(ra["subvol_heat_flux"], rb["subvol_heat_flux"])
+    for k in ("ids", "modes", "positions", "occupation", "n_timesteps", "collision_facets"):
+        assert np.array_equal(pa[k], pb[k], equal_nan=True), k
