@@ -241,7 +241,8 @@ def config_dict(a, n_per_gpu, where):
          (f"parameters_test geometry: box 5e3x1e3x1e3 A, T/T/R/R/P, eta {CASE.get('eta', 0)} A, 10 slice SVs, linear T (BASELINE configs[0] scaled up; diagnostic)")
     return {"workload": wl,
             "particles_per_gpu": int(n_per_gpu), "mode_table": f"synthetic {a.mesh}^3 x 6", "subvolumes": int(CASE.get("slices", 20)) if CASE["name"] == "c2" else 10,
-            "particle_order": "tiled modes (as initialised)" if getattr(a, "no_sort", False) else "sorted by mode at set-up",
+            "particle_order": "tiled modes (as initialised)" if getattr(a, "no_sort", False) else
+            "sorted by mode at set-up; timed in the freshly ordered state (the order erodes as slots are recycled: +13 % per step after 100 steps, profiles/README.md)",
             "l2_policy": "inputs larger than L2 (no flush)" if n_per_gpu * 44 > 2.6e8 else "state fits L2; L2 flushed between timed steps",
             "parallelism": f"particle shards x{a.gpus}, per-step all-reduce of the per-SV vectors ({getattr(a, 'exchange', '?')})" if a.gpus > 1 else "single GPU"}
 

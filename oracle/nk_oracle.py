@@ -26,7 +26,7 @@ normalised cumulative sum.
 from __future__ import annotations
 
 import copy
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 

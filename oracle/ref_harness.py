@@ -15,7 +15,6 @@ imports it: there the checker is ``oracle/nk_oracle.py`` plus the fixtures in ``
 """
 from __future__ import annotations
 
-import argparse
 import ast
 import importlib.abc
 import importlib.util
