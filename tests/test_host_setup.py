@@ -169,3 +169,26 @@ def test_geometry_accepts_wire_primitive(tmp_path):
         geo = Geometry(args)
     assert len(geo.res_facets) == 2 and len(geo.rough_facets) == geo.n_of_facets - 2
     assert np.isclose(np.ptp(geo.bounds[:, 2]), 2000.0)
+
+
+def test_command_line_surface_equals_the_reference():
+    """argument_parser.py is part of the drop-in boundary: every flag of the reference's parser exists here
+    with the same short name, default, nargs, type and choices -- checked against the reference's own parser object when
+    /root/reference is on this box."""
+    import importlib.util
+    path = "/root/reference/argument_parser.py"
+    if not os.path.isfile(path):
+        pytest.skip("/root/reference not present on this box")
+    spec = importlib.util.spec_from_file_location("ref_argument_parser", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    key = lambda a: [o for o in a.option_strings if o.startswith("--")][0]
+    theirs = {key(a): a for a in ref.initialise_parser(False)._actions if any(o.startswith("--") for o in a.option_strings)}
+    ours = {key(a): a for a in ap.initialise_parser(False)._actions if any(o.startswith("--") for o in a.option_strings)}
+    assert sorted(theirs) == sorted(ours)
+    for name, a in theirs.items():
+        b = ours[name]
+        assert sorted(a.option_strings) == sorted(b.option_strings), name
+        assert a.default == b.default and a.nargs == b.nargs, name
+        assert getattr(a.type, "__name__", a.type) == getattr(b.type, "__name__", b.type), name
+        assert (a.choices is None) == (b.choices is None) and (a.choices is None or sorted(a.choices) == sorted(b.choices)), name
