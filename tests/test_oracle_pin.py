@@ -115,3 +115,30 @@ def test_philox_known_answers():
     for c, k, want in kat:
         got = tuple(int(v) for v in philox4x32_10(*c, *k))
         assert got == want
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference not present on this box")
+@pytest.mark.parametrize("name", ["c1_mixed", "c2_crossplane", "c5_box_grid_radial"])
+def test_convergence_file_format_equals_the_reference(name, tmp_path):
+    """convergence.txt is an interface (Visualisation parses it by column position, Population.py:1841-1939): the header and
+    the rows written by nanokappa_b200's Population must be character-identical to the reference's for the same state.
+    The reference writes its file during construction; our writer is fed the reference's own geometry and values."""
+    import types
+    from nanokappa_b200.classes.Population import Population
+    ref_dir, our_dir = tmp_path / "ref", tmp_path / "ours"
+    ref_dir.mkdir(); our_dir.mkdir()
+    with contextlib.redirect_stdout(io.StringIO()):
+        args, geo, ph, pop = gen_golden.build_reference(gen_golden.CONFIGS[name][0], 5, results=str(ref_dir))
+    theirs = (ref_dir / "convergence.txt").read_text().splitlines()
+    stub = types.SimpleNamespace(results_folder_name=str(our_dir), n_of_subvols=pop.n_of_subvols, n_of_reservoirs=pop.n_of_reservoirs)
+    for k in ("current_timestep", "t", "total_energy", "res_energy_balance", "res_heat_flux", "N_p", "subvol_temperature",
+              "subvol_energy", "subvol_heat_flux", "subvol_N_p", "subvol_kappa", "kappa", "svcon_kappa"):
+        if hasattr(pop, k):
+            setattr(stub, k, getattr(pop, k))
+    Population.open_convergence(stub, geo)
+    Population.write_convergence(stub, geo)
+    ours = (our_dir / "convergence.txt").read_text().splitlines()
+    assert ours[0] == theirs[0], "header differs"
+    assert len(ours) == len(theirs) == 2
+    strip = lambda row: row.split(" ", 1)[1]           # drop the wall-clock token
+    assert strip(ours[1]) == strip(theirs[1]), "row format differs"
