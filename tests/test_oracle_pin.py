@@ -142,3 +142,25 @@ def test_convergence_file_format_equals_the_reference(name, tmp_path):
     assert len(ours) == len(theirs) == 2
     strip = lambda row: row.split(" ", 1)[1]           # drop the wall-clock token
     assert strip(ours[1]) == strip(theirs[1]), "row format differs"
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference not present on this box")
+def test_particle_dump_format_equals_the_reference(tmp_path):
+    """particle_data.txt is the --part_dist restart format (Population.py:2071-2091): same header lines (but the date) and
+    the same rows for the same particles."""
+    import types
+    from nanokappa_b200.classes.Population import Population
+    ref_dir, our_dir = tmp_path / "ref", tmp_path / "ours"
+    ref_dir.mkdir(); our_dir.mkdir()
+    with contextlib.redirect_stdout(io.StringIO()):
+        args, geo, ph, pop = gen_golden.build_reference(gen_golden.CONFIGS["c1_mixed"][0], 5, results=str(ref_dir))
+        pop.write_final_state(geo)
+    theirs = (ref_dir / "particle_data.txt").read_text().splitlines()
+    stub = types.SimpleNamespace(results_folder_name=str(our_dir), args=args, N_p=pop.N_p, current_timestep=0, view=object(),
+                                 _particles=lambda: dict(modes=np.asarray(pop.modes), positions=np.asarray(pop.positions),
+                                                         occupation=np.asarray(pop.occupation)))
+    Population.write_final_state(stub, geo)
+    ours = (our_dir / "particle_data.txt").read_text().splitlines()
+    assert len(ours) == len(theirs)
+    keep = lambda lines: [l for l in lines if "Date and time" not in l]
+    assert keep(ours) == keep(theirs)
