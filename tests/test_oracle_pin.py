@@ -164,3 +164,54 @@ def test_particle_dump_format_equals_the_reference(tmp_path):
     assert len(ours) == len(theirs)
     keep = lambda lines: [l for l in lines if "Date and time" not in l]
     assert keep(ours) == keep(theirs)
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference not present on this box")
+@pytest.mark.parametrize("name", ["c1_mixed", "c5_box_grid_radial"])
+def test_postprocessing_chain_equals_the_reference(name, tmp_path):
+    """The every-100-steps chain that feeds back into the run (Population.run_timestep :1729-1735): the reference is run for
+    201 steps with its own outputs; our Visualisation must parse ITS convergence.txt into the same arrays and rolling
+    statistics, and our update_residue / write_subvolume_state, fed those, must write the rows the reference wrote."""
+    import types
+    from nanokappa_b200.classes.Population import Population
+    from nanokappa_b200.classes.Visualisation import Visualisation
+    ref_dir, our_dir = tmp_path / "ref", tmp_path / "ours"
+    ref_dir.mkdir(); our_dir.mkdir()
+    text = gen_golden.CONFIGS[name][0].replace("--particles total 4000", "--particles total 1500").replace("--particles total 3000", "--particles total 1500")
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+        args, geo, ph, pop = gen_golden.build_reference(text, 5, results=str(ref_dir))
+        np.random.seed(3)
+        for _ in range(201):
+            pop.run_timestep(geo, ph)
+    rv = pop.view
+    with contextlib.redirect_stdout(io.StringIO()):
+        ours = Visualisation(args, geo, ph)
+        ours.read_convergence()
+    slice_type = geo.subvol_type == "slice"
+    for k in ("T", "N_p", "en_res", "phi_res", "sv_phi", "mean_T", "std_T", "mean_sv_phi", "std_sv_phi", "mean_en_res", "std_en_res") + \
+            (("sv_k", "k", "mean_sv_k", "std_sv_k") if slice_type else ("mean_con_k", "std_con_k", "mean_con_dT", "std_con_dT", "mean_con_phi", "std_con_phi")):
+        _eq(k, getattr(rv, k), getattr(ours, k))
+    # residue row of step 200 and the subvolume tables written at step 200
+    stub = types.SimpleNamespace(view=ours, n_of_subvols=pop.n_of_subvols, n_of_reservoirs=pop.n_of_reservoirs, slice_axis=getattr(pop, "slice_axis", 0),
+                                 results_folder_name=str(our_dir), conv_crit=pop.conv_crit, conv_count_min=pop.conv_count_min, conv_count=0,
+                                 finish_sim=False, args=args, subvol_volume=np.asarray(pop.subvol_volume))
+    Population.initialise_residue(stub, geo)
+    # the reference's residue at step 200 compares with the means of step 100: replay both checks
+    their_rows = (ref_dir / "residue.txt").read_text().splitlines()
+    full = (ref_dir / "convergence.txt").read_text().splitlines()
+    for upto in (11, 21):                               # rows of steps 0..100 and 0..200 (header + one row per 10 steps)
+        (our_dir / "convergence.txt").write_text("\n".join(full[:upto + 1]) + "\n")
+        ours.convergence_file = str(our_dir / "convergence.txt")
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+            ours.read_convergence()
+            Population.update_residue(stub, geo)
+        if upto == 11:
+            # run_timestep(200) dumps the state BEFORE it post-processes: the files left by the reference carry the rolling
+            # statistics of the step-100 check (Population.py:1729-1733), ours must too
+            Population.write_subvolume_state(stub, geo)
+    our_rows = (our_dir / "residue.txt").read_text().splitlines()
+    assert our_rows[-1] == their_rows[-1] and len(our_rows) == 2
+    keep = lambda p: [l for l in p.read_text().splitlines() if "Date and time" not in l]
+    assert keep(our_dir / "subvolumes.txt") == keep(ref_dir / "subvolumes.txt")
+    if not slice_type:
+        assert keep(our_dir / "subvol_connections.txt") == keep(ref_dir / "subvol_connections.txt")
