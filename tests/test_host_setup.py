@@ -192,3 +192,27 @@ def test_command_line_surface_equals_the_reference():
         assert a.default == b.default and a.nargs == b.nargs, name
         assert getattr(a.type, "__name__", a.type) == getattr(b.type, "__name__", b.type), name
         assert (a.choices is None) == (b.choices is None) and (a.choices is None or sorted(a.choices) == sorted(b.choices)), name
+
+
+@pytest.mark.parametrize("shape,dims", [("zigzag", "500 100 30 20 8 4"), ("corrugated", "300 100 60 10 5"), ("freewire", "100 300 60 200 80 100 9")])
+def test_wire_primitives_match_the_reference_geometry(shape, dims):
+    """The same --geometry / --dimensions through the reference's Geometry (when /root/reference is here) and ours: same
+    bounding box, same facets (count and areas), same boundary-condition assignment; the volume agrees to the accuracy of
+    the reference's own estimate (ours is the exact divergence-theorem value)."""
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("/root/reference not present on this box")
+    from nanokappa_b200.classes.Geometry import Geometry
+    text = gen_golden.PARAMS_C4.format(eta=3, n=100).replace("--geometry cylinder --dimensions 3000 600 10", f"--geometry {shape} --dimensions {dims}") \
+        .replace("--subvolumes voronoi 6", "--subvolumes slice 4 2")
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+        rg = rh.make_geometry(rh.parse_parameters_text(text, "/tmp/nk_prim_ref", overrides=dict(fig_plot=[], output=["screen"])))
+        args = ap.initialise_parser(False).parse_args(text.replace("kappa-m313131.hdf5", "synthetic:3").split())
+        args.results_folder = "/tmp/nk_prim_ours"
+        mg = Geometry(args)
+    assert np.allclose(rg.bounds, mg.bounds, atol=1e-9)
+    assert rg.n_of_facets == mg.n_of_facets
+    assert np.allclose(np.sort(rg.facets_area), np.sort(mg.facets_area), rtol=1e-9)
+    assert sorted(rg.bound_cond.tolist()) == sorted(mg.bound_cond.tolist()) and len(rg.res_facets) == len(mg.res_facets)
+    assert np.isclose(rg.volume, mg.volume, rtol=1e-4)
+    assert np.allclose(np.sort(rg.subvol_center[:, 2]), np.sort(mg.subvol_center[:, 2]), rtol=1e-9)
