@@ -216,3 +216,19 @@ def test_wire_primitives_match_the_reference_geometry(shape, dims):
     assert sorted(rg.bound_cond.tolist()) == sorted(mg.bound_cond.tolist()) and len(rg.res_facets) == len(mg.res_facets)
     assert np.isclose(rg.volume, mg.volume, rtol=1e-4)
     assert np.allclose(np.sort(rg.subvol_center[:, 2]), np.sort(mg.subvol_center[:, 2]), rtol=1e-9)
+
+
+def test_parameters_file_parses_like_the_reference(monkeypatch):
+    """`nanokappa.py -ff parameters_test.txt` (the file the reference ships): both parsers must produce the same namespace."""
+    import importlib.util
+    import sys
+    path = "/root/reference/argument_parser.py"
+    if not os.path.isfile(path):
+        pytest.skip("/root/reference not present on this box")
+    spec = importlib.util.spec_from_file_location("ref_argument_parser2", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    argv = ["nanokappa.py", "-ff", "/root/reference/parameters_test.txt"]
+    monkeypatch.setattr(sys, "argv", argv)
+    theirs, ours = vars(ref.read_args(False)), vars(ap.read_args(False, list(argv)))
+    assert theirs == ours
