@@ -275,37 +275,53 @@ class Geometry:
         return cover * self.volume
 
     def get_subvol_connections(self):
-        """Neighbour pairs (i < j).  Slices: i <-> i+1 (Geometry.py:968-975).  Otherwise the Voronoi
-        neighbours of the centres whose connecting segment stays inside the solid (the reference
-        prunes all pairs with a plane heuristic, Geometry.py:977-1052; both describe the Voronoi
-        adjacency of the centres)."""
+        """Neighbour pairs (i < j) of the subvolume centres (Geometry.py:961-1052).  Slices: i <-> i+1.  Otherwise the
+        reference's greedy pruning, restated: candidate pairs are those whose midpoint lies inside the solid and whose
+        connecting segment does not leave it; they are visited from the shortest to the longest, and a pair (i, j) is
+        dropped when its midpoint lies on or beyond the bisector plane of a connection (i, k) or (j, k) confirmed before it
+        (the farther centre is then hidden behind the nearer one).  The number and order of the connections is part of the
+        convergence.txt format, so the visiting order (NumPy's argsort of the distances, ties included) is kept."""
         print('Getting subvol connections...')
         S = self.n_of_subvols
+        c = self.subvol_center
         if self.subvol_type == 'slice' or S < 2:
             con = np.stack((np.arange(S - 1), np.arange(1, S)), axis=1) if S > 1 else np.zeros((0, 2), dtype=int)
         else:
-            pairs = set()
-            c = self.subvol_center
-            if S >= 5 and np.linalg.matrix_rank(c - c.mean(axis=0), tol=1e-9) == 3:
-                tri = Delaunay(c)
-                for simplex in tri.simplices:
-                    for a in range(4):
-                        for b in range(a + 1, 4):
-                            pairs.add((min(simplex[a], simplex[b]), max(simplex[a], simplex[b])))
-            else:
-                pairs = {(i, j) for i in range(S) for j in range(i + 1, S)}
-            pairs = np.array(sorted(pairs), dtype=int).reshape(-1, 2)
-            keep = np.ones(pairs.shape[0], dtype=bool)
+            mid = (c + np.expand_dims(c, 1)) / 2                  # mid[a, b]
+            nrm = c - np.expand_dims(c, 1)                        # nrm[a, b] = c[b] - c[a]
+            dist = np.linalg.norm(nrm, axis=-1)
+            ii, jj = np.triu_indices(S, k=1)                      # lexicographically ordered pairs i < j
+            pairs = np.stack((ii, jj), axis=1)
+            pairs = pairs[self.mesh.contains(mid[pairs[:, 0], pairs[:, 1], :])]
             if pairs.shape[0]:
-                mid = (c[pairs[:, 0]] + c[pairs[:, 1]]) / 2
-                keep &= self.mesh.contains(mid)
-                _, t, _ = Mesh.find_boundary(self.mesh, c[pairs[:, 0]], c[pairs[:, 1]] - c[pairs[:, 0]])
-                keep &= t > 1
-                # a pair is a Voronoi neighbour only if no third centre is closer to the midpoint
-                d_mid = np.linalg.norm(mid - c[pairs[:, 0]], axis=1)
-                nearest = cKDTree(c).query(mid, k=3)[0]
-                keep &= nearest[:, -1] >= d_mid * (1 - 1e-9)
-            con = pairs[keep]
+                _, t, _ = Mesh.find_boundary(self.mesh, c[pairs[:, 0], :], nrm[pairs[:, 0], pairs[:, 1], :])
+                pairs = pairs[t > 1, :]
+            n_p = pairs.shape[0]
+            confirmed = np.zeros(n_p, dtype=bool)
+            remove = np.zeros(n_p, dtype=bool)
+            order = np.argsort(dist[pairs[:, 0], pairs[:, 1]])
+            for idx in order:
+                i, j = pairs[idx]
+                for a in (i, j):                                   # connections of i, then (if still alive) of j
+                    if remove[idx]:
+                        break
+                    touching = np.nonzero(np.any(pairs == a, axis=1) & confirmed)[0]
+                    for row in touching:
+                        k = pairs[row, 0] if pairs[row, 1] == a else pairs[row, 1]
+                        if np.sum((mid[i, j, :] - mid[a, k, :]) * nrm[a, k, :]) >= 0:
+                            remove[idx] = True
+                if not remove[idx]:
+                    confirmed[idx] = True
+            con = pairs[~remove, :]
+            used = np.unique(con)
+            if used.shape[0] != S and used.shape[0] > 0:           # upstream keeps only the connected subvolumes (:1035-1046)
+                relabel = -np.ones(S, dtype=int)
+                relabel[used] = np.arange(used.shape[0])
+                self.subvol_center = c[used, :]
+                if hasattr(self, 'subvol_volume') and np.size(self.subvol_volume) == S:
+                    self.subvol_volume = np.asarray(self.subvol_volume)[used]
+                self.n_of_subvols = used.shape[0]
+                con = relabel[con]
         self.subvol_connections = con
         self.n_of_subvol_con = con.shape[0]
         self.subvol_con_vectors = self.subvol_center[con[:, 1], :] - self.subvol_center[con[:, 0], :] if con.shape[0] else np.zeros((0, 3))

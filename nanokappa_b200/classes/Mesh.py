@@ -253,9 +253,14 @@ class Mesh:
         return f, d, xc
 
     def contains(self, x):
-        """Point-in-solid by crossing parity along +x (with a generic direction to dodge edges)."""
+        """Point-in-solid by crossing parity.  A ray that grazes an edge shared by two triangles is counted twice (or not at
+        all), and "generic" directions with simple ratios do meet edges of meshes with simple aspect ratios (a (3, 2, 1) ray from
+        the centre line of a 2:1 face runs along its diagonal), so three unrelated directions vote."""
         x = np.asarray(x, dtype=float).reshape(-1, 3)
-        d = np.array([0.8017837257372732, 0.5345224838248488, 0.2672612419124244])   # generic: misses edges
+        dirs = np.array([[0.6827316519, 0.5341127043, 0.4985163227],
+                         [-0.3711942835, 0.8260437511, 0.4241559872],
+                         [0.2903178467, -0.4478291235, 0.8456771093]])
+        dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
         out = np.zeros(x.shape[0], dtype=bool)
         inb = np.nonzero(np.all(x >= self.bounds[0] - self.tol, axis=1) & np.all(x <= self.bounds[1] + self.tol, axis=1))[0]
         keep = np.ones(self.n_of_faces, dtype=bool)
@@ -264,18 +269,21 @@ class Mesh:
         n, k = self.face_normals[keep], self.face_k[keep]
         inv = np.linalg.inv(self.face_basis_matrix[keep])                      # (F,3,3)
         org = self.face_origins[keep]
-        den = n @ d
         chunk = max(1, int(2e6 // max(1, n.shape[0])))
         for s in range(0, inb.shape[0], chunk):
             idx = inb[s:s + chunk]
             p = x[idx]
-            with np.errstate(divide='ignore', invalid='ignore'):
-                t = -(p @ n.T + k) / den                                          # (P,F)
-            c = p[:, None, :] + t[..., None] * d - org[None]
-            bar = np.einsum('fij,pfj->pfi', inv, c)
-            a, b = bar[..., 0], bar[..., 1]
-            hit = np.isfinite(t) & (t > self.tol) & (a >= 0) & (b >= 0) & (a + b <= 1)
-            out[idx] = (hit.sum(axis=1) % 2) == 1
+            votes = np.zeros(idx.shape[0], dtype=int)
+            for d in dirs:
+                den = n @ d
+                with np.errstate(divide='ignore', invalid='ignore'):
+                    t = -(p @ n.T + k) / den                                      # (P,F)
+                c = p[:, None, :] + t[..., None] * d - org[None]
+                bar = np.einsum('fij,pfj->pfi', inv, c)
+                a, b = bar[..., 0], bar[..., 1]
+                hit = np.isfinite(t) & (t > self.tol) & (a >= 0) & (b >= 0) & (a + b <= 1)
+                votes += (hit.sum(axis=1) % 2) == 1
+            out[idx] = votes >= 2
         return out
 
     contains_naive = contains

@@ -232,3 +232,27 @@ def test_parameters_file_parses_like_the_reference(monkeypatch):
     monkeypatch.setattr(sys, "argv", argv)
     theirs, ours = vars(ref.read_args(False)), vars(ap.read_args(False, list(argv)))
     assert theirs == ours
+
+
+@pytest.mark.parametrize("subvols", ["grid 3 2 1", "grid 2 2 2", "voronoi 9"])
+def test_subvolume_connections_equal_the_reference(subvols):
+    """Geometry.get_subvol_connections (Geometry.py:961-1052): the list of connected subvolume pairs fixes the columns of
+    convergence.txt and the per-connection kappa; for the reference's own centres our restatement of its greedy pruning
+    must return the same pairs in the same order."""
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("/root/reference not present on this box")
+    from nanokappa_b200.classes.Geometry import Geometry
+    text = gen_golden.PARAMS_C5.format(eta=2, n=100).replace("--subvolumes grid 3 2 1", "--subvolumes " + subvols)
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+        np.random.seed(5)
+        rg = rh.make_geometry(rh.parse_parameters_text(text, "/tmp/nk_con_ref", overrides=dict(fig_plot=[], output=["screen"])))
+        args = ap.initialise_parser(False).parse_args(text.replace("kappa-m313131.hdf5", "synthetic:3").split())
+        args.results_folder = "/tmp/nk_con_ours"
+        mg = Geometry(args)
+        if "voronoi" in subvols:                       # random centres: give ours the reference's, then connect them
+            mg.subvol_center = np.array(rg.subvol_center); mg.n_of_subvols = rg.n_of_subvols
+            mg.get_subvol_connections()
+    assert np.array_equal(np.asarray(rg.subvol_center), np.asarray(mg.subvol_center))
+    assert np.array_equal(np.asarray(rg.subvol_connections), np.asarray(mg.subvol_connections))
+    assert np.array_equal(np.asarray(rg.subvol_con_vectors), np.asarray(mg.subvol_con_vectors))
