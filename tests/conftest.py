@@ -10,7 +10,7 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 # keep the Monte-Carlo set-up loops (voronoi Lloyd relaxation, subvolume volumes) short in the test-suite
 os.environ.setdefault("NK_VORONOI_MAX_SAMPLES", "20000")
-os.environ.setdefault("NK_VOLUME_MAX_SAMPLES", "200000")
+os.environ.setdefault("NK_VOLUME_MAX_SAMPLES", "50000")
 
 
 def pytest_configure(config):
