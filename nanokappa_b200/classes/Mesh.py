@@ -273,17 +273,21 @@ class Mesh:
         for s in range(0, inb.shape[0], chunk):
             idx = inb[s:s + chunk]
             p = x[idx]
-            votes = np.zeros(idx.shape[0], dtype=int)
-            for d in dirs:
+            def parity(q, d):
                 den = n @ d
                 with np.errstate(divide='ignore', invalid='ignore'):
-                    t = -(p @ n.T + k) / den                                      # (P,F)
-                c = p[:, None, :] + t[..., None] * d - org[None]
+                    t = -(q @ n.T + k) / den                                      # (P,F)
+                c = q[:, None, :] + t[..., None] * d - org[None]
                 bar = np.einsum('fij,pfj->pfi', inv, c)
                 a, b = bar[..., 0], bar[..., 1]
                 hit = np.isfinite(t) & (t > self.tol) & (a >= 0) & (b >= 0) & (a + b <= 1)
-                votes += (hit.sum(axis=1) % 2) == 1
-            out[idx] = votes >= 2
+                return (hit.sum(axis=1) % 2) == 1
+            first, second = parity(p, dirs[0]), parity(p, dirs[1])
+            res = first & second
+            tie = np.nonzero(first != second)[0]                                   # a grazed edge: the third ray decides
+            if tie.shape[0]:
+                res[tie] = parity(p[tie], dirs[2])
+            out[idx] = res
         return out
 
     contains_naive = contains
