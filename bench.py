@@ -242,7 +242,7 @@ def reference_arm(a):
     if rank != 0:
         return
     n = int(a.cpu_particles)
-    procs = max(1, min(int(a.ref_procs) if a.ref_procs else (os.cpu_count() or 1), 64))
+    procs = max(1, min(int(a.ref_procs) if a.ref_procs else (os.cpu_count() or 1), 32))
     single, dt1, _ = cpu_run(n, a.steps, a.warmup, a.mesh)
     if procs > 1:
         value, dt, updates = cpu_run_all_cores(n, a.steps, a.warmup, a.mesh, procs)
