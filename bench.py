@@ -68,6 +68,8 @@ def workload(n_total, mesh):
         text = PARAMS_C1.format(mat="/nonexistent_material_folder/", mesh=mesh, n=int(n_total), eta=CASE.get("eta", 0))
     else:
         text = PARAMS.format(mat="/nonexistent_material_folder/", mesh=mesh, n=int(n_total)).replace("--subvolumes slice 20 0", "--subvolumes slice {} 0".format(int(CASE.get("slices", 20))))
+    if CASE.get("material", "si") == "ge":             # Ge cell of test_material/Ge/POSCAR (configs[2]); synthetic table on that lattice
+        text = text.replace("synthetic:{}".format(mesh), "synthetic:{}:ge".format(mesh))
     args = ap.initialise_parser(False).parse_args(text.split())
     args.results_folder = "/tmp"
     with contextlib.redirect_stdout(io.StringIO()):
@@ -237,11 +239,28 @@ def cpu_run_all_cores(n_particles, steps, warmup, mesh, procs):
     return updates / slowest, slowest, updates
 
 
+PORT_CALIBRATION = os.path.join(ROOT, "profiles", "r2_port_calibration.json")
+
+
+def port_calibration_note():
+    """Port-vs-unmodified-reference factor measured in the build container (tests/run_port_calibration.py)."""
+    try:
+        c = json.load(open(PORT_CALIBRATION))
+        return "port / unmodified reference on the same inputs (build container, {} particles x {} steps): {:.3f}x".format(
+            c["particles"], c["steps"], c["port_over_reference"])
+    except Exception:
+        return "port calibration file missing"
+
+
 def reference_arm(a):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    n = int(a.cpu_particles)
+    # the CPU arm must not touch the GPU or the CUDA library: E(T) table on the host (cached on disk for the replicas)
+    os.environ["NK_ENERGY_TABLE"] = "host"
+    os.environ.setdefault("NK_TABLE_CACHE", "/tmp/nk_table_cache")
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    n = int(a.ref_particles)
     procs = max(1, min(int(a.ref_procs) if a.ref_procs else (os.cpu_count() or 1), 32))
     single, dt1, _ = cpu_run(n, a.steps, a.warmup, a.mesh)
     if procs > 1:
@@ -257,7 +276,7 @@ def reference_arm(a):
                          "sample": f"{procs} independent replicas (one process per host core; the reference itself is single-threaded) of "
                                    f"{n} particles x {a.steps} timesteps of the same thin-film case (oracle/nk_oracle.py + SciPy cKDTree / "
                                    f"RegularGridInterpolator + gc.collect as the reference calls them); one replica alone: {single:.3e} updates/s; "
-                                   f"host has {os.cpu_count()} cores"},
+                                   f"host has {os.cpu_count()} cores; {port_calibration_note()}"},
         "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -268,9 +287,9 @@ def config_dict(a, n_per_gpu, where):
           "(BASELINE configs[1] geometry at configs[4] scale)") if CASE["name"] == "c2" else \
          (f"parameters_test geometry: box 5e3x1e3x1e3 A, T/T/R/R/P, eta {CASE.get('eta', 0)} A, 10 slice SVs, linear T (BASELINE configs[0] scaled up; diagnostic)")
     return {"workload": wl,
-            "particles_per_gpu": int(n_per_gpu), "mode_table": f"synthetic {a.mesh}^3 x 6", "subvolumes": int(CASE.get("slices", 20)) if CASE["name"] == "c2" else 10,
+            "particles_per_gpu": int(n_per_gpu), "mode_table": f"synthetic {a.mesh}^3 x 6 on the {CASE.get('material', 'si').capitalize()} cell", "subvolumes": int(CASE.get("slices", 20)) if CASE["name"] == "c2" else 10,
             "particle_order": "tiled modes (as initialised)" if getattr(a, "no_sort", False) else
-            "sorted by mode at set-up; timed in the freshly ordered state (the order erodes as slots are recycled: +13 % per step after 100 steps, profiles/README.md)",
+            "ordered by mode at set-up (nk_sort_by_mode) with per-mode slot pools, so emitted particles land among their own mode; `value` = first steps after set-up, `sustained` = long run incl. re-sorts",
             "l2_policy": "inputs larger than L2 (no flush)" if n_per_gpu * 44 > 2.6e8 else "state fits L2; L2 flushed between timed steps",
             "parallelism": f"particle shards x{a.gpus}, per-step all-reduce of the per-SV vectors ({getattr(a, 'exchange', '?')})" if a.gpus > 1 else "single GPU"}
 
@@ -447,6 +466,9 @@ def gpu_arm(a):
                 "avg_launch_ms": step_ms,
                 "kernel_share_of_step": {k: v / max(sum(prof.values()), 1e-12) for k, v in prof.items()}}
 
+    # ---- sustained: a long run with the maintenance a long run needs (re-sorts), timed as a whole
+    sustained = sustained_run(a, eng, world, rank, local, one_step, barrier, peak) if a.sustained_steps > 0 else None
+
     # ---- end to end through host buffers (pinned): full particle state H2D, one timestep, state + per-SV results D2H
     e2e = e2e_run(a, eng, n, world, rank, one_step, dev, fused)
 
@@ -464,7 +486,7 @@ def gpu_arm(a):
             cpu = {"value": cpu_val, "unit": "updates/s", "cores": 1, "kind": "port",
                    "sample": f"{int(a.cpu_particles)} particles x {a.cpu_steps} timesteps of the same case, {cpu_dt:.1f} s "
                              f"(oracle port with the SciPy calls + gc.collect the reference makes; single-threaded like the reference; "
-                             f"host has {os.cpu_count()} cores)"}
+                             f"host has {os.cpu_count()} cores; {port_calibration_note()})"}
         line = {
             "metric": "particle-timestep updates/s", "value": value, "unit": "updates/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -472,7 +494,7 @@ def gpu_arm(a):
             "clocks": clocks, "gpu_launches": int((2 + (1 if prof.get("k_finalize", 0.0) > 0 else 0)) * a.steps),
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                     "timesteps_per_call": 1, "calls": e2e["calls"], "api": e2e["api"], "numa_node_rank0": numa},
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "sustained": sustained,
             "particles_alive": int(n_alive1),
         }
         if world == 1 and CASE["name"] == "c2" and not a.no_cpu and n >= 10 ** 7:
@@ -483,6 +505,54 @@ def gpu_arm(a):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def sustained_run(a, eng, world, rank, local, one_step, barrier, peak):
+    """`--sustained-steps` consecutive timesteps (default 1000, >= 2 s at 1e8 particles) INCLUDING the maintenance pass a long
+    run performs (nk_sort_by_mode every NK_RESORT_EVERY = 500 steps, as Population.run_timestep does), timed as one region with
+    CUDA events and its own clock record.  This is the number a 10 000-iteration run lives at; `value` above is the first
+    `--steps` steps after set-up."""
+    import torch
+    import torch.distributed as dist
+    steps = int(a.sustained_steps)
+    every = int(os.environ.get("NK_RESORT_EVERY", 500))
+    sampler = ClockSampler(local)
+    n0 = eng.results()["N_p"]
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps // 100 + 2)]
+    if rank == 0:
+        sampler.start()
+    eng.profile_begin()
+    barrier()
+    marks[0].record()
+    resorts, sort_s = 0, 0.0
+    for k in range(steps):
+        if every > 0 and k > 0 and k % every == 0:
+            t0 = time.perf_counter()
+            eng.sort_by_mode()
+            eng.synchronize()
+            sort_s += time.perf_counter() - t0
+            resorts += 1
+        one_step()
+        if (k + 1) % 100 == 0:
+            marks[(k + 1) // 100].record()
+    last = torch.cuda.Event(enable_timing=True)
+    last.record()
+    barrier()
+    ms = marks[0].elapsed_time(last)
+    prof, nprof = eng.profile_end()
+    clocks = sampler.stop() if rank == 0 else None
+    n1 = eng.results()["N_p"]
+    _, alive_local = eng.slot_count()
+    if world > 1:
+        tmax = torch.tensor([ms], device=eng.device, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    per100 = [marks[i].elapsed_time(marks[i + 1]) / 100.0 for i in range(steps // 100)]
+    kstep_ms = prof["k_step"] / max(nprof, 1)
+    return {"value": 0.5 * (n0 + n1) * steps / (ms * 1e-3), "unit": "updates/s", "steps": steps, "ms_per_step": ms / steps,
+            "resort_every": every, "resorts": resorts, "resort_ms_each": 1e3 * sort_s / max(resorts, 1),
+            "ms_per_step_by_100": per100, "kstep_avg_ms": kstep_ms,
+            "kstep_roofline_frac": BYTES_PER_UPDATE * alive_local / (kstep_ms * 1e-3) / 1e9 / peak, "clocks": clocks}
 
 
 def e2e_run(a, eng, n, world, rank, one_step, dev, fused=False):
@@ -557,7 +627,10 @@ def main():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--particles", type=float, default=1e8, help="particles per GPU")
     p.add_argument("--mesh", type=int, default=31, help="q-mesh of the synthetic mode table (31 -> 29791 x 6 modes)")
-    p.add_argument("--cpu-particles", type=float, default=2e5)
+    p.add_argument("--cpu-particles", type=float, default=2e5, help="bounded CPU sample of the cpu_baseline leg of the GPU arm")
+    p.add_argument("--ref-particles", type=float, default=1e6, help="--impl reference: particles per replica (SURVEY 8d: 1e6)")
+    p.add_argument("--sustained-steps", type=int, default=1000, help="steps of the sustained measurement (maintenance included); 0 = skip")
+    p.add_argument("--material", default="si", choices=["si", "ge"], help="lattice of the synthetic mode table (ge: configs[2])")
     p.add_argument("--cpu-steps", type=int, default=100)
     p.add_argument("--ref-procs", type=int, default=0, help="--impl reference: parallel replicas (0 = one per host core)")
     p.add_argument("--e2e-calls", type=int, default=3)
@@ -568,7 +641,7 @@ def main():
     p.add_argument("--eta", type=float, default=0.0, help="roughness of the R facets in --case c1")
     p.add_argument("--slices", type=int, default=20, help="slice subvolumes of --case c2 (20 = README case; 100 = the configs[2] layout, diagnostic)")
     a = p.parse_args()
-    CASE["name"] = a.case; CASE["eta"] = a.eta; CASE["slices"] = a.slices
+    CASE["name"] = a.case; CASE["eta"] = a.eta; CASE["slices"] = a.slices; CASE["material"] = a.material
     if a.impl == "reference":
         reference_arm(a)
     else:

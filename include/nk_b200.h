@@ -132,14 +132,23 @@ int nk_bind_particles(nk_ctx* ctx, int64_t capacity,
                       double* px, double* py, double* pz, double* tc, double* occ,
                       int32_t* mode, int32_t* omode, int32_t* cfacet,
                       double* cx, double* cy, double* cz, int64_t* pid);
-int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots);     /* slots [0, n_slots) are in use or free-listed */
+/* Slots [0, n_slots) are in use or free (mode = -1).  Runs a census: counts the live particles and puts every free
+ * slot of the range on the free-slot ring, so a caller that hands over arrays with holes (np.delete never ran) gets them
+ * recycled by the emission.  Forgets the mode regions of nk_sort_by_mode. */
+int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots);
 int nk_get_slot_count(nk_ctx* ctx, int64_t* n_slots, int64_t* n_alive);
-/* Optional, after the caller has ordered the particle arrays by mode (a set-up / maintenance choice that makes the mode-table
- * gathers of neighbouring particles coalesce): first_slot_of_mode (n_modes, host) = index of the first slot holding each flat
- * mode (insertion point for absent modes).  With NK_FREE_BUCKETS=1 emitted particles are then placed in free slots next to
- * their own mode (experimental: it did not slow the erosion of the order measurably, profiles/README.md); by default the map
- * is recorded and all free slots share one ring.  NULL forgets the map; nk_set_slot_count forgets it too. */
-int nk_set_mode_slots(nk_ctx* ctx, const int64_t* first_slot_of_mode);
+/* Maintenance pass between timesteps (replaces Population.delete_particles' compaction, Population.py:832-850, which the
+ * reference runs on every step): counting sort of the live particles by flat mode into a second set of arrays ("back
+ * buffers", same capacity and alignment as nk_bind_particles), one fused pass over all twelve fields.  On return the back
+ * buffers ARE the bound particle arrays and the previous ones are free for the next call.  Why by mode: the streaming
+ * kernel's mode-table gathers of neighbouring particles then hit one cache line.  With pool_frac > 0 or pool_fixed > 0
+ * every mode region gets pool_fixed + ceil(pool_frac * count) spare slots and its own free-slot ring: an emitted particle
+ * takes a slot inside the region of its own mode, so the order survives emission and absorption (ignored when the
+ * geometry has rough facets -- particles change mode in place there -- or when the spare slots do not fit the capacity).
+ * Results are unchanged by the pass (sums are order independent, identity is `pid`). */
+int nk_sort_by_mode(nk_ctx* ctx, double* px, double* py, double* pz, double* tc, double* occ,
+                    int32_t* mode, int32_t* omode, int32_t* cfacet, double* cx, double* cy, double* cz, int64_t* pid,
+                    double pool_frac, int pool_fixed, int64_t* n_slots_out, int64_t* n_alive_out);
 int nk_set_sv_temperature(nk_ctx* ctx, const double* T_sv_host);   /* Population.subvol_temperature */
 int nk_get_sv_temperature(nk_ctx* ctx, double* T_sv_host);
 int nk_set_timestep(nk_ctx* ctx, int64_t current_timestep);
@@ -238,16 +247,30 @@ int nk_last_transfer_bytes(nk_ctx* ctx, int64_t* h2d, int64_t* d2h);
  * 0 streaming kernel first block in, 1 last block out, 2 rare-path kernel first block in, 3 last item done,
  * 4 closing block enters the finalize, 5 leaves it; 6-7 unused. */
 int nk_debug_trace(nk_ctx* ctx, uint64_t* out8);
+/* Which kernels the last step used: 0 direct streaming kernel, 4 per-(mode, subvolume) table variant; + 8 when the rare path
+ * ran with block-cooperative triangle tiles (meshes beyond 128 triangles). */
+int nk_last_step_variant(nk_ctx* ctx);
 
 /* ---- multi-GPU ------------------------------------------------------------------------------------ */
 
-/* Particle shards: each rank owns a block of particles and a mode-range of every reservoir's
- * emission table; the only exchange is the per-step sum of the per-SV / per-reservoir accumulators.
+/* Particle shards: each rank owns a block of particles; every rank advances the whole reservoir table and the copies an
+ * entry emits are dealt round-robin over the ranks (copy k of an entry that has emitted `fire` particles so far belongs to
+ * rank (fire + k + mode) % world), so each rank injects 1/world of every mode and the union over ranks is exactly the
+ * single-GPU emission; the only exchange is the per-step sum of the per-SV / per-reservoir accumulators.
  * nk_acc_buffer exposes that vector (device pointer + length in doubles) so the host layer can run
  * ncclAllReduce on it between the two halves of a step (nk_step_local / nk_step_finalize), or
  * register peer buffers for the fused one-shot exchange (nk_comm_*). */
 int nk_set_rank(nk_ctx* ctx, int rank, int world);
 int nk_acc_buffer(nk_ctx* ctx, double** dev_ptr, int64_t* n_doubles);
+/* Run state that is neither a table nor a particle, for checkpoints that continue bit-exactly without rebuilding the
+ * tables: res_counter (R, Q*J) f64; res_fire (R, Q*J) u8 emission deal counters; res_acc (4R) energy-balance / flux
+ * accumulators of the current convergence window (Population.res_energy_balance / res_heat_flux between two
+ * convergence rows); n_leaving (R) f64 Population.N_leaving of the previous step (feeds one_to_one); results
+ * (nk_results_len doubles) the block behind nk_get_results.  Host pointers; NULL skips a field. */
+int nk_results_len(nk_ctx* ctx);
+int nk_get_run_state(nk_ctx* ctx, double* res_counter, uint8_t* res_fire, double* res_acc, double* n_leaving, double* results);
+int nk_set_run_state(nk_ctx* ctx, const double* res_counter, const uint8_t* res_fire, const double* res_acc,
+                     const double* n_leaving, const double* results);
 int nk_step_local(nk_ctx* ctx);      /* kernels of one step up to the accumulators */
 int nk_step_finalize(nk_ctx* ctx);   /* accumulators -> T_sv, results; closes the step */
 /* Fused exchange over NVLink peer memory (replaces the all-reduce above): every rank exports its mailbox as a

@@ -42,7 +42,10 @@ SIGNATURES = {
     "nk_bind_particles": (C.c_int, [VP, C.c_int64] + [VP] * 12),
     "nk_set_slot_count": (C.c_int, [VP, C.c_int64]),
     "nk_get_slot_count": (C.c_int, [VP, c_lp, c_lp]),
-    "nk_set_mode_slots": (C.c_int, [VP, VP]),
+    "nk_sort_by_mode": (C.c_int, [VP] + [VP] * 12 + [C.c_double, C.c_int, c_lp, c_lp]),
+    "nk_results_len": (C.c_int, [VP]),
+    "nk_get_run_state": (C.c_int, [VP] + [VP] * 5),
+    "nk_set_run_state": (C.c_int, [VP] + [VP] * 5),
     "nk_set_sv_temperature": (C.c_int, [VP, VP]),
     "nk_get_sv_temperature": (C.c_int, [VP, VP]),
     "nk_set_timestep": (C.c_int, [VP, C.c_int64]),
@@ -64,6 +67,7 @@ SIGNATURES = {
     "nk_advance_host": (C.c_int, [VP, C.c_int64, C.c_int] + [VP] * 12 + [c_lp, VP, VP, VP]),
     "nk_last_transfer_bytes": (C.c_int, [VP, c_lp, c_lp]),
     "nk_debug_trace": (C.c_int, [VP, VP]),
+    "nk_last_step_variant": (C.c_int, [VP]),
     "nk_outside_slots": (C.c_int, [VP, C.c_double, VP, C.c_int64, c_lp]),
     "nk_set_rank": (C.c_int, [VP, C.c_int, C.c_int]),
     "nk_acc_buffer": (C.c_int, [VP, C.POINTER(VP), c_lp]),

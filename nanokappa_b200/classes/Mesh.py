@@ -60,7 +60,9 @@ class Mesh:
         b2 = v[f[:, 2]] - v[f[:, 0]]
         cr = np.cross(b1, b2)
         nrm = np.linalg.norm(cr, axis=1)
-        self.face_areas = nrm / 2
+        # the reference takes the 1-D norm face by face (Mesh.py:220: sqrt(dot(x, x)), BLAS), which differs from the
+        # axis-wise norm by one ulp for some triangles; areas feed the emission entry probabilities, so match it exactly
+        self.face_areas = np.array([np.linalg.norm(c) for c in cr]) / 2 if cr.shape[0] else nrm / 2
         self.area = float(self.face_areas.sum())
         self.face_centroid = v[f].mean(axis=1)
         self.face_normals = cr / nrm[:, None]

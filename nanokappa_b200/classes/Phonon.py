@@ -50,11 +50,19 @@ class Phonon(Constants):
     def load_table(self):
         name = self.args.hdf_file[self.mat_index]
         if name.startswith('synthetic:'):
-            lattice = None
+            # synthetic:N[:si|ge] -- analytic N^3 x 6 table on the lattice of the POSCAR when the file exists, else on the
+            # built-in Si cell, or on the Ge cell of test_material/Ge/POSCAR (frequencies scaled by 0.58: Ge's optical
+            # branches end near 9 THz)
+            parts = name.split(':')
+            lattice, f_scale = None, 1.0
             poscar = os.path.join(self.mat_folder, self.args.poscar_file[self.mat_index])
             if os.path.isfile(poscar):
                 lattice = synthetic.read_poscar_lattice(poscar)
-            return synthetic.make_table(int(name.split(':')[1]), lattice=lattice)
+            if len(parts) > 2 and parts[2].lower() == 'ge':
+                f_scale = 0.58
+                if lattice is None:
+                    lattice = synthetic.GE_LATTICE
+            return synthetic.make_table(int(parts[1]), lattice=lattice, f_scale=f_scale)
         path = name if os.path.isabs(name) else os.path.join(self.mat_folder, name)
         if path.endswith('.npz'):
             z = np.load(path)

@@ -250,6 +250,16 @@ class Population(PopulationSetup):
         occupation = None
         if self._can_init_on_device(geometry, key):
             return self._initialise_on_device(geometry, phonon)
+        if key.endswith('.npz'):
+            # binary checkpoint written by write_final_state above NK_TEXT_DUMP_MAX particles (the text restart file of the
+            # reference, particle_data.txt, is handled below): exact continuation, per rank in a sharded run
+            self.engine.allocate(1024)
+            self.load_checkpoint(key if self.world == 1 or self.rank == 0 else os.path.join(os.path.dirname(key), 'rank{}'.format(self.rank), os.path.basename(key)))
+            r = self._pull_results()
+            self.subvol_heat_flux = r['subvol_heat_flux']
+            self.calculate_kappa(geometry)
+            self.res_energy_balance = r['res_energy_balance']; self.res_heat_flux = r['res_heat_flux']
+            return
         if key in ('random_domain', 'center_domain'):
             positions = self.generate_positions(self.N_p, geometry.mesh, key.split('_')[0])
         elif key == 'random_subvol':
@@ -409,32 +419,34 @@ class Population(PopulationSetup):
 
     # ---- binary checkpoint: everything needed to continue bit-exactly ---------------------------
     def save_checkpoint(self, path):
-        """Live particles (f64 positions, unlike the 1e-3 A text dump), collision clocks, reservoir counters,
-        subvolume temperatures, step counter and the Philox seed.  `np.savez` container."""
-        p = self.engine.particles(flush=True)
-        r = self.engine.results()
-        np.savez(path, ids=p['ids'], positions=p['positions'], modes=p['modes'], omega_modes=p['omega_modes'],
-                 occupation=p['occupation'], n_timesteps=p['n_timesteps'], collision_facets=p['collision_facets'],
-                 collision_positions=p['collision_positions'], res_counter=self.engine.res_counter(),
-                 subvol_temperature=np.asarray(self.subvol_temperature if self.current_timestep == 0 else r['subvol_temperature']),
-                 current_timestep=self.current_timestep, seed=self.seed)
+        """Live particles (f64 positions, unlike the 1e-3 A text dump), collision clocks, reservoir counters and deal
+        counters, the reservoir balances accumulated since the last convergence row, N_leaving (feeds one_to_one), the
+        results block, subvolume temperatures, step counter and the Philox seed (``Engine.checkpoint``).  `np.savez`
+        container; in a sharded run every rank writes its own shard."""
+        z = self.engine.checkpoint()
+        if self.current_timestep == 0:
+            z['subvol_temperature'] = np.asarray(self.subvol_temperature, dtype=float)
+        z['current_timestep'] = np.int64(self.current_timestep)
+        z['world'] = np.int64(self.world); z['rank'] = np.int64(self.rank)
+        np.savez(path, **z)
 
     def load_checkpoint(self, path):
+        """Continue from ``save_checkpoint``.  The tables, the rank and the exchange buffers of the context are left
+        untouched (only particles and run state are replaced), so it is valid inside a sharded run too: every rank loads
+        the shard it wrote."""
         z = np.load(path)
-        J = self.engine.J
         if int(z['seed']) != self.seed:
             raise Exception('checkpoint was written with seed {} but this run uses {}'.format(int(z['seed']), self.seed))
-        self.engine.set_tables(self.tables, res_counter=z['res_counter'].reshape(self.res_counter.shape))
-        self.engine.allocate(int(z['ids'].shape[0] * float(os.environ.get('NK_CAPACITY_FACTOR', 1.25))) + 1024)
-        self.engine.load_particles(z['positions'], z['modes'][:, 0] * J + z['modes'][:, 1], z['occupation'], ids=z['ids'],
-                                   omodes=z['omega_modes'], n_timesteps=z['n_timesteps'], collision_facets=z['collision_facets'],
-                                   collision_positions=z['collision_positions'])
-        self.subvol_temperature = z['subvol_temperature']
-        self.engine.set_sv_temperature(self.subvol_temperature)
+        if 'world' in z.files and (int(z['world']) != self.world or int(z['rank']) != self.rank):
+            raise Exception('checkpoint belongs to rank {} of {} but this process is rank {} of {}'.format(
+                int(z['rank']), int(z['world']), self.rank, self.world))
+        self.engine.restore(z, capacity_factor=float(os.environ.get('NK_CAPACITY_FACTOR', 1.25)))
+        self.subvol_temperature = np.array(z['subvol_temperature'])
         self.current_timestep = int(z['current_timestep'])
         self.t = self.current_timestep * self.dt
-        self.engine.set_timestep(self.current_timestep)
         self._cache_key = None
+        if self.N_p >= float(os.environ.get('NK_RESORT_MIN', 1e6)):
+            self.engine.sort_by_mode()
 
     def assign_temperatures(self, subvol_id, geometry):
         """Initial subvolume temperatures for --temp_dist (Population.py:565-655)."""
@@ -576,10 +588,10 @@ class Population(PopulationSetup):
             for sv in range(self.n_of_subvols):
                 info += ' {:>7.3f}'.format(self.subvol_temperature[sv])
             print(info + ' ]')
-        # maintenance: emitted particles reuse the slots of absorbed ones, which erodes the order by mode made at set-up and
-        # with it the locality of the mode-table gathers (+13 % per step after 100 steps at 1e8 particles, profiles/README.md);
-        # re-sorting costs about 12 steps' worth, so large populations are re-ordered every NK_RESORT_EVERY steps (0 = never)
-        every = int(os.environ.get('NK_RESORT_EVERY', 250))
+        # maintenance: the per-mode slot pools keep emitted particles among their own mode, but a mode's pool runs dry or
+        # fills up as its population fluctuates; the counting sort (a few ms at 1e8 particles) re-centres the regions every
+        # NK_RESORT_EVERY steps (0 = never).  Results do not depend on it.
+        every = int(os.environ.get('NK_RESORT_EVERY', 500))
         if every > 0 and self.current_timestep > 0 and (self.current_timestep % every) == 0 and \
                 self.N_p >= float(os.environ.get('NK_RESORT_MIN', 1e6)):
             self.engine.sort_by_mode()
@@ -603,12 +615,67 @@ class Population(PopulationSetup):
         elif (self.current_timestep % 100) == 99:
             self._pull_results()
 
+    # ---- the reference's per-step methods as seams.  On the GPU drift, emission, boundary scattering and the
+    # per-subvolume sums are ONE fused pass over the particles (k_step + k_rare) and the lifetime scattering is deferred to
+    # the head of the next pass, so the sequence the reference's run_timestep spells out
+    #     drift -> fill_reservoirs -> add_reservoir_particles -> boundary_scattering -> refresh_temperatures -> lifetime_scattering
+    # maps to: drift() launches the fused step, the four methods in the middle find their work already done, and
+    # lifetime_scattering() applies the deferred relaxation and closes the step.  Called in that order they advance the
+    # population by exactly one timestep, like run_timestep (without its every-10 / every-100-step outputs).
     def drift(self):
-        raise Exception('drift() is fused into the GPU timestep; call run_timestep().')
+        """Population.drift (Population.py:790-795) -- opens a fused timestep on the device."""
+        if getattr(self, '_seam_open', False):
+            raise Exception('drift() was already called for this timestep; finish it with lifetime_scattering().')
+        if self.sharded is not None:
+            self.sharded.step(1)
+        else:
+            self.engine.step(1)
+        self._seam_open = True
+
+    def _seam_done(self, name):
+        if not getattr(self, '_seam_open', False):
+            raise Exception(name + '() is part of the fused GPU timestep: call drift() first (or run_timestep()).')
+
+    def fill_reservoirs(self, geometry, phonon):
+        """Population.fill_reservoirs (Population.py:356-489): done by the emission scan of the fused step."""
+        self._seam_done('fill_reservoirs')
+
+    def add_reservoir_particles(self, geometry, phonon):
+        """Population.add_reservoir_particles (Population.py:525-552): done by the rare-path kernel of the fused step."""
+        self._seam_done('add_reservoir_particles')
+
+    def boundary_scattering(self, geometry, phonon):
+        """Population.boundary_scattering (Population.py:1546-1683): done by the rare-path kernel of the fused step."""
+        self._seam_done('boundary_scattering')
+
+    def lifetime_scattering(self, phonon):
+        """Population.lifetime_scattering (Population.py:1701-1710): applies the deferred relaxation (nk_flush_relaxation)
+        and closes the timestep opened by drift()."""
+        self._seam_done('lifetime_scattering')
+        self.engine.flush_relaxation()
+        self._seam_open = False
+        self.current_timestep += 1
+        self.t = self.current_timestep * self.dt
+        self._cache_key = None
+
+    def calculate_energy(self, geometry, phonon):
+        """Population.calculate_energy (Population.py:704-728): per-subvolume energy densities of the last step
+        (block-private bins of k_step, closed by the finalize)."""
+        self._pull_results()
+        return self.subvol_energy
+
+    def calculate_heat_flux(self, geometry, phonon):
+        """Population.calculate_heat_flux (Population.py:730-747): the device evaluates it on convergence steps."""
+        self.subvol_heat_flux = self.engine.results()['subvol_heat_flux']
+        return self.subvol_heat_flux
 
     def refresh_temperatures(self, geometry, phonon):
         """Recompute subvolume energies/temperatures from the current particles without moving them
-        (used by the --part_dist restart loop, Population.py:297-304)."""
+        (used by the --part_dist restart loop, Population.py:297-304).  Inside a drift() ... lifetime_scattering()
+        sequence the fused step has already done it: only the results are pulled."""
+        if getattr(self, '_seam_open', False):
+            self._pull_results()
+            return
         p = self.engine.particles(flush=False)
         om = phonon.omega.reshape(-1)[p['omega_modes']]
         sv = geometry.subvol_classifier.predict(p['positions'])

@@ -17,6 +17,15 @@ NK_DEVI double dot3(double ax, double ay, double az, double bx, double by, doubl
 }
 NK_DEVI double norm3(double x, double y, double z) { return sqrt(dot3(x, y, z, x, y, z)); }
 
+// Newton-refined reciprocal of a positive normal double (<= 2 ulp): MUFU.RCP64H + 4 DFMA, no branch
+__device__ __forceinline__ double nk_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 keyed by (particle id, step, stream); see oracle/philox.py for the contract
 // ------------------------------------------------------------------------------------------------
@@ -317,6 +326,10 @@ NK_DEVI void nk_ray_faces(const NkFace* faces, int F, double x, double y, double
         // t = -num/den can only reach the tolerance when num and den have opposite signs (0, inf and NaN quotients are
         // rejected below anyway): skip the IEEE division for the planes the ray moves away from -- half of a convex mesh
         if (!((num < 0.0 && den > 0.0) || (num > 0.0 && den < 0.0))) continue;
+        // conservative filter before the IEEE division: |num| * rcp(|den|) is within a few ulp of t, so a face whose
+        // approximate t exceeds the best one by more than 1e-12 relative can never satisfy t < tbest below.  Only
+        // skips work; every accepted face still goes through the exact arithmetic.
+        if (tbest < CUDART_INF && fabs(num) * nk_rcp(fabs(den)) > tbest * (1.0 + 1e-12)) continue;
         double t = -nk_div(num, den);
         if (!(t >= NK_TOL) || isinf(t)) continue;                 // also rejects NaN
         if (!(t < tbest)) continue;                               // cannot become the first minimum
@@ -349,8 +362,10 @@ struct NkParticle {
     int mode, omode;
     double omega, vx, vy, vz;
     int cf; double cx, cy, cz;
-    long long id;
+    long long id;                // < 0: not loaded yet (read from pid[slot] on first use)
+    long long slot;              // slot of an existing particle, -1 for a particle being emitted
     bool alive;
+    bool mode_changed, occ_changed;   // what a rough-wall event modified (write-back of the rare path)
 };
 
 // Boundary loop of one particle whose next collision lies inside the current step
@@ -365,88 +380,106 @@ struct NkGeo {
     const double* normal; const double* centroid;
 };
 
-__device__ __forceinline__ void nk_boundary_events(const NkP& P, const NkGeo& G, NkParticle& p, long long step, double* acc) {
-    const NkFace* faces = G.faces;
-    double done = 0.0;
-    double ts = p.tc;
-    unsigned int ev = 0;
+struct NkEvState {
+    double done;        // fraction of the step already simulated (calculated_ts)
+    double ts;          // time to the next collision in units of dt (n_timesteps being rebuilt)
+    unsigned int ev;    // rough-wall events so far in this step (Philox stream index)
+    int it;             // event counter (cap)
+};
+__device__ __forceinline__ void nk_event_begin(const NkParticle& p, NkEvState& st) { st.done = 0.0; st.ts = p.tc; st.ev = 0; st.it = 0; }
+
+// Advances the event loop of one particle until it either needs a new ray (returns true: origin p.x/y/z, direction p.v;
+// feed the answer to nk_event_ray_done and call again) or is finished (returns false: absorbed -> p.alive == false,
+// otherwise p.tc holds the new clock).
+__device__ __forceinline__ bool nk_event_advance(const NkP& P, const NkGeo& G, NkParticle& p, NkEvState& st, long long step, double* acc) {
     const double dt = P.dt;
-    for (int it = 0; it < 4096; ++it) {
-        int cfi = p.cf < 0 ? P.nf - 1 : p.cf;                    // bound_cond[-1] for escaped rays (:667, :1487)
-        int cond = G.bc[cfi];
-        double rem = nk_sub(1.0, done);
-        if (rem > ts) {
-            if (cond == NK_BC_T || cond == NK_BC_F) {
-                // I. absorbed by a reservoir (:1565-1608)
-                int r = G.res[cfi];
-                if (r >= 0) {
-                    double e = nk_mul(nk_mul(P.hbar, p.omega), nk_sub(p.occ, nk_bose(P, P.res_T[r], p.omega)));
-                    const double* n = G.normal + 3 * cfi;
-                    double vn = dot3(p.vx, p.vy, p.vz, n[0], n[1], n[2]);
-                    NK_RACC_N(P, acc, NK_ACC_NLEAVE(P.S, P.R) + r);
-                    NK_RACC_E(P, acc, NK_ACC_EBAL(P.S, P.R) + r, -e);
-                    NK_RACC_F(P, acc, NK_ACC_RFLUX(P.S, P.R) + 3 * r + 0, nk_div(nk_mul(e, p.vx), vn));
-                    NK_RACC_F(P, acc, NK_ACC_RFLUX(P.S, P.R) + 3 * r + 1, nk_div(nk_mul(e, p.vy), vn));
-                    NK_RACC_F(P, acc, NK_ACC_RFLUX(P.S, P.R) + 3 * r + 2, nk_div(nk_mul(e, p.vz), vn));
-                }
-                p.alive = false;
-                return;
+    if (st.it++ >= 4096) { atomicOr(&P.dyn->error, NK_ERR_EVENTS); p.tc = st.ts; return false; }
+    int cfi = p.cf < 0 ? P.nf - 1 : p.cf;                    // bound_cond[-1] for escaped rays (:667, :1487)
+    int cond = G.bc[cfi];
+    double rem = nk_sub(1.0, st.done);
+    if (rem > st.ts) {
+        if (cond == NK_BC_T || cond == NK_BC_F) {
+            // I. absorbed by a reservoir (:1565-1608)
+            int r = G.res[cfi];
+            if (r >= 0) {
+                double e = nk_mul(nk_mul(P.hbar, p.omega), nk_sub(p.occ, nk_bose(P, P.res_T[r], p.omega)));
+                const double* n = G.normal + 3 * cfi;
+                double vn = dot3(p.vx, p.vy, p.vz, n[0], n[1], n[2]);
+                NK_RACC_N(P, acc, NK_ACC_NLEAVE(P.S, P.R) + r);
+                NK_RACC_E(P, acc, NK_ACC_EBAL(P.S, P.R) + r, -e);
+                NK_RACC_F(P, acc, NK_ACC_RFLUX(P.S, P.R) + 3 * r + 0, nk_div(nk_mul(e, p.vx), vn));
+                NK_RACC_F(P, acc, NK_ACC_RFLUX(P.S, P.R) + 3 * r + 1, nk_div(nk_mul(e, p.vy), vn));
+                NK_RACC_F(P, acc, NK_ACC_RFLUX(P.S, P.R) + 3 * r + 2, nk_div(nk_mul(e, p.vz), vn));
             }
-            // start of the path segment that ends at the collision point (:1472-1474, :1504-1508)
-            double qx = p.x, qy = p.y, qz = p.z;
-            if (done == 0.0) { qx = nk_sub(qx, nk_mul(p.vx, dt)); qy = nk_sub(qy, nk_mul(p.vy, dt)); qz = nk_sub(qz, nk_mul(p.vz, dt)); }
-            double dist = norm3(nk_sub(p.cx, qx), nk_sub(p.cy, qy), nk_sub(p.cz, qz));
-            if (cond == NK_BC_P) {
-                // II. periodic wrap (:1463-1489)
-                int g = p.cf >= 0 ? G.partner[p.cf] : -1;
-                if (g < 0) { P.dyn->error |= NK_ERR_EVENTS; break; }
-                const double* cg = G.centroid + 3 * g; const double* ch = G.centroid + 3 * p.cf;
-                double nx = nk_add(p.cx, nk_sub(cg[0], ch[0])), ny = nk_add(p.cy, nk_sub(cg[1], ch[1])), nz = nk_add(p.cz, nk_sub(cg[2], ch[2]));
-                done = nk_add(done, nk_div(dist, norm3(nk_mul(p.vx, dt), nk_mul(p.vy, dt), nk_mul(p.vz, dt))));
-                p.x = nx; p.y = ny; p.z = nz;
-                double t;
-                nk_find_boundary_1(P, faces, nx, ny, nz, p.vx, p.vy, p.vz, p.cx, p.cy, p.cz, t, p.cf);
-                ts = nk_div(t, dt);
-            } else {
-                // III. rough facet: specular or diffuse (:1491-1544, :941-1015)
-                done = nk_add(done, nk_div(dist, nk_mul(norm3(p.vx, p.vy, p.vz), dt)));
-                p.x = p.cx; p.y = p.cy; p.z = p.cz;
-                int fr = G.rough[cfi];
-                double u_dice, u_pick;
-                nk_uniforms(P, p.id, step, NK_STREAM_ROUGH0 + ev, u_dice, u_pick);
-                ++ev;
-                size_t li = (size_t)fr * P.M + p.mode;
-                bool spec = P.true_spec[li] && (u_dice <= P.specularity[li]);
-                if (spec) {
-                    p.mode = P.spec_out[li];                         // omega and occupation are kept (:955-971)
-                } else {
-                    const double* rou = P.roulette + (size_t)fr * P.M;
-                    double target = nk_mul(u_pick, rou[P.M - 1]);
-                    int lo = 0, hi = P.M;                            // searchsorted left
-                    while (lo < hi) { int mid = (lo + hi) >> 1; if (rou[mid] < target) lo = mid + 1; else hi = mid; }
-                    p.mode = min(lo, P.M - 1);
-                    p.omode = p.mode;
-                    p.omega = P.mprop[p.mode].omega;
-                    double Tc = nk_particle_T(P, P.svc, P.sv_axis, P.sv_mid, P.T_sv, p.cx, p.cy, p.cz, -1);
-                    p.occ = nk_bose(P, Tc, p.omega);
-                }
-                NkMode m = P.mprop[p.mode];
-                p.vx = m.vx; p.vy = m.vy; p.vz = m.vz;
-                double t;
-                nk_find_boundary_1(P, faces, p.x, p.y, p.z, p.vx, p.vy, p.vz, p.cx, p.cy, p.cz, t, p.cf);
-                ts = nk_div(t, dt);
-            }
-            continue;
+            p.alive = false;
+            return false;
         }
-        // IV. no further collision in this step (:1670-1681).  rem == ts never terminates upstream;
-        // here it takes this branch.
-        p.x = nk_add(p.x, nk_mul(nk_mul(p.vx, dt), rem));
-        p.y = nk_add(p.y, nk_mul(nk_mul(p.vy, dt), rem));
-        p.z = nk_add(p.z, nk_mul(nk_mul(p.vz, dt), rem));
-        ts = nk_sub(ts, rem);
-        p.tc = ts;
-        return;
+        // start of the path segment that ends at the collision point (:1472-1474, :1504-1508)
+        double qx = p.x, qy = p.y, qz = p.z;
+        if (st.done == 0.0) { qx = nk_sub(qx, nk_mul(p.vx, dt)); qy = nk_sub(qy, nk_mul(p.vy, dt)); qz = nk_sub(qz, nk_mul(p.vz, dt)); }
+        double dist = norm3(nk_sub(p.cx, qx), nk_sub(p.cy, qy), nk_sub(p.cz, qz));
+        if (cond == NK_BC_P) {
+            // II. periodic wrap (:1463-1489)
+            int g = p.cf >= 0 ? G.partner[p.cf] : -1;
+            if (g < 0) { atomicOr(&P.dyn->error, NK_ERR_EVENTS); p.tc = st.ts; return false; }
+            const double* cg = G.centroid + 3 * g; const double* ch = G.centroid + 3 * p.cf;
+            double nx = nk_add(p.cx, nk_sub(cg[0], ch[0])), ny = nk_add(p.cy, nk_sub(cg[1], ch[1])), nz = nk_add(p.cz, nk_sub(cg[2], ch[2]));
+            st.done = nk_add(st.done, nk_div(dist, norm3(nk_mul(p.vx, dt), nk_mul(p.vy, dt), nk_mul(p.vz, dt))));
+            p.x = nx; p.y = ny; p.z = nz;
+        } else {
+            // III. rough facet: specular or diffuse (:1491-1544, :941-1015)
+            st.done = nk_add(st.done, nk_div(dist, nk_mul(norm3(p.vx, p.vy, p.vz), dt)));
+            p.x = p.cx; p.y = p.cy; p.z = p.cz;
+            int fr = G.rough[cfi];
+            double u_dice, u_pick;
+            if (p.id < 0) p.id = P.pid[p.slot];
+            nk_uniforms(P, p.id, step, NK_STREAM_ROUGH0 + st.ev, u_dice, u_pick);
+            ++st.ev;
+            size_t li = (size_t)fr * P.M + p.mode;
+            bool spec = P.true_spec[li] && (u_dice <= P.specularity[li]);
+            p.mode_changed = true;
+            if (spec) {
+                p.mode = P.spec_out[li];                         // omega and occupation are kept (:955-971)
+            } else {
+                const double* rou = P.roulette + (size_t)fr * P.M;
+                double target = nk_mul(u_pick, rou[P.M - 1]);
+                int lo = 0, hi = P.M;                            // searchsorted left
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (rou[mid] < target) lo = mid + 1; else hi = mid; }
+                p.mode = min(lo, P.M - 1);
+                p.omode = p.mode;
+                p.omega = P.mprop[p.mode].omega;
+                double Tc = nk_particle_T(P, P.svc, P.sv_axis, P.sv_mid, P.T_sv, p.cx, p.cy, p.cz, -1);
+                p.occ = nk_bose(P, Tc, p.omega);
+                p.occ_changed = true;
+            }
+            NkMode m = P.mprop[p.mode];
+            p.vx = m.vx; p.vy = m.vy; p.vz = m.vz;
+        }
+        return true;
     }
-    P.dyn->error |= NK_ERR_EVENTS;
-    p.tc = ts;
+    // IV. no further collision in this step (:1670-1681).  rem == ts never terminates upstream;
+    // here it takes this branch.
+    p.x = nk_add(p.x, nk_mul(nk_mul(p.vx, dt), rem));
+    p.y = nk_add(p.y, nk_mul(nk_mul(p.vy, dt), rem));
+    p.z = nk_add(p.z, nk_mul(nk_mul(p.vz, dt), rem));
+    st.ts = nk_sub(st.ts, rem);
+    p.tc = st.ts;
+    return false;
+}
+// answer of the ray query an event asked for: the next collision (find_boundary of the new ray, :1480, :1526-1532)
+__device__ __forceinline__ void nk_event_ray_done(const NkP& P, NkParticle& p, NkEvState& st, double t, int cf) {
+    p.cf = cf;
+    p.cx = nk_add(p.x, nk_mul(t, p.vx)); p.cy = nk_add(p.y, nk_mul(t, p.vy)); p.cz = nk_add(p.z, nk_mul(t, p.vz));   // inf*0 = NaN like NumPy
+    st.ts = nk_div(t, P.dt);
+}
+
+// the whole loop for one thread that sweeps the triangles by itself (small meshes staged in shared memory)
+__device__ __forceinline__ void nk_boundary_events(const NkP& P, const NkGeo& G, NkParticle& p, long long step, double* acc) {
+    NkEvState st;
+    nk_event_begin(p, st);
+    while (nk_event_advance(P, G, p, st, step, acc)) {
+        double tbest = CUDART_INF; int fbest = -1;
+        nk_ray_faces(G.faces, P.F, p.x, p.y, p.z, p.vx, p.vy, p.vz, tbest, fbest);
+        nk_event_ray_done(P, p, st, tbest, fbest);
+    }
 }

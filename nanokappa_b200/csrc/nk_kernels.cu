@@ -20,6 +20,7 @@
 //
 // nk_types.cuh    parameter block (NkP), device-resident step state (NkDyn), accumulator / result layouts
 // nk_device.cuh   exact-arithmetic helpers, Philox, table look-ups, classification, ray-triangle search, boundary events
+// nk_tiles.cuh    TMA-staged triangle tiles shared by the ray kernels
 // nk_ops.cuh ... nk_hostpipe.cuh   kernels, in dependency order
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -34,10 +35,11 @@
 #include "../../include/nk_b200.h"
 #include "nk_device.cuh"
 
+#include "nk_tiles.cuh"
 #include "nk_ops.cuh"
 #include "nk_stream.cuh"
-#include "nk_stream_variants.cuh"
 #include "nk_rare.cuh"
+#include "nk_sort.cuh"
 #include "nk_hostpipe.cuh"
 
 // =================================================================================================
@@ -57,7 +59,10 @@ struct nk_ctx {
     double hot_lo = 0, hot_hi = 0;
     int step_blocks = 0;
     int step_blocks_variant = -1;
-    int step_variant = 0;
+    bool force_tiled = false;      // NK_RARE_TILED=1: use the tiled rare-path kernel also for small meshes (tests)
+    bool rare_attr_set = false;
+    bool last_rare_tiled = false;
+    int* sort_count = nullptr; int* sort_cursor = nullptr; int* mode_first_dev = nullptr; long long* sort_totals = nullptr;
     bool use_tab = true;           // NK_STEP_TAB=0 disables the per-(mode, subvolume) table variant
     bool force_tab = false;        // NK_STEP_TAB=force: use it regardless of the particle count (tests)
     bool tab_dirty = true;         // T_sv changed since k_mode_tables last ran
@@ -72,7 +77,6 @@ struct nk_ctx {
     cudaEvent_t ev_cold = nullptr;
     bool sparse_cold = true;       // NK_HOST_SPARSE=0: upload the cold arrays densely
     bool l2_persist = false, l2_window_set = false;      // NK_L2_PERSIST=1 (experiment)
-    int* mode_bucket_dev = nullptr;    // storage of NkP::mode_bucket
     bool use_pipeline = true;      // NK_HOST_PIPELINE=0 disables it
     long long xfer_h2d = 0, xfer_d2h = 0;   // bytes of the last nk_advance_host call
     void* comm_block = nullptr;    // flags + mailboxes of the fused exchange
@@ -157,7 +161,7 @@ int nk_create(int device, nk_ctx** out) {
     }
     if (const char* e = getenv("NK_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));   // experiment: 32 / 64 / 128
     if (const char* e = getenv("NK_STEP_TAB")) { ctx->use_tab = strcmp(e, "0") != 0; ctx->force_tab = !strcmp(e, "force"); }
-    if (const char* e = getenv("NK_STEP_IMPL")) ctx->step_variant = !strcmp(e, "tma") ? 1 : (!strcmp(e, "ldg1") ? 2 : (!strcmp(e, "pf") ? 3 : 0));
+    ctx->force_tiled = getenv_is_one("NK_RARE_TILED");
     NkDyn z; memset(&z, 0, sizeof(z));
     ctx->P.dyn = nk_upload<NkDyn>(ctx, &z, 1);
     *out = ctx;
@@ -249,6 +253,7 @@ int nk_set_subvols(nk_ctx* ctx, int S, const double* centres, const double* volu
     cudaSetDevice(ctx->device);
     NkP& P = ctx->P;
     if (S < 1) { ctx->err = "n_subvols must be >= 1"; return -1; }
+    if (S > 1400) { ctx->err = "n_subvols above 1400 is not supported: the per-block subvolume bins no longer fit the 227 KB of shared memory"; return -1; }
     if (interp == NK_INTERP_LINEAR && !is_slice) { ctx->err = "linear temperature interpolation needs slice subvolumes; the reference falls back to NK_INTERP_RADIAL there"; return -1; }
     if (interp == NK_INTERP_RADIAL && is_slice) { ctx->err = "radial temperature interpolation on slice subvolumes is singular upstream (collinear centres)"; return -1; }
     if (interp < NK_INTERP_NEAREST || interp > NK_INTERP_RADIAL) { ctx->err = "unknown temp_interp"; return -1; }
@@ -328,7 +333,6 @@ int nk_set_phonon(nk_ctx* ctx, int Q, int J, int NT, const double* Tg, const dou
     ctx->h_tau.assign(tau, tau + (size_t)NT * M);
     ctx->h_Tg.assign(Tg, Tg + NT);
     if (ctx->hot_hi == 0) { ctx->hot_lo = 295.0; ctx->hot_hi = 305.0; }
-    P.emit_m_lo = 0; P.emit_m_hi = M;
     return nk_build_tau4(ctx);
 }
 
@@ -389,6 +393,7 @@ int nk_set_reservoirs(nk_ctx* ctx, int R, const int32_t* res_facet, const double
     NK_UP(dd, double, rou.data(), rou.size()); P.res_roulette = dd;
     NK_UP(dd, double, nl.data(), nl.size()); P.res_nleave = dd;
     NK_UP(dd, double, (const double*)nullptr, (size_t)std::max(R, 1) * P.M); P.emit_u = dd;
+    { unsigned char* du; NK_UP(du, unsigned char, (const unsigned char*)nullptr, (size_t)std::max(R, 1) * P.M); P.res_fire = du; }
     return nk_alloc_scratch(ctx);
 }
 
@@ -436,20 +441,20 @@ int nk_bind_particles(nk_ctx* ctx, int64_t cap, double* px, double* py, double* 
     if (((uintptr_t)mode | (uintptr_t)omode) & 7) { ctx->err = "mode arrays must be 8-byte aligned"; return -1; }
     P.cap = cap; P.px = px; P.py = py; P.pz = pz; P.tc = tc; P.occ = occ; P.mode = mode; P.omode = omode; P.cfacet = cfacet;
     P.cx = cx; P.cy = cy; P.cz = cz; P.pid = (long long*)pid;
+    if (P.M <= 0) { ctx->err = "nk_set_phonon before nk_bind_particles (the free-slot rings are per mode)"; return -1; }
     int* di;
     NK_UP(di, int, (const int*)nullptr, (size_t)cap); P.hitlist = di;
-    // free-slot rings (NkP::fr_*): one bucket ring per mode for the ordered region + the global ring of `cap` entries
-    {
-        // (experiment, off by default: NK_FREE_BUCKETS=1 -- measured no gain, see profiles/README.md; without it every slot
-        //  recycles through the global ring)
-        const char* e = getenv("NK_FREE_BUCKETS");
-        long long B = (e && !strcmp(e, "1")) ? std::max<long long>(1, std::min<long long>(P.M, cap)) : 1;
-        P.fr_B = (int)B;
-        P.fr_bsize = (int)((cap + B - 1) / B);
-        NK_UP(di, int, (const int*)nullptr, (size_t)P.fr_B * P.fr_bsize + (size_t)cap); P.freelist = di;
-        long long* dl; NK_UP(dl, long long, (const long long*)nullptr, 3 * ((size_t)P.fr_B + 1)); P.fr_ctr = dl;
-        P.mode_bucket = nullptr; P.fr_sorted = 0;          // until nk_set_mode_slots: every slot recycles through the global ring
-    }
+    // dense hit records for up to 1/16 of the slots per step (more hits fall back to the particle arrays)
+    P.hitrec_cap = std::min<long long>(cap, std::max<long long>(65536, cap / 16));
+    { NkHitRec* dr; NK_UP(dr, NkHitRec, (const NkHitRec*)nullptr, (size_t)P.hitrec_cap); P.hitrec = dr; }
+    // free-slot rings (NkP::fr_*): ring 0 = global ring (freelist[cap, 2 cap)), ring 1 + m = region of mode m (freelist[0, cap))
+    NK_UP(di, int, (const int*)nullptr, 2 * (size_t)cap); P.freelist = di;
+    { long long* dl; NK_UP(dl, long long, (const long long*)nullptr, 3 * ((size_t)P.M + 1)); P.fr_ctr = dl; }
+    NK_UP(ctx->mode_first_dev, int, (const int*)nullptr, (size_t)P.M + 1);
+    NK_UP(ctx->sort_count, int, (const int*)nullptr, (size_t)P.M);
+    NK_UP(ctx->sort_cursor, int, (const int*)nullptr, (size_t)P.M);
+    NK_UP(ctx->sort_totals, long long, (const long long*)nullptr, 2);
+    P.mode_first = ctx->mode_first_dev; P.n_rings = 1; P.fr_sorted = 0;      // until nk_sort_by_mode: every slot recycles through the global ring
     ctx->particles_bound = true;
     return 0;
 }
@@ -465,15 +470,6 @@ static int nk_write_dyn(nk_ctx* ctx, const NkDyn* d) {
     return 0;
 }
 
-// count live slots (mode >= 0) on the host side of a tiny kernel-free path: done with a reduction kernel
-__global__ void k_count_alive(NkP P, unsigned long long* out) {
-    const long long n = P.dyn->n_slots;
-    unsigned long long c = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) c += P.mode[i] >= 0;
-    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
-}
-
 int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots) {
     cudaSetDevice(ctx->device);
     if (!ctx->particles_bound) { ctx->err = "nk_bind_particles first"; return -1; }
@@ -482,10 +478,13 @@ int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots) {
     ctx->h_slots_hint = n_slots;
     d.n_slots = n_slots; d.fr_head = d.fr_tail = d.fr_snap = 0; d.n_hits = 0; d.n_emit = 0; d.n_new = 0; d.last_hits = 0; d.last_new = 0; d.blocks_done = 0;
     if (nk_write_dyn(ctx, &d)) return -1;
-    NK_CK(cudaMemsetAsync(ctx->P.fr_ctr, 0, 3 * ((size_t)ctx->P.fr_B + 1) * sizeof(long long), ctx->stream));   // all free-slot rings empty
-    ctx->P.mode_bucket = nullptr; ctx->P.fr_sorted = 0;      // a new slot layout: the mode map (if any) must be published again
-    unsigned long long* dc; NK_CK(cudaMalloc(&dc, 8)); NK_CK(cudaMemset(dc, 0, 8));
-    k_count_alive<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->P, dc);
+    // a new slot layout: all rings empty, no mode regions (nk_sort_by_mode publishes them again); the census below puts
+    // every free slot (mode < 0) of [0, n_slots) on the global ring, so holes in the caller's arrays are recycled
+    NK_CK(cudaMemsetAsync(ctx->P.fr_ctr, 0, 3 * ((size_t)ctx->P.M + 1) * sizeof(long long), ctx->stream));
+    ctx->P.n_rings = 1; ctx->P.fr_sorted = 0;
+    unsigned long long* dc; NK_CK(cudaMalloc(&dc, 8)); NK_CK(cudaMemsetAsync(dc, 0, 8, ctx->stream));
+    k_census<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->P, dc);
+    k_census_publish<<<1, 1, 0, ctx->stream>>>(ctx->P);
     unsigned long long hc = 0;
     NK_CK(cudaStreamSynchronize(ctx->stream));
     NK_CK(cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost));
@@ -495,25 +494,58 @@ int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots) {
     return nk_write_dyn(ctx, &d);
 }
 
-int nk_set_mode_slots(nk_ctx* ctx, const int64_t* first_slot_of_mode) {
+// Maintenance pass between timesteps (nk_sort.cuh): live particles ordered by mode into the BACK buffers, free slots
+// squeezed out; with pool_frac / pool_fixed > 0 every mode region gets spare slots and its own free-slot ring.  On return the
+// back buffers are the bound particle arrays (the caller swaps its handles) and the old front buffers are scratch.
+int nk_sort_by_mode(nk_ctx* ctx, double* px, double* py, double* pz, double* tc, double* occ, int32_t* mode, int32_t* omode,
+                    int32_t* cfacet, double* cx, double* cy, double* cz, int64_t* pid, double pool_frac, int pool_fixed,
+                    int64_t* n_slots_out, int64_t* n_alive_out) {
     cudaSetDevice(ctx->device);
     NkP& P = ctx->P;
-    if (!ctx->particles_bound || P.M == 0) { ctx->err = "nk_set_phonon and nk_bind_particles first"; return -1; }
-    NK_CK(cudaStreamSynchronize(ctx->stream));
-    // pending free slots are dropped (they stay unused until the next compaction): the rings change meaning
-    NK_CK(cudaMemset(P.fr_ctr, 0, 3 * ((size_t)P.fr_B + 1) * sizeof(long long)));
-    if (!first_slot_of_mode || !getenv_is_one("NK_FREE_BUCKETS")) { P.mode_bucket = nullptr; P.fr_sorted = 0; return 0; }
-    NkDyn d; if (nk_read_dyn(ctx, &d)) return -1;
-    std::vector<int> mb(P.M);
-    for (int m = 0; m < P.M; ++m) {
-        long long b = first_slot_of_mode[m] / P.fr_bsize;
-        mb[m] = (int)std::max<long long>(0, std::min<long long>(b, P.fr_B - 1));
+    if (!ctx->particles_bound) { ctx->err = "nk_bind_particles first"; return -1; }
+    if (((uintptr_t)px | (uintptr_t)py | (uintptr_t)pz | (uintptr_t)tc | (uintptr_t)occ) & 15) { ctx->err = "particle arrays must be 16-byte aligned"; return -1; }
+    if (((uintptr_t)mode | (uintptr_t)omode) & 7) { ctx->err = "mode arrays must be 8-byte aligned"; return -1; }
+    if (px == P.px || mode == P.mode) { ctx->err = "nk_sort_by_mode needs a second set of arrays (back buffers)"; return -1; }
+    cudaStream_t st = ctx->stream;
+    const int M = P.M;
+    bool pools = (pool_frac > 0.0 || pool_fixed > 0) && !ctx->has_rough;      // rough walls change modes in place: regions would not hold
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        NK_CK(cudaMemsetAsync(ctx->sort_count, 0, (size_t)M * sizeof(int), st));
+        k_sort_hist<<<ctx->n_sm * 8, 256, 0, st>>>(P, ctx->sort_count);
+        k_sort_scan<<<1, 1024, 0, st>>>(M, ctx->sort_count, ctx->mode_first_dev, ctx->sort_cursor, pools ? pool_frac : 0.0, pools ? pool_fixed : 0,
+                                        ctx->sort_totals);
+        NK_CK(cudaGetLastError());
+        long long tot[2] = {0, 0};
+        NK_CK(cudaMemcpyAsync(tot, ctx->sort_totals, sizeof(tot), cudaMemcpyDeviceToHost, st));
+        NK_CK(cudaStreamSynchronize(st));
+        if (tot[0] > P.cap) {
+            if (pools) { pools = false; continue; }               // no room for the spare slots: plain compaction
+            ctx->err = "nk_sort_by_mode: more live particles than capacity"; return -1;
+        }
+        const long long n_dst = tot[0], n_live = tot[1];
+        int* perm = P.hitlist;                                    // cap ints, free between timesteps
+        if (n_dst > 0) NK_CK(cudaMemsetAsync(perm, 0xFF, (size_t)n_dst * sizeof(int), st));
+        k_sort_rank<<<ctx->n_sm * 8, 256, 0, st>>>(P, ctx->sort_cursor, perm);
+        NkSoA src{P.px, P.py, P.pz, P.tc, P.occ, P.cx, P.cy, P.cz, P.mode, P.omode, P.cfacet, P.pid};
+        NkSoA dst{px, py, pz, tc, occ, cx, cy, cz, mode, omode, cfacet, (long long*)pid};
+        if (n_dst > 0) k_sort_permute<<<ctx->n_sm * 8, 256, 0, st>>>(src, dst, perm, n_dst);
+        if (P.cap > n_dst) NK_CK(cudaMemsetAsync(mode + n_dst, 0xFF, (size_t)(P.cap - n_dst) * sizeof(int), st));    // free slots beyond
+        k_sort_pools<<<ctx->n_sm, 256, 0, st>>>(M, ctx->sort_count, ctx->mode_first_dev, P.fr_ctr, P.freelist, pools ? 1 : 0);
+        NK_CK(cudaGetLastError());
+        P.px = px; P.py = py; P.pz = pz; P.tc = tc; P.occ = occ; P.mode = mode; P.omode = omode; P.cfacet = cfacet;
+        P.cx = cx; P.cy = cy; P.cz = cz; P.pid = (long long*)pid;
+        P.fr_sorted = pools ? n_dst : 0;
+        P.n_rings = pools ? M + 1 : 1;
+        NkDyn d; if (nk_read_dyn(ctx, &d)) return -1;
+        d.n_slots = n_dst; d.n_alive = n_live; d.fr_head = d.fr_tail = d.fr_snap = 0;
+        d.n_hits = 0; d.n_emit = 0; d.n_new = 0; d.last_hits = 0; d.last_new = 0; d.blocks_done = 0;
+        if (nk_write_dyn(ctx, &d)) return -1;
+        ctx->h_slots_hint = n_dst;
+        if (n_slots_out) *n_slots_out = n_dst;
+        if (n_alive_out) *n_alive_out = n_live;
+        return 0;
     }
-    if (!ctx->mode_bucket_dev) { int* di; NK_UP(di, int, (const int*)nullptr, (size_t)P.M); ctx->mode_bucket_dev = di; }
-    NK_CK(cudaMemcpy(ctx->mode_bucket_dev, mb.data(), (size_t)P.M * sizeof(int), cudaMemcpyHostToDevice));
-    P.mode_bucket = ctx->mode_bucket_dev;
-    P.fr_sorted = d.n_slots;                   // the ordered region: everything in use right now
-    return 0;
+    return -1;
 }
 
 int nk_get_slot_count(nk_ctx* ctx, int64_t* n_slots, int64_t* n_alive) {
@@ -597,7 +629,7 @@ static inline int nk_grid(long long n, int threads, int cap_blocks) {
 int nk_find_boundary(nk_ctx* ctx, int64_t n, const double* x, const double* v, double* xc, double* tc, int32_t* fc) {
     cudaSetDevice(ctx->device);
     if (n <= 0) return 0;
-    k_find_boundary<<<nk_grid(n, 256, 0), 256, 0, ctx->stream>>>(ctx->P, n, x, v, xc, tc, fc);
+    k_find_boundary<<<nk_grid(n, NK_RAY_THREADS, ctx->n_sm * 8), NK_RAY_THREADS, NK_TILE_SMEM_BYTES, ctx->stream>>>(ctx->P, n, x, v, xc, tc, fc);
     NK_CK(cudaGetLastError());
     return 0;
 }
@@ -659,7 +691,7 @@ static int nk_check_ready(nk_ctx* ctx) {
 int nk_init_collisions(nk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (nk_check_ready(ctx)) return -1;
-    k_init_collisions<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(ctx->P);
+    k_init_collisions<<<ctx->n_sm * 4, NK_RAY_THREADS, NK_TILE_SMEM_BYTES, ctx->stream>>>(ctx->P);
     NK_CK(cudaGetLastError());
     return 0;
 }
@@ -683,22 +715,19 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     // library), so the launch-uniform RELAX / FLUX variants can be chosen without a device read-back
     const bool relax = ctx->h_relax_pending;
     const bool flux = ((ctx->h_step + 1) % P.n_dt_to_conv) == 0;
-    int variant = ctx->step_variant;                          // 0: 2 particles/thread LDG.128, 1: TMA pipeline, 2: 1 particle/thread
+    int variant = 0;                                          // 0: direct arithmetic, 4: per-(mode, subvolume) tables
     if (phase == 2) variant = ctx->last_variant;
     else {
-    if (variant == 1 && (P.cap % NK_TILE) != 0) variant = 0;
     // per-(mode, subvolume) tables pay off once there are a few particles per table entry
     // ... and while the table (16 B per entry, rebuilt every step) stays L2-sized: at S = 100 x 1.8e5 modes (286 MB) the
     // rebuild costs what the leaner inner loop saves (profiles/README.md)
-    if (variant == 0 && ctx->use_tab && fast && P.hot_tab &&
+    if (ctx->use_tab && fast && P.hot_tab &&
         (ctx->force_tab || (ctx->h_slots_hint >= 2 * (long long)P.M * P.S && (long long)P.M * P.S <= NK_TAB_MAX_ENTRIES))) variant = 4;
     if (variant == 4 && ctx->tab_dirty) {
         k_mode_tables<<<ctx->n_sm * 8, 256, nk_hot_smem_bytes(P.S), ctx->stream>>>(P);
         NK_CK(cudaGetLastError());
         ctx->tab_dirty = false;
     }
-    if (variant == 1) smem = NK_STAGES * sizeof(NkTileSmem) + (NK_STAGES + 1) * 8 + nk_step_smem(P);
-    if (variant == 3) smem = 2 * sizeof(NkPfStage) + nk_step_smem(P);
     // experiment (NK_L2_PERSIST=1): keep the (mode, subvolume) table in the persisting part of the L2 while 8 GB of particle
     // state stream through it
     if (variant == 4 && ctx->l2_persist && !ctx->l2_window_set) {
@@ -731,7 +760,6 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     if (!plan) {
         kern<<<ctx->step_blocks, NK_STEP_THREADS, smem, ctx->stream>>>(P);
     } else {
-        if (variant != 0 && variant != 4) { ctx->err = "chunked launch needs the direct or table step kernel"; return -1; }
         for (int c = 0; c < plan->n; ++c) {
             NkP Pc = P;
             Pc.slot_lo = (long long)c * plan->chunk;
@@ -748,12 +776,31 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     }
     if (phase == 1) return 0;
     const size_t fin_smem = (3 * (size_t)P.S + 2 * (size_t)nk_acc_len(P.S, P.R)) * 8;
+    const bool tiled = P.F > NK_RARE_FACES || ctx->force_tiled;
+    ctx->last_rare_tiled = tiled;
+    const size_t rare_smem = fin_smem + (tiled ? NK_TILE_SMEM_BYTES : 0);
+    if (!ctx->rare_attr_set) {
+        // k_rare keeps ~25 KB of static shared memory (triangles + facet tables): opt in when static + dynamic exceed 48 KB
+        const int want = (int)(fin_smem + NK_TILE_SMEM_BYTES);
+        if (want + 26 * 1024 > 48 * 1024) {
+            cudaFuncSetAttribute(k_rare<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem);
+            cudaFuncSetAttribute(k_rare<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem);
+            cudaFuncSetAttribute(k_rare_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+            cudaFuncSetAttribute(k_rare_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+        }
+        ctx->rare_attr_set = true;
+    }
     // one item per thread; the number of items is known on the device only, so size the grid for ~5 % of the slots
     // (hits + emission are 0.2-2 % of the particles per step; more items are covered by the grid-stride loop)
     const long long want_blocks = (ctx->h_slots_hint / 20 + NK_RARE_THREADS - 1) / NK_RARE_THREADS;
     const int rare_blocks = (int)std::min<long long>((long long)ctx->n_sm * 16, std::max<long long>(ctx->n_sm, want_blocks));
-    if (fuse_finalize) k_rare<true><<<rare_blocks, NK_RARE_THREADS, fin_smem, ctx->stream>>>(P);
-    else k_rare<false><<<rare_blocks, NK_RARE_THREADS, fin_smem, ctx->stream>>>(P);
+    if (tiled) {
+        if (fuse_finalize) k_rare_tiled<true><<<rare_blocks, NK_RARE_THREADS, rare_smem, ctx->stream>>>(P);
+        else k_rare_tiled<false><<<rare_blocks, NK_RARE_THREADS, rare_smem, ctx->stream>>>(P);
+    } else {
+        if (fuse_finalize) k_rare<true><<<rare_blocks, NK_RARE_THREADS, rare_smem, ctx->stream>>>(P);
+        else k_rare<false><<<rare_blocks, NK_RARE_THREADS, rare_smem, ctx->stream>>>(P);
+    }
     NK_CK(cudaGetLastError());
     nk_prof_mark(ctx);
     if (fuse_finalize) {
@@ -770,6 +817,8 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
 }
 
 int nk_step_local(nk_ctx* ctx) { return nk_step_kernels(ctx, false); }
+
+int nk_last_step_variant(nk_ctx* ctx) { return ctx->last_variant + (ctx->last_rare_tiled ? 8 : 0); }
 
 int nk_step_finalize(nk_ctx* ctx) {
     cudaSetDevice(ctx->device);
@@ -1159,8 +1208,7 @@ int nk_advance_host(nk_ctx* ctx, int64_t n_in, int n_steps, double* px, double* 
     if (nk_check_ready(ctx)) return -1;
     NkP& P = ctx->P;
     if (n_in > P.cap) { ctx->err = "n_in exceeds bound capacity"; return -1; }
-    const bool pipe = ctx->use_pipeline && n_steps == 1 && (P.world == 1 || P.comm_on) && n_in >= (1 << 20) && !ctx->profiling &&
-                      (ctx->step_variant == 0);
+    const bool pipe = ctx->use_pipeline && n_steps == 1 && (P.world == 1 || P.comm_on) && n_in >= (1 << 20) && !ctx->profiling;
     int rc = pipe ? nk_advance_host_pipelined(ctx, n_in, px, py, pz, tc, occ, mode, omode, cfacet, cx, cy, cz, pid, n_out)
                   : nk_advance_host_simple(ctx, n_in, n_steps, px, py, pz, tc, occ, mode, omode, cfacet, cx, cy, cz, pid, n_out);
     if (rc) return rc;
@@ -1200,12 +1248,39 @@ int nk_last_transfer_bytes(nk_ctx* ctx, int64_t* h2d, int64_t* d2h) {
 int nk_set_rank(nk_ctx* ctx, int rank, int world) {
     NkP& P = ctx->P;
     if (world < 1 || rank < 0 || rank >= world) { ctx->err = "bad rank/world"; return -1; }
-    if (P.M == 0) { ctx->err = "nk_set_phonon first"; return -1; }
+    if (world > 255) { ctx->err = "at most 255 ranks (emission copies are dealt with an 8-bit counter)"; return -1; }
+    // every rank advances the whole reservoir table; copies are dealt round-robin per table entry (nk_emit_owner)
     P.rank = rank; P.world = world;
-    long long M = P.M;
-    P.emit_m_lo = (int)(M * rank / world);
-    P.emit_m_hi = (int)(M * (rank + 1) / world);
     return 0;
+}
+
+// ---- run state that is neither a table nor a particle: reservoir counters, emission deal counters, the accumulators of the
+//      current convergence window, N_leaving of the previous step, the results block.  Checkpoints use it to continue
+//      bit-exactly WITHOUT rebuilding the tables (nk_set_reservoirs would also reset the accumulators and the rank).
+int nk_results_len(nk_ctx* ctx) { return nk_out_len(ctx->P.S, ctx->P.R); }
+static int nk_run_state_io(nk_ctx* ctx, bool write, double* res_counter, uint8_t* res_fire, double* res_acc, double* n_leaving, double* results) {
+    cudaSetDevice(ctx->device);
+    NkP& P = ctx->P;
+    if (!P.res_counter || !P.out) { ctx->err = "nk_set_reservoirs first"; return -1; }
+    NK_CK(cudaStreamSynchronize(ctx->stream));
+    const size_t rm = (size_t)P.R * P.M;
+    auto io = [&](void* dev, void* host, size_t bytes) -> cudaError_t {
+        if (!host || !bytes) return cudaSuccess;
+        return write ? cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice) : cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost);
+    };
+    NK_CK(io(P.res_counter, res_counter, rm * 8));
+    NK_CK(io(P.res_fire, res_fire, rm));
+    NK_CK(io(P.res_acc, res_acc, 4 * (size_t)P.R * 8));
+    NK_CK(io(P.res_nleave, n_leaving, (size_t)P.R * 8));
+    NK_CK(io(P.out, results, (size_t)nk_out_len(P.S, P.R) * 8));
+    return 0;
+}
+int nk_get_run_state(nk_ctx* ctx, double* res_counter, uint8_t* res_fire, double* res_acc, double* n_leaving, double* results) {
+    return nk_run_state_io(ctx, false, res_counter, res_fire, res_acc, n_leaving, results);
+}
+int nk_set_run_state(nk_ctx* ctx, const double* res_counter, const uint8_t* res_fire, const double* res_acc, const double* n_leaving,
+                     const double* results) {
+    return nk_run_state_io(ctx, true, (double*)res_counter, (uint8_t*)res_fire, (double*)res_acc, (double*)n_leaving, (double*)results);
 }
 int nk_acc_buffer(nk_ctx* ctx, double** p, int64_t* n) {
     if (!ctx->P.acc) { ctx->err = "accumulators not allocated yet"; return -1; }

@@ -1,6 +1,6 @@
 // nk_ops.cuh -- shared-memory subvolume tables and the operator kernels behind the reference's method seams
-// Part of the single translation unit nk_kernels.cu (included in this order: nk_ops.cuh, nk_stream.cuh,
-// nk_stream_variants.cuh, nk_rare.cuh, nk_hostpipe.cuh); see DESIGN.md section 4.
+// Part of the single translation unit nk_kernels.cu (included in this order: nk_tiles.cuh, nk_ops.cuh, nk_stream.cuh,
+// nk_rare.cuh, nk_sort.cuh, nk_hostpipe.cuh); see DESIGN.md section 4.
 #pragma once
 
 // =================================================================================================
@@ -24,34 +24,34 @@ __device__ __forceinline__ NkSvSmem nk_load_sv(const NkP& P, double* sm) {
 }
 __host__ __device__ static inline size_t nk_sv_smem_doubles(int S) { return (size_t)6 * S; }
 
-// Mesh.find_boundary operator seam: one ray per thread, triangles staged through shared memory.
-#define NK_FACE_TILE 256
-__global__ void __launch_bounds__(256) k_find_boundary(NkP P, long long n, const double* __restrict__ x,
-                                                        const double* __restrict__ v, double* __restrict__ xc,
-                                                        double* __restrict__ tc, int* __restrict__ fc) {
-    __shared__ NkFace sf[NK_FACE_TILE];
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    double px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0;
-    if (i < n) { px = x[3 * i]; py = x[3 * i + 1]; pz = x[3 * i + 2]; vx = v[3 * i]; vy = v[3 * i + 1]; vz = v[3 * i + 2]; }
-    double tbest = CUDART_INF; int fbest = -1;
-    for (int f0 = 0; f0 < P.F; f0 += NK_FACE_TILE) {
-        int nt = min(NK_FACE_TILE, P.F - f0);
-        __syncthreads();
-        const double* src = reinterpret_cast<const double*>(P.faces + f0);
-        double* dst = reinterpret_cast<double*>(sf);
-        for (int k = threadIdx.x; k < nt * (int)(sizeof(NkFace) / 8); k += blockDim.x) dst[k] = src[k];
-        __syncthreads();
-        if (i < n) nk_ray_faces(sf, nt, px, py, pz, vx, vy, vz, tbest, fbest);
-    }
-    if (i < n) {
-        tc[i] = tbest; fc[i] = fbest;
-        xc[3 * i] = nk_add(px, nk_mul(tbest, vx)); xc[3 * i + 1] = nk_add(py, nk_mul(tbest, vy)); xc[3 * i + 2] = nk_add(pz, nk_mul(tbest, vz));
+// Mesh.find_boundary operator seam: one ray per thread, the triangles stream through shared memory in TMA-staged tiles
+// (nk_tiles.cuh).  Launch with NK_TILE_SMEM_BYTES of dynamic shared memory.
+#define NK_RAY_THREADS 256
+__global__ void __launch_bounds__(NK_RAY_THREADS) k_find_boundary(NkP P, long long n, const double* __restrict__ x,
+                                                                   const double* __restrict__ v, double* __restrict__ xc,
+                                                                   double* __restrict__ tc, int* __restrict__ fc) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    NkTilePipe tp;
+    nk_tiles_init(tp, tile_smem, P);
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + threadIdx.x;
+        const bool live = i < n;
+        double px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0;
+        if (live) { px = x[3 * i]; py = x[3 * i + 1]; pz = x[3 * i + 2]; vx = v[3 * i]; vy = v[3 * i + 1]; vz = v[3 * i + 2]; }
+        double tbest = CUDART_INF; int fbest = -1;
+        nk_tiles_sweep(tp, P, live, px, py, pz, vx, vy, vz, tbest, fbest);
+        if (live) {
+            tc[i] = tbest; fc[i] = fbest;
+            xc[3 * i] = nk_add(px, nk_mul(tbest, vx)); xc[3 * i + 1] = nk_add(py, nk_mul(tbest, vy)); xc[3 * i + 2] = nk_add(pz, nk_mul(tbest, vz));
+        }
     }
 }
 
-// first collision of every live slot (Population.py:308-316)
-__global__ void __launch_bounds__(256) k_init_collisions(NkP P) {
-    __shared__ NkFace sf[NK_FACE_TILE];
+// first collision of every live slot (Population.py:308-316): P = N rays against all F triangles
+__global__ void __launch_bounds__(NK_RAY_THREADS) k_init_collisions(NkP P) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    NkTilePipe tp;
+    nk_tiles_init(tp, tile_smem, P);
     const long long n = P.dyn->n_slots;
     for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
         long long i = base + threadIdx.x;
@@ -59,15 +59,7 @@ __global__ void __launch_bounds__(256) k_init_collisions(NkP P) {
         double px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0;
         if (live) { NkMode m = P.mprop[P.mode[i]]; px = P.px[i]; py = P.py[i]; pz = P.pz[i]; vx = m.vx; vy = m.vy; vz = m.vz; }
         double tbest = CUDART_INF; int fbest = -1;
-        for (int f0 = 0; f0 < P.F; f0 += NK_FACE_TILE) {
-            int nt = min(NK_FACE_TILE, P.F - f0);
-            __syncthreads();
-            const double* src = reinterpret_cast<const double*>(P.faces + f0);
-            double* dst = reinterpret_cast<double*>(sf);
-            for (int k = threadIdx.x; k < nt * (int)(sizeof(NkFace) / 8); k += blockDim.x) dst[k] = src[k];
-            __syncthreads();
-            if (live) nk_ray_faces(sf, nt, px, py, pz, vx, vy, vz, tbest, fbest);
-        }
+        nk_tiles_sweep(tp, P, live, px, py, pz, vx, vy, vz, tbest, fbest);
         if (live) {
             P.tc[i] = nk_div(tbest, P.dt); P.cfacet[i] = fbest;
             P.cx[i] = nk_add(px, nk_mul(tbest, vx)); P.cy[i] = nk_add(py, nk_mul(tbest, vy)); P.cz[i] = nk_add(pz, nk_mul(tbest, vz));

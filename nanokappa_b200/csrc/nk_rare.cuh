@@ -1,12 +1,21 @@
 // nk_rare.cuh -- the rare path of a timestep (boundary events, emission), the closing block, the in-kernel exchange, the relaxation flush
-// Part of the single translation unit nk_kernels.cu (included in this order: nk_ops.cuh, nk_stream.cuh,
-// nk_stream_variants.cuh, nk_rare.cuh, nk_hostpipe.cuh); see DESIGN.md section 4.
+// Part of the single translation unit nk_kernels.cu (included in this order: nk_tiles.cuh, nk_ops.cuh, nk_stream.cuh,
+// nk_rare.cuh, nk_sort.cuh, nk_hostpipe.cuh); see DESIGN.md section 4.
 #pragma once
 
 // ---- helpers shared by the rare-path code ------------------------------------------------------------------
 __device__ __forceinline__ void nk_store_particle(const NkP& P, long long i, const NkParticle& p) {
     P.px[i] = p.x; P.py[i] = p.y; P.pz[i] = p.z; P.tc[i] = p.tc; P.occ[i] = p.occ;
     P.mode[i] = p.mode; P.omode[i] = p.omode; P.cfacet[i] = p.cf; P.cx[i] = p.cx; P.cy[i] = p.cy; P.cz[i] = p.cz;
+}
+// write-back of a particle that went through the event loop: position, clock and the new collision always change, mode /
+// omega-carrying mode / occupation only at a rough wall.  Unchanged fields are not rewritten (every scattered 8-byte
+// store costs a 32-byte sector read-modify-write in DRAM).
+__device__ __forceinline__ void nk_store_after_events(const NkP& P, long long i, const NkParticle& p) {
+    P.px[i] = p.x; P.py[i] = p.y; P.pz[i] = p.z; P.tc[i] = p.tc;
+    P.cfacet[i] = p.cf; P.cx[i] = p.cx; P.cy[i] = p.cy; P.cz[i] = p.cz;
+    if (p.mode_changed) { P.mode[i] = p.mode; P.omode[i] = p.omode; }
+    if (p.occ_changed) P.occ[i] = p.occ;
 }
 // refresh_temperatures contribution of one particle handled outside k_step; `acc` is the block-private
 // (shared memory) copy of the accumulator vector
@@ -22,52 +31,49 @@ __device__ __forceinline__ void nk_accumulate(const NkP& P, double* acc, const N
     }
 }
 
-// Free slots live in rings (NkP::fr_*): absorbed particles push at the tail of the ring of their slot -- the bucket ring of an
-// ordered slot, the global ring otherwise -- and emission pops at the head of the bucket where the new particle's mode lives
-// (then its neighbours, then the global ring), but only entries pushed in EARLIER steps (below the ring's `snap`, advanced in
-// the prologue of the next streaming kernel), so that pushes and pops of the same launch never touch the same entry.  A bucket
-// ring only ever receives its own fr_bsize slots and the global ring holds cap entries: no ring can overflow.
-__device__ __forceinline__ void nk_kill(const NkP& P, double* acc, long long i) {
+// Free slots live in rings (NkP::fr_*): an absorbed particle pushes its slot at the tail of the ring that owns the slot -- the
+// ring of the mode region the slot lies in (ordered part of the array), the global ring otherwise -- and emission pops at
+// the head of the new particle's own mode ring (then the global ring, then it appends), but only entries pushed in EARLIER
+// steps (below the ring's `snap`, advanced in the prologue of the next streaming kernel), so that pushes and pops of the
+// same launch never touch the same entry.  A mode ring only ever receives the slots of its own region and the global ring
+// holds cap entries: no ring can overflow.
+__device__ __forceinline__ int nk_region_of_slot(const NkP& P, long long i, int mode_hint) {
+    const int* f = P.mode_first;
+    if (mode_hint >= 0 && (long long)f[mode_hint] <= i && i < (long long)f[mode_hint + 1]) return mode_hint;
+    int lo = 0, hi = P.M;                       // last m with first[m] <= i  (regions of size 0 share their start with the next one)
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((long long)f[mid] <= i) lo = mid; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ void nk_kill(const NkP& P, double* acc, long long i, int old_mode) {
     P.mode[i] = -1;
-    const bool ordered = i < P.fr_sorted;
-    const int b = ordered ? (int)(i / P.fr_bsize) : P.fr_B;
-    const unsigned long long size = ordered ? (unsigned long long)P.fr_bsize : (unsigned long long)P.cap;
-    long long* c = P.fr_ctr + 3 * (size_t)b;
+    int ring = 0; long long base = P.cap; unsigned long long size = (unsigned long long)P.cap;
+    if (i < P.fr_sorted) {
+        const int m = nk_region_of_slot(P, i, old_mode);
+        ring = 1 + m; base = P.mode_first[m]; size = (unsigned long long)(P.mode_first[m + 1] - P.mode_first[m]);
+    }
+    long long* c = P.fr_ctr + 3 * (size_t)ring;
     const unsigned long long k = atomicAdd((unsigned long long*)(c + 1), 1ull);
-    P.freelist[(size_t)b * P.fr_bsize + (k % size)] = (int)i;
+    P.freelist[base + (long long)(k % size)] = (int)i;
     NK_RACC_N(P, acc, NK_ACC_NABS(P.S, P.R));
 }
-__device__ __forceinline__ long long nk_pop_ring(const NkP& P, int b, long long size) {
-    long long* c = P.fr_ctr + 3 * (size_t)b;
+__device__ __forceinline__ long long nk_pop_ring(const NkP& P, int ring, long long base, long long size) {
+    long long* c = P.fr_ctr + 3 * (size_t)ring;
     if (*(volatile long long*)c >= c[2]) return -1;                     // nothing recyclable here (cheap look before the atomic)
     const long long old = (long long)atomicAdd((unsigned long long*)c, 1ull);
     // a claim beyond the snapshot is not returned: the next prologue clamps the head back
-    return old < c[2] ? (long long)P.freelist[(size_t)b * P.fr_bsize + (old % size)] : -1;
+    return old < c[2] ? (long long)P.freelist[base + (old % size)] : -1;
 }
 __device__ __forceinline__ long long nk_take_slot(const NkP& P, int mode) {
-    if (P.mode_bucket && P.fr_sorted > 0) {
-        const int b0 = P.mode_bucket[mode];
-        for (int t = 0; t < 5; ++t) {
-            const int b = b0 + ((t & 1) ? (t + 1) / 2 : -(t / 2));      // b0, b0+1, b0-1, b0+2, b0-2
-            if (b < 0 || b >= P.fr_B) continue;
-            const long long s = nk_pop_ring(P, b, P.fr_bsize);
+    if (P.fr_sorted > 0) {
+        const long long base = P.mode_first[mode], size = P.mode_first[mode + 1] - base;
+        if (size > 0) {
+            const long long s = nk_pop_ring(P, 1 + mode, base, size);
             if (s >= 0) return s;
         }
     }
     {
-        const long long s = nk_pop_ring(P, P.fr_B, P.cap);
+        const long long s = nk_pop_ring(P, 0, P.cap, P.cap);
         if (s >= 0) return s;
-    }
-    if (P.mode_bucket && P.fr_sorted > 0) {
-        // the neighbourhood is exhausted (a rank of a sharded run emits only its share of the modes but absorbs all of them):
-        // take a free slot from anywhere rather than growing the slot range -- a few probes of pseudo-random buckets
-        unsigned int h = (unsigned int)clock64() * 2654435761u + (unsigned int)mode * 40503u + threadIdx.x;
-        const unsigned int used = (unsigned int)min((long long)P.fr_B, P.fr_sorted / P.fr_bsize + 1);
-        for (int t = 0; t < 8; ++t) {
-            h = h * 1664525u + 1013904223u;
-            const long long s = nk_pop_ring(P, (int)((h >> 8) % used), P.fr_bsize);
-            if (s >= 0) return s;
-        }
     }
     long long slot = (long long)nk_agg_inc((unsigned long long*)&P.dyn->n_slots);      // nothing recyclable: append
     if (slot >= P.cap) {
@@ -78,16 +84,13 @@ __device__ __forceinline__ long long nk_take_slot(const NkP& P, int mode) {
     return slot;
 }
 
-// One emission-list entry: n_new copies of mode m entering through reservoir r (Population.py:385-406,
-// :491-508, add_reservoir_particles :525-552, Mesh.sample_surface Mesh.py:923-951).
 // One new particle of reservoir r in mode m entering the domain dt_in before the end of the step
-// (Population.fill_reservoirs :491-508 + add_reservoir_particles :525-552 + Mesh.sample_surface :923-951).
-__device__ __forceinline__ void nk_emit_particle(const NkP& P, const NkGeo& G, double* acc, int r, int m, long long id, double dt_in,
-                                                 double uface, double us, double ur, long long step, bool with_flux) {
-    const double dt = P.dt;
+// (Population.fill_reservoirs :491-508 + add_reservoir_particles :525-552 + Mesh.sample_surface :923-951), in three
+// parts around the ray query for its first collision.
+__device__ __forceinline__ void nk_emit_setup(const NkP& P, int r, int m, long long id, double uface, double us, double ur,
+                                              NkParticle& p, double& x0, double& y0, double& z0) {
     const NkMode mp = P.mprop[m];
-    NkParticle p;
-    p.id = id;
+    p.id = id; p.slot = -1; p.mode_changed = false; p.occ_changed = false;
     // face ~ area: searchsorted(cdf, u, side='right') as np.random.choice does
     const int f0 = P.res_face_ptr[r], f1 = P.res_face_ptr[r + 1];
     int lo = f0, hi = f1;
@@ -96,20 +99,30 @@ __device__ __forceinline__ void nk_emit_particle(const NkP& P, const NkGeo& G, d
     const double* V = P.face_vertices + 9 * (size_t)face;
     const double rs = sqrt(us);
     const double a0 = nk_sub(1.0, rs), a1 = nk_mul(nk_sub(1.0, ur), rs), a2 = nk_mul(ur, rs);
-    const double x0 = nk_add(nk_add(nk_mul(a0, V[0]), nk_mul(a1, V[3])), nk_mul(a2, V[6]));
-    const double y0 = nk_add(nk_add(nk_mul(a0, V[1]), nk_mul(a1, V[4])), nk_mul(a2, V[7]));
-    const double z0 = nk_add(nk_add(nk_mul(a0, V[2]), nk_mul(a1, V[5])), nk_mul(a2, V[8]));
+    x0 = nk_add(nk_add(nk_mul(a0, V[0]), nk_mul(a1, V[3])), nk_mul(a2, V[6]));
+    y0 = nk_add(nk_add(nk_mul(a0, V[1]), nk_mul(a1, V[4])), nk_mul(a2, V[7]));
+    z0 = nk_add(nk_add(nk_mul(a0, V[2]), nk_mul(a1, V[5])), nk_mul(a2, V[8]));
     p.mode = m; p.omode = m; p.omega = mp.omega; p.vx = mp.vx; p.vy = mp.vy; p.vz = mp.vz;
-    double t;
-    nk_find_boundary_1(P, G.faces, x0, y0, z0, p.vx, p.vy, p.vz, p.cx, p.cy, p.cz, t, p.cf);
+    p.x = x0; p.y = y0; p.z = z0;                    // ray origin of the first-collision query
+    p.alive = true;
+}
+// after the ray query (t, cf) from (x0, y0, z0): clocks, entry drift, occupation.  Returns true when the first collision
+// falls inside this very step (the event loop must run).
+__device__ __forceinline__ bool nk_emit_post(const NkP& P, double* acc, int r, double dt_in, double x0, double y0, double z0, double t, int cf,
+                                             NkParticle& p) {
+    const double dt = P.dt;
+    p.cf = cf;
+    p.cx = nk_add(x0, nk_mul(t, p.vx)); p.cy = nk_add(y0, nk_mul(t, p.vy)); p.cz = nk_add(z0, nk_mul(t, p.vz));
     p.tc = nk_sub(nk_div(t, dt), nk_div(dt_in, dt));
     p.x = nk_add(x0, nk_mul(p.vx, dt_in)); p.y = nk_add(y0, nk_mul(p.vy, dt_in)); p.z = nk_add(z0, nk_mul(p.vz, dt_in));
     p.occ = nk_bose(P, P.res_T[r], p.omega);
-    p.alive = true;
     NK_RACC_N(P, acc, NK_ACC_NEMIT(P.S, P.R));
-    if (p.tc < 0.0) nk_boundary_events(P, G, p, step, acc);
-    if (!p.alive) { NK_RACC_N(P, acc, NK_ACC_NABS(P.S, P.R)); return; }   // crossed the whole domain within the step
-    const long long slot = nk_take_slot(P, m);
+    return p.tc < 0.0;
+}
+// the particle is final: give it a slot (unless it crossed the whole domain within the step) and bin it
+__device__ __forceinline__ void nk_emit_finish(const NkP& P, double* acc, NkParticle& p, bool with_flux) {
+    if (!p.alive) { NK_RACC_N(P, acc, NK_ACC_NABS(P.S, P.R)); return; }
+    const long long slot = nk_take_slot(P, p.mode);
     if (slot < 0) return;
     nk_store_particle(P, slot, p);
     P.pid[slot] = p.id;
@@ -119,63 +132,108 @@ __device__ __forceinline__ void nk_emit_particle(const NkP& P, const NkGeo& G, d
     }
     nk_accumulate(P, acc, p, with_flux);
 }
+__device__ __forceinline__ void nk_emit_particle(const NkP& P, const NkGeo& G, double* acc, int r, int m, long long id, double dt_in,
+                                                 double uface, double us, double ur, long long step, bool with_flux) {
+    NkParticle p;
+    double x0, y0, z0;
+    nk_emit_setup(P, r, m, id, uface, us, ur, p, x0, y0, z0);
+    double t = CUDART_INF; int cf = -1;
+    nk_ray_faces(G.faces, P.F, x0, y0, z0, p.vx, p.vy, p.vz, t, cf);
+    if (nk_emit_post(P, acc, r, dt_in, x0, y0, z0, t, cf, p)) nk_boundary_events(P, G, p, step, acc);
+    nk_emit_finish(P, acc, p, with_flux);
+}
 
-// One emission-list entry (constant / fixed_rate): n_new copies of mode m from reservoir r.
-__device__ __forceinline__ void nk_emit_entry(const NkP& P, const NkGeo& G, double* acc, int r, int m, int n_new, long long step, bool with_flux) {
+// id, entry time and surface draws of copy c (1-based) of an emission-list entry (constant / fixed_rate, Population.py:385-406)
+__device__ __forceinline__ void nk_emit_copy_draws(const NkP& P, int r, int m, int c, long long step, long long& id, double& dt_in,
+                                                   double& uface, double& us, double& ur) {
     const double dt = P.dt;
     const size_t idx = (size_t)r * P.M + m;
     const double prob = P.enter_prob[idx];
     // numerator of the first copy's entry time: the counter after this step's update, or this step's dice
     const double lead = P.res_gen == NK_RESGEN_FIXED_RATE ? P.emit_u[idx] : P.res_counter[idx];
+    id = NK_EMIT_ID_BASE + (((step * P.R + r) * (long long)P.M + m) * NK_EMIT_CMAX + (c - 1));
+    double ua;
+    nk_uniforms(P, id, step, NK_STREAM_EMIT_A, ua, uface);
+    nk_uniforms(P, id, step, NK_STREAM_EMIT_B, us, ur);
+    dt_in = (c == 1) ? nk_mul(dt, nk_sub(1.0, nk_div(lead, prob)))
+                     : nk_mul(dt, nk_sub(1.0, nk_div(nk_add((double)(c - 1), ua), prob)));
+}
+// One emission-list entry (constant / fixed_rate): the copies of mode m from reservoir r that belong to this rank.
+__device__ __forceinline__ void nk_emit_entry(const NkP& P, const NkGeo& G, double* acc, int r, int m, int n_new, unsigned int fire,
+                                              long long step, bool with_flux) {
     for (int c = n_new; c >= 1; --c) {
-        const long long id = NK_EMIT_ID_BASE + (((step * P.R + r) * (long long)P.M + m) * NK_EMIT_CMAX + (c - 1));
-        double ua, uface, us, ur;
-        nk_uniforms(P, id, step, NK_STREAM_EMIT_A, ua, uface);
-        nk_uniforms(P, id, step, NK_STREAM_EMIT_B, us, ur);
-        const double dt_in = (c == 1) ? nk_mul(dt, nk_sub(1.0, nk_div(lead, prob)))
-                                      : nk_mul(dt, nk_sub(1.0, nk_div(nk_add((double)(c - 1), ua), prob)));
+        if (P.world > 1 && nk_emit_owner(P, m, fire, c - 1) != P.rank) continue;
+        long long id; double dt_in, uface, us, ur;
+        nk_emit_copy_draws(P, r, m, c, step, id, dt_in, uface, us, ur);
         nk_emit_particle(P, G, acc, r, m, id, dt_in, uface, us, ur, step, with_flux);
     }
 }
 
-// One re-emitted particle of the one_to_one mode: k-th particle of reservoir r (Population.py:457-489).
-__device__ __forceinline__ void nk_emit_one_to_one(const NkP& P, const NkGeo& G, double* acc, long long e, long long step, bool with_flux) {
-    int r = 0;
+// draws of the k-th re-emitted particle of the one_to_one mode (Population.py:457-489); returns false past the end
+__device__ __forceinline__ bool nk_one_to_one_draws(const NkP& P, long long e, long long step, int& r, int& m, long long& id, double& dt_in,
+                                                    double& uface, double& us, double& ur) {
+    r = 0;
     for (; r < P.R; ++r) {
         const long long share = nk_one_to_one_share(P, r);
         if (e < share) break;
         e -= share;
     }
-    if (r >= P.R) return;
+    if (r >= P.R) return false;
     const long long k = P.rank + e * P.world;
-    const long long id = NK_EMIT_ID_BASE + (step * P.R + r) * ((long long)P.M * NK_EMIT_CMAX) + k;
-    double ua, uface, us, ur, umode, udt;
+    id = NK_EMIT_ID_BASE + (step * P.R + r) * ((long long)P.M * NK_EMIT_CMAX) + k;
+    double ua, umode, udt;
     nk_uniforms(P, id, step, NK_STREAM_EMIT_A, ua, uface);
     nk_uniforms(P, id, step, NK_STREAM_EMIT_B, us, ur);
     nk_uniforms(P, id, step, NK_STREAM_EMIT_C, umode, udt);
     const double* rou = P.res_roulette + (size_t)r * P.M;
     int lo = 0, hi = P.M;                                    // searchsorted left
     while (lo < hi) { int mid = (lo + hi) >> 1; if (rou[mid] < umode) lo = mid + 1; else hi = mid; }
-    nk_emit_particle(P, G, acc, r, min(lo, P.M - 1), id, nk_mul(P.dt, udt), uface, us, ur, step, with_flux);
+    m = min(lo, P.M - 1);
+    dt_in = nk_mul(P.dt, udt);
+    return true;
+}
+__device__ __forceinline__ void nk_emit_one_to_one(const NkP& P, const NkGeo& G, double* acc, long long e, long long step, bool with_flux) {
+    int r, m; long long id; double dt_in, uface, us, ur;
+    if (!nk_one_to_one_draws(P, e, step, r, m, id, dt_in, uface, us, ur)) return;
+    nk_emit_particle(P, G, acc, r, m, id, dt_in, uface, us, ur, step, with_flux);
 }
 
-// One hit-list entry: the boundary event loop of an existing particle.
-__device__ __forceinline__ void nk_hit_entry(const NkP& P, const NkGeo& G, double* acc, long long i, long long step, bool with_flux) {
-    NkParticle p;
-    p.x = P.px[i]; p.y = P.py[i]; p.z = P.pz[i]; p.tc = P.tc[i]; p.occ = P.occ[i];
-    p.mode = P.mode[i]; p.omode = P.omode[i];
+// load hit-list entry w: from its dense record when it has one, from the particle arrays otherwise; cold fields
+// (collision facet / point) always come from the arrays, the id only when a rough wall needs it
+__device__ __forceinline__ long long nk_load_hit(const NkP& P, unsigned int w, NkParticle& p) {
+    long long i;
+    if ((long long)w < P.hitrec_cap) {
+        const double4* r = reinterpret_cast<const double4*>(P.hitrec + w);
+        const double4 a = r[0], b = r[1];
+        p.x = a.x; p.y = a.y; p.z = a.z; p.tc = a.w; p.occ = b.x;
+        i = __double2loint(b.y); p.mode = __double2hiint(b.y); p.omode = __double2loint(b.z);
+    } else {
+        i = P.hitlist[w];
+        p.x = P.px[i]; p.y = P.py[i]; p.z = P.pz[i]; p.tc = P.tc[i]; p.occ = P.occ[i];
+        p.mode = P.mode[i]; p.omode = P.omode[i];
+    }
     const NkMode m = P.mprop[p.mode];
     p.vx = m.vx; p.vy = m.vy; p.vz = m.vz;
     p.omega = (p.omode == p.mode) ? m.omega : P.mprop[p.omode].omega;
     p.cf = P.cfacet[i]; p.cx = P.cx[i]; p.cy = P.cy[i]; p.cz = P.cz[i];
-    p.id = P.pid[i]; p.alive = true;
-    nk_boundary_events(P, G, p, step, acc);
+    p.id = -1; p.slot = i; p.alive = true; p.mode_changed = false; p.occ_changed = false;
+    return i;
+}
+__device__ __forceinline__ void nk_finish_hit(const NkP& P, double* acc, long long i, int mode_in, const NkParticle& p, bool with_flux) {
     if (p.alive) {
-        nk_store_particle(P, i, p);
+        nk_store_after_events(P, i, p);
         nk_accumulate(P, acc, p, with_flux);
     } else {
-        nk_kill(P, acc, i);
+        nk_kill(P, acc, i, mode_in);
     }
+}
+// One hit-list entry: the boundary event loop of an existing particle.
+__device__ __forceinline__ void nk_hit_entry(const NkP& P, const NkGeo& G, double* acc, unsigned int w, long long step, bool with_flux) {
+    NkParticle p;
+    const long long i = nk_load_hit(P, w, p);
+    const int mode_in = p.mode;
+    nk_boundary_events(P, G, p, step, acc);
+    nk_finish_hit(P, acc, i, mode_in, p, with_flux);
 }
 
 // coef = rbf_w . T (T may live in shared memory); all threads of the block take rows
@@ -290,7 +348,7 @@ __device__ void nk_finalize_block(const NkP& P, double* sm) {
 // all ranks get bit-identical sums without a separate collective launch.  Two mailbox parities: a rank can be
 // at most one step ahead of the slowest one.  The wait is bounded (~20 s): a missing peer raises NK_ERR_COMM
 // instead of hanging the GPU.
-__device__ void nk_exchange_sums(const NkP& P) {
+__device__ bool nk_exchange_sums(const NkP& P) {
     // message of a rank: the 128-bit fixed-point sums {lo, hi} of every accumulator entry, then the f64 side bins.  The
     // integer parts are added exactly, so the world totals -- and with them T_sv -- do not depend on how the particles
     // are spread over the ranks: a sharded run repeats the single-GPU run bit for bit.
@@ -306,6 +364,7 @@ __device__ void nk_exchange_sums(const NkP& P) {
     }
     __threadfence_system();
     __syncthreads();
+    int timed_out = 0;
     if ((int)threadIdx.x < W) {
         volatile unsigned long long* f = P.peer_flags[threadIdx.x] + (size_t)par * W + P.rank;
         *f = seq;
@@ -313,10 +372,11 @@ __device__ void nk_exchange_sums(const NkP& P) {
         volatile unsigned long long* mine = P.flags_local + (size_t)par * W + threadIdx.x;
         const long long t0 = clock64();
         while (*mine != seq) {
-            if (clock64() - t0 > 40000000000LL) { atomicOr(&P.dyn->error, NK_ERR_COMM); break; }   // ~20 s
+            if (clock64() - t0 > 40000000000LL) { atomicOr(&P.dyn->error, NK_ERR_COMM); timed_out = 1; break; }   // ~20 s
         }
     }
-    __syncthreads();
+    // a missing peer freezes the step (no temperatures from incomplete sums); the sticky error bit reaches the host
+    if (__syncthreads_or(timed_out)) return false;
     __threadfence_system();
     const volatile unsigned long long* box = reinterpret_cast<const volatile unsigned long long*>(P.mbox_local) + (size_t)par * W * stride;
     for (int i = threadIdx.x; i < len; i += blockDim.x) {
@@ -335,6 +395,7 @@ __device__ void nk_exchange_sums(const NkP& P) {
     }
     __threadfence();
     __syncthreads();
+    return true;
 }
 
 __global__ void __launch_bounds__(1024) k_finalize(NkP P) {
@@ -344,15 +405,60 @@ __global__ void __launch_bounds__(1024) k_finalize(NkP P) {
 
 // ---- the rare path of a step: boundary events of the hit list + reservoir emission -----------------------------
 // Work items [0, n_hits) are existing particles whose collision falls inside the step, [n_hits, n_hits + n_emit)
-// are emission-list entries.  One thread per item; triangles staged in shared memory when they fit.  With
-// FUSE the last block to finish closes the step (single-GPU path: no collective between the two halves).
+// are emission-list entries.  With FUSE the last block to finish closes the step (single-GPU path, or the in-kernel
+// exchange: no collective launch between the two halves).
+//   k_rare        meshes of at most NK_RARE_FACES triangles: they are staged in shared memory once per block and every
+//                 thread runs the event loop of its item on its own.
+//   k_rare_tiled  larger meshes: the threads of a block advance their items in lock step -- everybody runs until it
+//                 needs a ray (or is done), then the block sweeps the triangle tiles together (nk_tiles.cuh) -- so a
+//                 tile is fetched once per block and round instead of once per ray.
 #define NK_RARE_THREADS 128
 #define NK_RARE_FACES 128
 #define NK_RARE_FACETS 64
-template <bool FUSE>
 #ifndef NK_RARE_MIN_BLOCKS
 #define NK_RARE_MIN_BLOCKS 4
 #endif
+
+// merge of a block's private accumulators + the closing protocol shared by both kernels
+__device__ __forceinline__ void nk_rare_merge(const NkP& P, const double* racc, const long long* rq) {
+    const int nacc = nk_acc_len(P.S, P.R);
+    for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
+        nk_gacc_add(P.acc_q + 2 * k, rq[k]);
+        if (racc[k] != 0.0) atomicAdd(P.acc + k, racc[k]);
+    }
+    if (threadIdx.x == 0) {
+        // live count: + particles that got a slot (emitted - absorbed on arrival) - absorbed
+        const double d = (double)(rq[NK_ACC_NEMIT(P.S, P.R)] - rq[NK_ACC_NABS(P.S, P.R)]);
+        if (d != 0.0) atomicAdd((unsigned long long*)&P.dyn->n_alive, (unsigned long long)(long long)d);
+    }
+}
+template <bool FUSE>
+__device__ __forceinline__ void nk_rare_close(const NkP& P, double* sm_fin, int* s_last) {
+    // the last block to finish turns the fixed-point sums into the f64 accumulator vector; with FUSE it also closes the step
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(&P.dyn->blocks_done, 1u);
+        *s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (*s_last) {
+        __threadfence();
+        if (FUSE && P.comm_on) {
+            if (!nk_exchange_sums(P)) { if (threadIdx.x == 0) P.dyn->blocks_done = 0; return; }     // world totals, still in fixed point
+        }
+        nk_gacc_to_f64(P);
+        __threadfence();
+        __syncthreads();
+        if (!FUSE) { if (threadIdx.x == 0) P.dyn->blocks_done = 0; return; }
+        if (P.trace && threadIdx.x == 0) P.trace[4] = nk_globaltimer();
+        nk_finalize_block(P, sm_fin);
+        __syncthreads();
+        if (P.trace && threadIdx.x == 0) P.trace[5] = nk_globaltimer();
+    }
+}
+
+template <bool FUSE>
 __global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(NkP P) {
     __shared__ NkFace sfaces[NK_RARE_FACES];
     __shared__ int sfi[4 * NK_RARE_FACETS];
@@ -392,51 +498,124 @@ __global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(Nk
         const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
         for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < nh + ne; w += gridDim.x * blockDim.x) {
             if (w < nh) {
-                nk_hit_entry(P, G, racc, P.hitlist[w], step, with_flux);
+                nk_hit_entry(P, G, racc, w, step, with_flux);
             } else {
                 if (P.res_gen == NK_RESGEN_ONE_TO_ONE) {
                     nk_emit_one_to_one(P, G, racc, (long long)(w - nh), step, with_flux);
                 } else {
                     const int2 e = P.emitlist[w - nh];
-                    nk_emit_entry(P, G, racc, e.x >> 8, e.y, e.x & 0xff, step, with_flux);
+                    nk_emit_entry(P, G, racc, e.x >> 16, e.y, e.x & 0xff, (unsigned int)((e.x >> 8) & 0xff), step, with_flux);
                 }
             }
         }
         __syncthreads();
         NK_TRACE_MARK_MAX(P, 3);
-        for (int k = threadIdx.x; k < nacc; k += blockDim.x)
-        {
-            nk_gacc_add(P.acc_q + 2 * k, rq[k]);
-            if (racc[k] != 0.0) atomicAdd(P.acc + k, racc[k]);
-        }
-        if (threadIdx.x == 0) {
-            // live count: + particles that got a slot (emitted - absorbed on arrival) - absorbed
-            const double d = (double)(rq[NK_ACC_NEMIT(P.S, P.R)] - rq[NK_ACC_NABS(P.S, P.R)]);
-            if (d != 0.0) atomicAdd((unsigned long long*)&P.dyn->n_alive, (unsigned long long)(long long)d);
-        }
+        nk_rare_merge(P, racc, rq);
     }
-    {
-        // the last block to finish turns the fixed-point sums into the f64 accumulator vector; with FUSE it also closes the step
+    nk_rare_close<FUSE>(P, sm_fin, &s_last);
+}
+
+// The same work with block-cooperative triangle tiles.  Dynamic shared memory: NK_TILE_SMEM_BYTES for the tile pipeline,
+// then the closing block's scratch + this block's private accumulators (as k_rare).
+#define NK_ITEM_DONE 0
+#define NK_ITEM_EMIT_NEXT 1      // emission entry: pick the next copy that belongs to this rank
+#define NK_ITEM_EMIT_RAY 2       // waiting for the first-collision ray of a new particle
+#define NK_ITEM_EVENTS 3         // inside the boundary event loop
+template <bool FUSE>
+__global__ void __launch_bounds__(NK_RARE_THREADS, 2) k_rare_tiled(NkP P) {
+    extern __shared__ __align__(128) unsigned char rare_smem[];
+    __shared__ int s_last;
+    double* sm_fin = reinterpret_cast<double*>(rare_smem + NK_TILE_SMEM_BYTES);
+    NkGeo G;
+    G.faces = P.faces; G.bc = P.facet_bc; G.partner = P.facet_partner; G.res = P.facet_res; G.rough = P.facet_rough;
+    G.normal = P.facet_normal; G.centroid = P.facet_centroid;
+    NK_TRACE_MARK_FIRST(P, 2);
+    const bool has_work = (unsigned long long)blockIdx.x * blockDim.x < (unsigned long long)P.dyn->n_hits + P.dyn->n_emit;
+    if (has_work) {
+        NkTilePipe tp;
+        nk_tiles_init(tp, rare_smem, P);
+        double* racc = sm_fin + 3 * P.S;
+        const int nacc = nk_acc_len(P.S, P.R);
+        long long* rq = reinterpret_cast<long long*>(racc + nacc);
+        for (int k = threadIdx.x; k < nacc; k += blockDim.x) { racc[k] = 0.0; rq[k] = 0; }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            const unsigned int t = atomicAdd(&P.dyn->blocks_done, 1u);
-            s_last = (t == gridDim.x - 1);
+        const unsigned int nh = P.dyn->n_hits, ne = P.dyn->n_emit;
+        const long long step = P.dyn->step;
+        const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
+        for (unsigned int w0 = blockIdx.x * blockDim.x; w0 < nh + ne; w0 += gridDim.x * blockDim.x) {     // block-uniform
+            const unsigned int w = w0 + threadIdx.x;
+            NkParticle p;
+            NkEvState st;
+            int phase = NK_ITEM_DONE, kind = 0;           // kind 1: hit, 2: emission entry, 3: one_to_one particle
+            long long slot_i = -1; int mode_in = -1;
+            int r = 0, m = 0, c = 0; unsigned int fire = 0;
+            double dt_in = 0.0, x0 = 0.0, y0 = 0.0, z0 = 0.0;
+            p.alive = false; p.x = p.y = p.z = p.vx = p.vy = p.vz = 0.0;
+            if (w < nh) {
+                kind = 1;
+                slot_i = nk_load_hit(P, w, p);
+                mode_in = p.mode;
+                nk_event_begin(p, st);
+                phase = NK_ITEM_EVENTS;
+            } else if (w < nh + ne) {
+                if (P.res_gen == NK_RESGEN_ONE_TO_ONE) {
+                    kind = 3;
+                    long long id; double uface, us, ur;
+                    if (nk_one_to_one_draws(P, (long long)(w - nh), step, r, m, id, dt_in, uface, us, ur)) {
+                        nk_emit_setup(P, r, m, id, uface, us, ur, p, x0, y0, z0);
+                        phase = NK_ITEM_EMIT_RAY;
+                    }
+                } else {
+                    kind = 2;
+                    const int2 e = P.emitlist[w - nh];
+                    r = e.x >> 16; m = e.y; c = e.x & 0xff; fire = (unsigned int)((e.x >> 8) & 0xff);
+                    phase = NK_ITEM_EMIT_NEXT;
+                }
+            }
+            for (;;) {
+                // every thread runs until its item needs a ray or is finished
+                bool need = false;
+                while (phase != NK_ITEM_DONE && !need) {
+                    if (phase == NK_ITEM_EMIT_NEXT) {
+                        while (c >= 1 && P.world > 1 && nk_emit_owner(P, m, fire, c - 1) != P.rank) --c;
+                        if (c < 1) { phase = NK_ITEM_DONE; break; }
+                        long long id; double uface, us, ur;
+                        nk_emit_copy_draws(P, r, m, c, step, id, dt_in, uface, us, ur);
+                        nk_emit_setup(P, r, m, id, uface, us, ur, p, x0, y0, z0);
+                        phase = NK_ITEM_EMIT_RAY;
+                        need = true;
+                    } else if (phase == NK_ITEM_EMIT_RAY) {
+                        need = true;
+                    } else {                                   // NK_ITEM_EVENTS
+                        if (nk_event_advance(P, G, p, st, step, racc)) { need = true; break; }
+                        if (kind == 1) { nk_finish_hit(P, racc, slot_i, mode_in, p, with_flux); phase = NK_ITEM_DONE; }
+                        else {
+                            nk_emit_finish(P, racc, p, with_flux);
+                            if (kind == 2) { --c; phase = NK_ITEM_EMIT_NEXT; } else phase = NK_ITEM_DONE;
+                        }
+                    }
+                }
+                if (!__syncthreads_or(need ? 1 : 0)) break;
+                double tb = CUDART_INF; int fb = -1;
+                nk_tiles_sweep(tp, P, need, p.x, p.y, p.z, p.vx, p.vy, p.vz, tb, fb);
+                if (need) {
+                    if (phase == NK_ITEM_EMIT_RAY) {
+                        if (nk_emit_post(P, racc, r, dt_in, x0, y0, z0, tb, fb, p)) { nk_event_begin(p, st); phase = NK_ITEM_EVENTS; }
+                        else {
+                            nk_emit_finish(P, racc, p, with_flux);
+                            if (kind == 2) { --c; phase = NK_ITEM_EMIT_NEXT; } else phase = NK_ITEM_DONE;
+                        }
+                    } else {
+                        nk_event_ray_done(P, p, st, tb, fb);
+                    }
+                }
+            }
         }
         __syncthreads();
-        if (s_last) {
-            __threadfence();
-            if (FUSE && P.comm_on) nk_exchange_sums(P);       // world totals, still in fixed point
-            nk_gacc_to_f64(P);
-            __threadfence();
-            __syncthreads();
-            if (!FUSE) { if (threadIdx.x == 0) P.dyn->blocks_done = 0; return; }
-            if (P.trace && threadIdx.x == 0) P.trace[4] = nk_globaltimer();
-            nk_finalize_block(P, sm_fin);
-            __syncthreads();
-            if (P.trace && threadIdx.x == 0) P.trace[5] = nk_globaltimer();
-        }
+        NK_TRACE_MARK_MAX(P, 3);
+        nk_rare_merge(P, racc, rq);
     }
+    nk_rare_close<FUSE>(P, sm_fin, &s_last);
 }
 
 // apply the deferred lifetime_scattering so that `occ` is what the reference holds after run_timestep

@@ -1,6 +1,6 @@
 // nk_stream.cuh -- the streaming kernel of a timestep: relaxation, drift, binning (direct and table variants)
-// Part of the single translation unit nk_kernels.cu (included in this order: nk_ops.cuh, nk_stream.cuh,
-// nk_stream_variants.cuh, nk_rare.cuh, nk_hostpipe.cuh); see DESIGN.md section 4.
+// Part of the single translation unit nk_kernels.cu (included in this order: nk_tiles.cuh, nk_ops.cuh, nk_stream.cuh,
+// nk_rare.cuh, nk_sort.cuh, nk_hostpipe.cuh); see DESIGN.md section 4.
 #pragma once
 
 // ---- the streaming kernel ----------------------------------------------------------------------------
@@ -22,15 +22,6 @@
 #ifndef NK_STEP_MIN_BLOCKS
 #define NK_STEP_MIN_BLOCKS 4
 #endif
-
-// Newton-refined reciprocal of a positive normal double (<= 2 ulp): MUFU.RCP64H + 4 DFMA, no branch
-__device__ __forceinline__ double nk_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(fma(-x, r, 1.0), r, r);
-    r = fma(fma(-x, r, 1.0), r, r);
-    return r;
-}
 
 // Branch-free exp for the occupation arithmetic: argument clamped to [-708, 709] (results there are
 // ~1e-308 / ~1e308, i.e. 0 / inf for every use below), Cody-Waite reduction, degree-13 Taylor polynomial on
@@ -180,9 +171,14 @@ __device__ __forceinline__ long long nk_one_to_one_share(const NkP& P, int r) {
     return n > P.rank ? (n - P.rank + P.world - 1) / P.world : 0;
 }
 
+// which rank injects copy `k` (0-based) of a table entry that has emitted `fire` particles before this step
+__device__ __forceinline__ int nk_emit_owner(const NkP& P, int m, unsigned int fire, int k) {
+    return (int)((fire + (unsigned int)k + (unsigned int)m) % (unsigned int)P.world);
+}
+
 __device__ __forceinline__ void nk_emit_scan(const NkP& P) {
     // free-slot rings: slots freed in the previous step become recyclable, over-claims of exhausted rings are dropped
-    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b <= P.fr_B; b += (long long)gridDim.x * blockDim.x) {
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < P.n_rings; b += (long long)gridDim.x * blockDim.x) {
         long long* c = P.fr_ctr + 3 * b;
         const long long tail = c[1];
         if (c[0] > c[2]) c[0] = c[2];
@@ -198,13 +194,15 @@ __device__ __forceinline__ void nk_emit_scan(const NkP& P) {
         }
         return;
     }
-    const int mspan = P.emit_m_hi - P.emit_m_lo;
-    const long long total = (long long)P.R * mspan;
+    // Every rank advances the WHOLE table (identical on all ranks) and keeps the entries of which it owns at least one copy:
+    // copies are dealt round-robin per entry (nk_emit_owner), so each rank injects 1/world of every mode and its per-mode
+    // particle numbers stay in balance with what it absorbs.
+    const long long total = (long long)P.R * P.M;
     const long long step = P.dyn->step;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(e / mspan);
-        const int m = P.emit_m_lo + (int)(e % mspan);
-        const size_t idx = (size_t)r * P.M + m;
+        const int r = (int)(e / P.M);
+        const int m = (int)(e % P.M);
+        const size_t idx = (size_t)e;
         const double prob = P.enter_prob[idx];
         const double fixed = floor(prob);
         int extra;
@@ -223,8 +221,13 @@ __device__ __forceinline__ void nk_emit_scan(const NkP& P) {
         int n_new = (int)fixed + extra;
         if (n_new == 0) continue;
         if (n_new > NK_EMIT_CMAX) { atomicOr(&P.dyn->error, NK_ERR_CMAX); n_new = NK_EMIT_CMAX; }
+        const unsigned int fire = P.res_fire[idx];
+        P.res_fire[idx] = (unsigned char)(fire + (unsigned int)n_new);
+        bool mine = P.world == 1 || n_new >= P.world;
+        for (int k = 0; !mine && k < n_new; ++k) mine = nk_emit_owner(P, m, fire, k) == P.rank;
+        if (!mine) continue;
         const unsigned int k = atomicAdd(&P.dyn->n_emit, 1u);
-        P.emitlist[k] = make_int2((r << 8) | n_new, m);
+        P.emitlist[k] = make_int2((r << 16) | ((int)fire << 8) | n_new, m);
     }
 }
 
@@ -273,8 +276,18 @@ __device__ __forceinline__ bool nk_step_particle(const NkP& P, const NkSvSmem& s
     return false;
 }
 
-// warp-aggregated append of up to two slots per lane to the hit list (full-mask votes: call converged)
-__device__ __forceinline__ void nk_push_hits(const NkP& P, unsigned int lane, bool h0, bool h1, long long base) {
+// warp-aggregated append of up to two slots per lane to the hit list (full-mask votes: call converged).  The first
+// hitrec_cap entries of a step also get a dense 64-byte record of what this thread holds in registers, so that the rare
+// path reads its input coalesced; entries beyond that are re-read from the particle arrays (written below as usual).
+__device__ __forceinline__ void nk_write_hitrec(const NkP& P, unsigned int pos, int slot, double x, double y, double z, double tc, double occ,
+                                                int mode, int omode) {
+    if ((long long)pos >= P.hitrec_cap) return;
+    double4* r = reinterpret_cast<double4*>(P.hitrec + pos);
+    r[0] = make_double4(x, y, z, tc);
+    r[1] = make_double4(occ, __hiloint2double(mode, slot), __hiloint2double(0, omode), 0.0);
+}
+__device__ __forceinline__ void nk_push_hits(const NkP& P, unsigned int lane, bool h0, bool h1, long long base, const double2& X, const double2& Y,
+                                             const double2& Z, const double2& TC, const double2& OC, const int2& MD, const int2& OM) {
     const unsigned int m0 = __ballot_sync(0xffffffffu, h0);
     const unsigned int m1 = __ballot_sync(0xffffffffu, h1);
     if (m0 | m1) {
@@ -282,8 +295,16 @@ __device__ __forceinline__ void nk_push_hits(const NkP& P, unsigned int lane, bo
         if (lane == 0) pos = atomicAdd(&P.dyn->n_hits, __popc(m0) + __popc(m1));
         pos = __shfl_sync(0xffffffffu, pos, 0);
         const unsigned int below = (1u << lane) - 1u;
-        if (h0) P.hitlist[pos + __popc(m0 & below)] = (int)base;
-        if (h1) P.hitlist[pos + __popc(m0) + __popc(m1 & below)] = (int)(base + 1);
+        if (h0) {
+            const unsigned int k = pos + __popc(m0 & below);
+            P.hitlist[k] = (int)base;
+            nk_write_hitrec(P, k, (int)base, X.x, Y.x, Z.x, TC.x, OC.x, MD.x, OM.x);
+        }
+        if (h1) {
+            const unsigned int k = pos + __popc(m0) + __popc(m1 & below);
+            P.hitlist[k] = (int)(base + 1);
+            nk_write_hitrec(P, k, (int)(base + 1), X.y, Y.y, Z.y, TC.y, OC.y, MD.y, OM.y);
+        }
     }
 }
 
@@ -347,7 +368,7 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step(Nk
         bool h0 = false, h1 = false;
         if (base < n && MD.x >= 0) h0 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.x, OM.x, X.x, Y.x, Z.x, TC.x, OC.x);
         if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.y, OM.y, X.y, Y.y, Z.y, TC.y, OC.y);
-        nk_push_hits(P, lane, h0, h1, base);
+        nk_push_hits(P, lane, h0, h1, base, X, Y, Z, TC, OC, MD, OM);
         if (inb) {
             *reinterpret_cast<double2*>(P.px + base) = X;
             *reinterpret_cast<double2*>(P.py + base) = Y;
@@ -473,7 +494,7 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step_ta
         bool h0 = false, h1 = false;
         if (base < n && MD.x >= 0) h0 = nk_step_particle_tab<HAS_ROUGH, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.x, OM.x, X.x, Y.x, Z.x, TC.x, OC.x);
         if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle_tab<HAS_ROUGH, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.y, OM.y, X.y, Y.y, Z.y, TC.y, OC.y);
-        nk_push_hits(P, lane, h0, h1, base);
+        nk_push_hits(P, lane, h0, h1, base, X, Y, Z, TC, OC, MD, OM);
         if (inb) {
             *reinterpret_cast<double2*>(P.px + base) = X;
             *reinterpret_cast<double2*>(P.py + base) = Y;
@@ -485,4 +506,22 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step_ta
     __syncthreads();
     nk_flush_bins<FLUX>(P, binE, binF, binX, binC);
     NK_TRACE_MARK_MAX(P, 1);
+}
+
+
+// ---- launch-uniform variants: RELAX (a deferred relaxation is pending), FLUX (convergence step), rough walls present ----
+typedef void (*nk_step_fn)(NkP);
+template <bool TAB, bool A, bool B, bool C, bool D>
+static nk_step_fn nk_pick5() { return TAB ? (nk_step_fn)k_step_tab<A, B, C, D> : (nk_step_fn)k_step<A, B, C, D>; }
+template <bool TAB, bool A, bool B, bool C>
+static nk_step_fn nk_pick4(bool d) { return d ? nk_pick5<TAB, A, B, C, true>() : nk_pick5<TAB, A, B, C, false>(); }
+template <bool TAB, bool A, bool B>
+static nk_step_fn nk_pick3(bool c, bool d) { return c ? nk_pick4<TAB, A, B, true>(d) : nk_pick4<TAB, A, B, false>(d); }
+template <bool TAB, bool A>
+static nk_step_fn nk_pick2(bool b, bool c, bool d) { return b ? nk_pick3<TAB, A, true>(c, d) : nk_pick3<TAB, A, false>(c, d); }
+template <bool TAB>
+static nk_step_fn nk_pick1(bool a, bool b, bool c, bool d) { return a ? nk_pick2<TAB, true>(b, c, d) : nk_pick2<TAB, false>(b, c, d); }
+// variant 4 = per-(mode, subvolume) tables (needs FAST), 0 = direct
+static nk_step_fn nk_pick_step(int variant, bool rough, bool fast, bool relax, bool flux) {
+    return variant == 4 ? nk_pick1<true>(rough, true, relax, flux) : nk_pick1<false>(rough, fast, relax, flux);
 }

@@ -1,0 +1,100 @@
+// nk_tiles.cuh -- block-cooperative triangle tiles for Mesh.find_boundary (Mesh.py:806-856) on large meshes
+// Part of the single translation unit nk_kernels.cu (included in this order: nk_tiles.cuh, nk_ops.cuh, nk_stream.cuh,
+// nk_rare.cuh, nk_sort.cuh, nk_hostpipe.cuh); see DESIGN.md section 4.
+//
+// The reference intersects P rays with all F triangles through dense (P, F) temporaries (Population.py:810 chunks P).
+// Here the rays of a block keep their running minimum in registers while the triangles stream through shared memory in
+// tiles of NK_TILE_FACES records (160 B each), staged by the bulk async-copy engine (cp.async.bulk, SASS UBLKCP) into two
+// stages guarded by one mbarrier each: the copy of tile t+1 overlaps the sweep of tile t.  Every thread reads the same
+// triangle at the same time (shared-memory broadcast), so the kernel is bound by the FP64 pipe: 11 DADD/DMUL per
+// (ray, triangle) for the plane test plus a reciprocal-based filter that keeps the IEEE division for the few candidates
+// that can still beat the running minimum (nk_ray_faces).  A mesh of at most one tile is loaded once per block and stays
+// resident.  Tiles are swept in face order with a strict `<`, so ties resolve to the lowest face index like np.argmax.
+#pragma once
+
+#define NK_TILE_FACES 128
+#define NK_TILE_STAGE_BYTES (NK_TILE_FACES * (int)sizeof(NkFace))           // 20 KB
+#define NK_TILE_SMEM_BYTES (2 * NK_TILE_STAGE_BYTES + 128)                  // two stages + the mbarriers
+
+__device__ __forceinline__ unsigned int nk_smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void nk_mbar_init(void* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nk_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void nk_mbar_expect_tx(void* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nk_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void nk_mbar_wait(void* bar, unsigned int parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "NK_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra NK_DONE_%=;\n\t"
+        "bra NK_WAIT_%=;\n\t"
+        "NK_DONE_%=:\n\t}" ::"r"(nk_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void nk_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned int bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(nk_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(nk_smem_u32(bar)) : "memory");
+}
+
+struct NkTilePipe {
+    NkFace* buf;                     // two stages of NK_TILE_FACES faces (128-byte aligned shared memory)
+    unsigned long long* bar;         // one mbarrier per stage
+    unsigned int parity0, parity1;   // phase parities of the two stages (same value in every thread of the block)
+    bool resident;                   // the whole mesh fits stage 0 and has been loaded
+};
+
+__device__ __forceinline__ void nk_tile_issue(const NkTilePipe& tp, const NkP& P, int stage, int tile) {
+    const int f0 = tile * NK_TILE_FACES;
+    const unsigned int bytes = (unsigned int)(min(NK_TILE_FACES, P.F - f0) * (int)sizeof(NkFace));
+    nk_mbar_expect_tx(&tp.bar[stage], bytes);
+    nk_bulk_g2s(tp.buf + (size_t)stage * NK_TILE_FACES, P.faces + f0, bytes, &tp.bar[stage]);
+}
+
+// `smem` points to NK_TILE_SMEM_BYTES of 128-byte aligned shared memory.  Every thread of the block calls this once.
+__device__ __forceinline__ void nk_tiles_init(NkTilePipe& tp, unsigned char* smem, const NkP& P) {
+    tp.buf = reinterpret_cast<NkFace*>(smem);
+    tp.bar = reinterpret_cast<unsigned long long*>(smem + 2 * NK_TILE_STAGE_BYTES);
+    tp.parity0 = tp.parity1 = 0u;
+    tp.resident = false;
+    if (threadIdx.x == 0) {
+        nk_mbar_init(&tp.bar[0], 1);
+        nk_mbar_init(&tp.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (P.F <= NK_TILE_FACES) {
+        if (P.F > 0) {
+            if (threadIdx.x == 0) nk_tile_issue(tp, P, 0, 0);
+            nk_mbar_wait(&tp.bar[0], 0u);
+            tp.parity0 = 1u;
+        }
+        tp.resident = true;
+    }
+}
+
+// All threads of the block call this together; threads with need == false only help to keep the pipeline moving.
+__device__ __forceinline__ void nk_tiles_sweep(NkTilePipe& tp, const NkP& P, bool need, double x, double y, double z,
+                                               double vx, double vy, double vz, double& tbest, int& fbest) {
+    if (tp.resident) {
+        if (need) nk_ray_faces(tp.buf, P.F, x, y, z, vx, vy, vz, tbest, fbest);
+        return;
+    }
+    const int F = P.F, nt = (F + NK_TILE_FACES - 1) / NK_TILE_FACES;
+    __syncthreads();                                 // the readers of the previous sweep are done with both stages
+    if (threadIdx.x == 0) {
+        nk_tile_issue(tp, P, 0, 0);
+        if (nt > 1) nk_tile_issue(tp, P, 1, 1);
+    }
+    for (int t = 0; t < nt; ++t) {
+        const int b = t & 1;
+        nk_mbar_wait(&tp.bar[b], b ? tp.parity1 : tp.parity0);
+        if (b) tp.parity1 ^= 1u; else tp.parity0 ^= 1u;
+        if (need) nk_ray_faces(tp.buf + (size_t)b * NK_TILE_FACES, min(NK_TILE_FACES, F - t * NK_TILE_FACES), x, y, z, vx, vy, vz, tbest, fbest);
+        if (t + 2 < nt) {
+            __syncthreads();                         // everybody has left stage b: refill it
+            if (threadIdx.x == 0) nk_tile_issue(tp, P, b, t + 2);
+        }
+    }
+}

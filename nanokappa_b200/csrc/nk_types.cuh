@@ -37,6 +37,16 @@ struct __align__(64) NkModeHot {
     double t[4];
 };
 
+// Dense hit record: what the streaming kernel holds in registers when a particle's collision falls inside the step.
+// The rare path reads these 64 B coalesced instead of gathering seven scattered sectors per hit.
+struct __align__(32) NkHitRec {
+    double x, y, z, tc;          // position after the drift, clock after the decrement (< 0)
+    double occ;                  // occupation after the deferred relaxation
+    int slot, mode;
+    int omode, pad0;
+    double pad1;
+};
+
 struct alignas(128) NkDyn {      // device-resident, mutated by kernels
     // line 0: fields touched once per block or once per step
     long long fr_snap;           // free-slot ring: fr_tail at the end of the previous step (pop limit)
@@ -110,7 +120,8 @@ struct NkP {
     unsigned int seed_lo, seed_hi;
     // ---- reservoirs
     int R; const int* res_facet; const double* res_T; const double* enter_prob; double* res_counter;
-    int emit_m_lo, emit_m_hi;         // this rank's share of every reservoir's mode table
+    unsigned char* res_fire;          // (R, M) particles emitted so far by each table entry (mod 256): copy k of an entry
+                                      // belongs to rank (fire + k + mode) % world, so every rank injects 1/world of EVERY mode
     int res_gen;                      // NK_RESGEN_* (--reservoir_gen)
     double* emit_u;                   // (R, M) this step's dice (fixed_rate)
     const double* res_roulette;       // (R, M) cumsum(enter_prob[r]) / max (one_to_one)
@@ -126,13 +137,14 @@ struct NkP {
     long long* pid;
     // ---- scratch owned by the ctx
     int* hitlist; int* freelist;
-    // Free slots are kept in rings with counters {head, tail, snap} in fr_ctr: one global ring (index fr_B, entries
-    // freelist[fr_B * fr_bsize ...], capacity cap) and, once the host has ordered the particles by mode and published where
-    // each mode lives (nk_set_mode_slots), fr_B bucket rings of fr_bsize consecutive slots each (ring b = freelist[b * fr_bsize,
-    // (b + 1) * fr_bsize)) for the ordered region [0, fr_sorted).  A new particle of mode m takes a slot from the bucket of
-    // its mode (mode_bucket[m]) or a neighbour, so the mode order -- and with it the locality of the mode-table gathers --
-    // survives emission and absorption; slots beyond the ordered region recycle through the global ring.
-    long long* fr_ctr; int fr_B; int fr_bsize; const int* mode_bucket; long long fr_sorted;
+    // Free slots are kept in rings with counters {head, tail, snap} in fr_ctr.  Ring 0 is the global ring (entries
+    // freelist[cap, 2 cap)).  Once nk_sort_by_mode has ordered the particles by mode (fr_sorted > 0) every mode m owns the
+    // slot region [mode_first[m], mode_first[m+1]) -- its live particles followed by a few spare slots -- and ring 1 + m
+    // (entries freelist[mode_first[m], mode_first[m+1])) recycles exactly those slots: an absorbed particle frees a slot of
+    // its region, the next emitted particle of that mode takes it, so the order by mode -- and with it the locality of the
+    // mode-table gathers -- survives emission and absorption.  Slots beyond fr_sorted recycle through the global ring.
+    long long* fr_ctr; int n_rings; const int* mode_first; long long fr_sorted;
+    NkHitRec* hitrec; long long hitrec_cap;   // dense records of the first hitrec_cap hit-list entries of a step
     int2* emitlist;                   // (R*M) {reservoir << 8 | copies, mode} of the entries emitting this step
     int* newslots; long long newslots_cap;   // slots that received an emitted particle in this step
     long long slot_lo, slot_hi;       // slot range the streaming kernel covers in this launch (chunked host pipeline)

@@ -154,6 +154,7 @@ class Engine:
                                                  _dp(t["occ"]), _dp(t["mode"]), _dp(t["omode"]), _dp(t["cfacet"]),
                                                  _dp(t["cx"]), _dp(t["cy"]), _dp(t["cz"]), _dp(t["pid"])), "nk_bind_particles")
         self.cap = cap
+        self.t_back = None
 
     def load_particles(self, positions, modes_flat, occupation, ids=None, omodes=None,
                        n_timesteps=None, collision_facets=None, collision_positions=None):
@@ -179,28 +180,34 @@ class Engine:
         if n_timesteps is None:
             self.init_collisions()
 
-    def sort_by_mode(self):
-        """Maintenance pass (not part of a timestep): compact the slots and order the live particles by
-        mode index, so that the 64-byte mode-record gathers of neighbouring lanes hit the same cache line.
-        Sums are order independent; particle identity is carried by `pid`.  Drops the free list."""
-        n, _ = self.slot_count()
+    FIELDS = ("px", "py", "pz", "tc", "occ", "mode", "omode", "cfacet", "cx", "cy", "cz", "pid")
+
+    def sort_by_mode(self, pools=None):
+        """Maintenance pass (not part of a timestep): compact the slots and order the live particles by mode
+        index with the library's counting sort (``nk_sort_by_mode``: one fused pass over all twelve fields into
+        a second set of arrays, which then become the bound ones), so that the 64-byte mode-record gathers of
+        neighbouring lanes hit the same cache line.  ``pools`` (default: on when there are >= NK_POOL_MIN = 64
+        particles per occupied mode): every mode region keeps a few spare slots and its own free-slot ring, so
+        emitted particles land among their own mode and the order survives emission / absorption; ``pools=False``
+        gives the plain compaction (live particles in [0, n_live)).  Sums are order independent; particle identity
+        is carried by ``pid``."""
+        import os
+        n, alive = self.slot_count()
         if n == 0:
             return
-        t = self.t
-        mode = t["mode"][:n]
-        key = torch.where(mode >= 0, mode, torch.full_like(mode, 2 ** 31 - 1))
-        perm = torch.argsort(key, stable=True)
-        n_live = int((mode >= 0).sum().item())
-        for k in ("px", "py", "pz", "tc", "occ", "mode", "omode", "cfacet", "cx", "cy", "cz", "pid"):
-            t[k][:n] = t[k][:n][perm]
-        del perm, key
-        t["mode"][n_live:n] = -1
-        torch.cuda.synchronize(self.device)
-        check(self.ctx, self.L.nk_set_slot_count(self.ctx, n_live), "nk_set_slot_count")
-        # where each mode lives now: emitted particles will be placed next to their own mode (nk_set_mode_slots)
-        first = torch.searchsorted(t["mode"][:n_live].contiguous(), torch.arange(self.M, device=self.device, dtype=torch.int32))
-        first = np.ascontiguousarray(first.cpu().numpy().astype(np.int64))
-        check(self.ctx, self.L.nk_set_mode_slots(self.ctx, first.ctypes.data_as(C.c_void_p)), "nk_set_mode_slots")
+        if getattr(self, "t_back", None) is None or self.t_back["px"].numel() != self.cap:
+            dev = self.device
+            self.t_back = {k: torch.empty_like(v) for k, v in self.t.items()}
+        frac, fixed = 0.0, 0
+        if pools is None:
+            pools = os.environ.get("NK_MODE_POOLS", "1") != "0" and alive >= int(os.environ.get("NK_POOL_MIN", 64)) * max(self.M, 1)
+        if pools:
+            frac = float(os.environ.get("NK_POOL_FRAC", 0.01)); fixed = int(os.environ.get("NK_POOL_FIXED", 2))
+        b = self.t_back
+        ns, na = C.c_int64(), C.c_int64()
+        check(self.ctx, self.L.nk_sort_by_mode(self.ctx, *[_dp(b[k]) for k in self.FIELDS], frac, fixed, C.byref(ns), C.byref(na)),
+              "nk_sort_by_mode")
+        self.t, self.t_back = self.t_back, self.t
 
     def set_sv_temperature(self, T):
         T = _f64(T)
@@ -234,6 +241,10 @@ class Engine:
         check(self.ctx, self.L.nk_profile_end(self.ctx, ms, C.byref(n)), "nk_profile_end")
         return dict(k_step=ms[0], k_rare=ms[1], k_finalize=ms[2]), n.value
 
+    def last_step_variant(self):
+        """0 direct / 4 table streaming kernel, + 8 if the rare path used triangle tiles (nk_last_step_variant)."""
+        return int(self.L.nk_last_step_variant(self.ctx))
+
     def synchronize(self):
         check(self.ctx, self.L.nk_synchronize(self.ctx), "nk_synchronize")
 
@@ -252,6 +263,64 @@ class Engine:
         if self.R:
             check(self.ctx, self.L.nk_get_res_counter(self.ctx, _p(out)), "nk_get_res_counter")
         return out
+
+    def run_state(self):
+        """Reservoir counters, emission deal counters, convergence-window accumulators, N_leaving and the results block
+        (what a checkpoint needs besides the particles and T_sv)."""
+        R, M = self.R, self.M
+        n = self.L.nk_results_len(self.ctx)
+        st = dict(res_counter=np.zeros((R, M)), res_fire=np.zeros((R, M), dtype=np.uint8), res_acc=np.zeros(4 * max(R, 1)),
+                  n_leaving=np.zeros(max(R, 1)), results_block=np.zeros(n))
+        if R:
+            check(self.ctx, self.L.nk_get_run_state(self.ctx, _p(st["res_counter"]), _p(st["res_fire"]), _p(st["res_acc"]),
+                                                    _p(st["n_leaving"]), _p(st["results_block"])), "nk_get_run_state")
+        else:
+            check(self.ctx, self.L.nk_get_run_state(self.ctx, None, None, None, None, _p(st["results_block"])), "nk_get_run_state")
+        return st
+
+    def set_run_state(self, res_counter=None, res_fire=None, res_acc=None, n_leaving=None, results_block=None):
+        keep = []
+
+        def a(x, dt):
+            if x is None:
+                return None
+            y = np.ascontiguousarray(np.asarray(x, dtype=dt))
+            keep.append(y)
+            return _p(y)
+        check(self.ctx, self.L.nk_set_run_state(self.ctx, a(res_counter, np.float64), a(res_fire, np.uint8), a(res_acc, np.float64),
+                                                a(n_leaving, np.float64), a(results_block, np.float64)), "nk_set_run_state")
+
+    def checkpoint(self):
+        """Everything needed to continue this context's run bit-exactly (besides the static tables and the seed): live
+        particles in f64, collision clocks, reservoir counters and deal counters, the accumulators of the open convergence
+        window, N_leaving, the results block, T_sv and the step counter.  Flushes the deferred relaxation."""
+        p = self.particles(flush=True)
+        st = self.run_state()
+        T = np.zeros(self.S)
+        check(self.ctx, self.L.nk_get_sv_temperature(self.ctx, _p(T)), "nk_get_sv_temperature")
+        out = dict(ids=p["ids"], positions=p["positions"], modes=p["modes"], omega_modes=p["omega_modes"], occupation=p["occupation"],
+                   n_timesteps=p["n_timesteps"], collision_facets=p["collision_facets"], collision_positions=p["collision_positions"],
+                   subvol_temperature=T, current_timestep=np.int64(self.timestep()), seed=np.int64(self.seed))
+        out.update(st)
+        return out
+
+    def restore(self, z, capacity_factor=1.25):
+        """Inverse of ``checkpoint`` on a context whose tables are already set (and, in a sharded run, whose rank is already
+        set): nothing is rebuilt, so rank, mailboxes and accumulator buffers stay valid."""
+        n = int(z["ids"].shape[0])
+        if self.cap < n + 2:
+            self.allocate(int(n * capacity_factor) + 1024)
+        J = self.J
+        modes = np.asarray(z["modes"])
+        self.load_particles(z["positions"], modes[:, 0] * J + modes[:, 1], z["occupation"], ids=z["ids"], omodes=z["omega_modes"],
+                            n_timesteps=z["n_timesteps"], collision_facets=z["collision_facets"], collision_positions=z["collision_positions"])
+        self.set_sv_temperature(z["subvol_temperature"])
+        self.set_timestep(int(z["current_timestep"]))
+        if self.R:
+            self.set_run_state(res_counter=z["res_counter"], res_fire=z["res_fire"], res_acc=z["res_acc"], n_leaving=z["n_leaving"],
+                               results_block=z["results_block"])
+        else:
+            self.set_run_state(results_block=z["results_block"])
 
     def results(self):
         S, R = self.S, self.R

@@ -4,9 +4,12 @@ Within a timestep every particle is independent given the previous subvolume tem
 coupling is the per-subvolume / per-reservoir sums.  So:
 
 * particles are split by index block across ranks (geometry, mode tables and LUTs are replicated);
-* every reservoir's (Q*J) emission table is split by mode range (``mode_range``) so that each rank
-  injects a deterministic share -- ids and random draws are keyed by (step, reservoir, mode, copy),
-  hence the union over ranks is exactly the single-GPU emission;
+* every rank advances the whole (R, Q*J) emission table; the copies an entry emits are dealt round-robin over the ranks
+  (``emission_owner``: copy k of an entry that has emitted ``fire`` particles before belongs to rank
+  ``(fire + k + mode) % world``), so each rank injects 1/world of EVERY mode -- its per-mode particle numbers stay in
+  balance with what it absorbs, which keeps the per-mode slot pools (``Engine.sort_by_mode``) and the live counts level.
+  Ids and random draws are keyed by (step, reservoir, mode, copy), hence the union over ranks is exactly the single-GPU
+  emission;
 * per step ONE all-reduce(sum, f64) of the accumulator vector ``[sum e (S), count (S), sum v e (3S),
   per reservoir N_leaving / E_bal / flux, emitted, absorbed]`` (<= a few KB) between the two halves of
   the step: ``step_local`` (stream + emit + boundary kernels) and ``step_finalize`` (T_sv, results).
@@ -29,9 +32,10 @@ import torch.distributed as dist
 from ._lib import check
 
 
-def mode_range(rank, world, n_modes):
-    """Contiguous share [lo, hi) of the flat mode index owned by `rank` (same split as nk_set_rank)."""
-    return (n_modes * rank) // world, (n_modes * (rank + 1)) // world
+def emission_owner(fire, copy, mode, world):
+    """Rank that injects copy `copy` (0-based) of a reservoir-table entry of flat mode `mode` that has emitted `fire`
+    particles before this step (csrc: nk_emit_owner; the device keeps `fire` modulo 256)."""
+    return (fire % 256 + copy + mode) % world
 
 
 F64_FIELDS = ("px", "py", "pz", "tc", "occ", "cx", "cy", "cz", "pid")      # pid travels as its bit pattern
@@ -180,7 +184,7 @@ class ShardedEngine:
         if not mine:
             return {}
         eng.flush_relaxation()
-        eng.sort_by_mode()                      # live particles in [0, n_live), free list dropped
+        eng.sort_by_mode(pools=False)           # live particles in [0, n_live), free list dropped
         n_live, _ = eng.slot_count()
         n_out = sum(n for _, n in mine)
         if n_out > n_live:
@@ -205,7 +209,7 @@ class ShardedEngine:
         if not blocks:
             return 0
         eng.flush_relaxation()
-        eng.sort_by_mode()
+        eng.sort_by_mode(pools=False)
         n_live, _ = eng.slot_count()
         n_in = sum(b[0].shape[1] for b in blocks)
         if n_live + n_in > eng.cap:

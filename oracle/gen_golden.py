@@ -81,6 +81,67 @@ PARAMS_C5 = """
 --n_mean 10 --results_folder x --conv_crit 0 10 --colormap jet --output screen --max_sim_time 0-00:00:00
 """
 
+# C4 proper: an STL-IMPORTED mesh (finely faceted cylinder written by the reference's own Mesh.export_stl, 4 x 160 = 640
+# triangles, 162 facets), voronoi subvolumes, rough side walls (eta > 0) -> ray-mesh intersection over many tiles, facet
+# tables beyond the shared-memory copies of the rare-path kernel.  `{stl}` is replaced by the generated file.
+PARAMS_C9 = """
+--mat_folder test_material/Si/ --hdf_file kappa-m313131.hdf5 --poscar_file POSCAR
+--geometry {stl} --dimensions 1 1 1 --scale 1 1 1 --geo_rotation 0 0 0 xyz
+--subvolumes voronoi 8
+--bound_pos relative 0.5 0.5 -0.1 0.5 0.5 1.1
+--bound_cond T T R
+--bound_values 304 296 {eta}
+--reference_temp local --temp_dist cold --temp_interp nearest
+--particles total {n} --part_dist random_subvol --timestep 1 --iterations 1000
+--n_mean 10 --results_folder x --conv_crit 0 10 --colormap jet --output screen --max_sim_time 0-00:00:00
+"""
+STL_SIDES = 160
+
+
+def write_reference_stl(folder):
+    """A faceted cylinder (L 2500 A, R 500 A, STL_SIDES sides) exported as ASCII STL by the reference's Mesh.export_stl
+    (Mesh.py:953-975); returns the path.  trimesh is absent here, so Geometry.load_geo_file's tm.load (Geometry.py:82) is
+    served by this repository's STL reader (vertices merged like trimesh does)."""
+    import sys
+    import types
+    from nanokappa_b200.classes.Mesh import read_stl
+    ref = rh.load_reference()
+    args = rh.parse_parameters_text(PARAMS_C4.format(eta=3, n=100).replace("--dimensions 3000 600 10", "--dimensions 2500 500 {}".format(STL_SIDES))
+                                    .replace("--subvolumes voronoi 6", "--subvolumes slice 2 2"), "/tmp/nk_golden_results",
+                                    overrides=dict(fig_plot=[], output=["screen"]))
+    os.makedirs(folder, exist_ok=True)
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+        geo = ref.Geometry(args)
+        geo.mesh.export_stl("nk_c9_cylinder", folder)
+    path = os.path.join(folder, "nk_c9_cylinder.stl")
+
+    def _load(name, *a, **k):
+        v, f = read_stl(name)
+        return types.SimpleNamespace(vertices=v, faces=f)
+    sys.modules["trimesh"].__dict__["load"] = _load
+    return path
+
+
+def config_text(name, folder="/tmp/nk_golden_stl"):
+    """Parameter text of a configuration with its generated input files in place.  For the STL case the cylinder is
+    written by THIS repository's Geometry / Mesh.export_stl (same primitive, same text format as the reference's
+    exporter), so boxes without /root/reference can rebuild the input of the fixture."""
+    text = CONFIGS[name][0]
+    if "{stl}" not in text:
+        return text
+    import argument_parser as ap
+    from nanokappa_b200.classes.Geometry import Geometry
+    os.makedirs(folder, exist_ok=True)
+    t = PARAMS_C4.format(eta=3, n=100).replace("--dimensions 3000 600 10", "--dimensions 2500 500 {}".format(STL_SIDES)) \
+                 .replace("--subvolumes voronoi 6", "--subvolumes slice 2 2").replace("--colormap jet", "")
+    args = ap.initialise_parser(False).parse_args(t.split())
+    args.results_folder = folder
+    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+        geo = Geometry(args)
+        geo.mesh.export_stl("nk_c9_cylinder_host", folder)
+    return text.replace("{stl}", os.path.join(folder, "nk_c9_cylinder_host.stl"))
+
+
 CONFIGS = {
     # name: (parameter text, table mesh n, lattice)
     "c1_specular": (PARAMS_C1.format(eta=0, n=4000), 5),
@@ -93,6 +154,7 @@ CONFIGS = {
     # the two debug emission modes of Population.fill_reservoirs on the cross-plane film
     "c7_fixed_rate": (PARAMS_C2.format(n=3000) + "--reservoir_gen fixed_rate\n", 5),
     "c8_one_to_one": (PARAMS_C2.format(n=3000) + "--reservoir_gen one_to_one\n", 5),
+    "c9_stl_voronoi": (PARAMS_C9.format(eta=3, n=3000, stl="{stl}"), 5),
 }
 
 STATE_FIELDS = ("positions", "modes", "omega", "group_vel", "occupation", "n_timesteps", "collision_facets",
@@ -155,6 +217,8 @@ def load_fixture(path):
 
 
 def generate(name, text, n_mesh):
+    if "{stl}" in text:
+        text = text.replace("{stl}", write_reference_stl("/tmp/nk_golden_results"))
     args, geo, ph, pop = build_reference(text, n_mesh)
     tb = extract.tables_from_reference(geo, ph, pop)
     st0 = extract.state_from_reference(ph, pop)

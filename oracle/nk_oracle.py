@@ -830,24 +830,42 @@ def init_collisions(tb, st):
 # particle shards: the same timestep with the population split over ranks.  Only the
 # per-subvolume / per-reservoir sums are exchanged (reduce_fn = all-reduce sum of one f64 vector).
 # ------------------------------------------------------------------------------------------------
-def run_timestep_sharded(tb, st, rng, reduce_fn, mode_lo, mode_hi):
-    """One timestep of one rank: emission restricted to flat modes [mode_lo, mode_hi), local boundary
-    loop, per-SV sums all-reduced before the temperatures are inverted.  With keyed random draws the
-    union of all ranks' particles equals the single-rank run."""
+def emission_owner(fire, copy, mode, world):
+    """Rank that injects copy `copy` (0-based) of a table entry of flat mode `mode` that has emitted `fire` particles before
+    this step (the device keeps `fire` in 8 bits; nanokappa_b200/csrc/nk_stream.cuh: nk_emit_owner)."""
+    return (np.asarray(fire) % 256 + copy + mode) % world
+
+
+def run_timestep_sharded(tb, st, rng, reduce_fn, rank, world):
+    """One timestep of one rank: every rank advances the whole reservoir table (identical on all ranks) and keeps the new
+    particles dealt to it (round-robin per table entry, emission_owner), local boundary loop, per-SV sums all-reduced
+    before the temperatures are inverted.  With keyed random draws the union of all ranks' particles equals the
+    single-rank run."""
     S = tb["sv_centres"].shape[0]
     R = tb["res_facet"].shape[0]
     Q, J = tb["omega"].shape
+    M = Q * J
     drift(tb, st)
     if R > 0:
-        full = tb["enter_prob"]
-        mask = np.zeros(Q * J, dtype=bool)
-        mask[mode_lo:mode_hi] = True
-        tb_local = dict(tb)
-        tb_local["enter_prob"] = np.where(mask.reshape(1, Q, J), full, 0.0)
-        counter_before = st.res_counter.copy()
-        new = fill_reservoirs(tb_local, st, rng)
-        # entries outside the share keep evolving on their owner only
-        st.res_counter = np.where(mask.reshape(1, Q, J), st.res_counter, counter_before)
+        if getattr(st, "res_fire", None) is None:
+            st.res_fire = np.zeros((R, M), dtype=np.int64)
+        new = fill_reservoirs(tb, st, rng)
+        ids = new["ids"]
+        if str(tb.get("res_gen", "constant")) == "one_to_one":
+            # the k-th re-emitted particle of a reservoir belongs to rank k % world
+            k = (ids - philox.EMIT_ID_BASE) % (M * philox.EMIT_CMAX)
+            mine = (k % world) == rank
+        else:
+            e = ids - philox.EMIT_ID_BASE
+            copy = e % philox.EMIT_CMAX
+            m = (e // philox.EMIT_CMAX) % M
+            r = (e // philox.EMIT_CMAX // M) % R
+            mine = emission_owner(st.res_fire[r, m], copy, m, world) == rank
+            np.add.at(st.res_fire, (r, m), 1)               # every copy advances the entry's deal counter, on every rank
+        n_new = ids.shape[0]
+        for k, v in list(new.items()):
+            if isinstance(v, np.ndarray) and v.shape[:1] == (n_new,):
+                new[k] = v[mine]
         add_reservoir_particles(tb, st, new)
     boundary_scattering(tb, st, rng)
     sv = classify(tb, st.positions)

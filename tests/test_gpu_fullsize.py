@@ -28,7 +28,7 @@ def _run(tmp, seed, steps, env=None, monkeypatch=None, params=None):
     from nanokappa_b200.classes.Phonon import Phonon
     from nanokappa_b200.classes.Population import Population
     if monkeypatch is not None:
-        for k in ("NK_STEP_TAB", "NK_STEP_IMPL"):
+        for k in ("NK_STEP_TAB", "NK_RARE_TILED"):
             monkeypatch.delenv(k, raising=False)
         for k, v in (env or {}).items():
             monkeypatch.setenv(k, v)

@@ -246,22 +246,29 @@ def test_capacity_overflow_is_reported(golden_dir):
         eng.slot_count()
 
 
-@pytest.mark.parametrize("name", ["c2_crossplane", "c4_cylinder_voronoi", "c1_mixed"])
+@pytest.mark.parametrize("name", ["c2_crossplane", "c4_cylinder_voronoi", "c1_mixed", "c8_one_to_one"])
 def test_step_kernel_variants_agree(name, golden_dir, monkeypatch):
-    """Every implementation of the streaming kernel (direct 128-bit, per-(mode, subvolume) tables, one
-    particle per thread, cp.async prefetch, TMA bulk pipeline) must give the same particles: integers
-    identical, occupations identical to the last bit (they share one arithmetic), T_sv to 1e-13."""
+    """Every implementation of a step -- streaming kernel with direct arithmetic or per-(mode, subvolume) tables, rare path
+    with one thread per item or with block-cooperative triangle tiles, particles in creation order or ordered by mode with
+    per-mode slot pools -- must give the same particles: integers identical, occupations identical to the last bit (they
+    share one arithmetic), T_sv to 1e-13."""
     tb, st, _ = _load(name, golden_dir)
     results = {}
+    keys = ("NK_STEP_TAB", "NK_RARE_TILED", "NK_POOL_MIN")
     for label, env in (("direct", {"NK_STEP_TAB": "0"}), ("tables", {"NK_STEP_TAB": "force"}),
-                       ("ldg1", {"NK_STEP_TAB": "0", "NK_STEP_IMPL": "ldg1"}), ("prefetch", {"NK_STEP_TAB": "0", "NK_STEP_IMPL": "pf"}),
-                       ("tma", {"NK_STEP_TAB": "0", "NK_STEP_IMPL": "tma"})):
-        for k in ("NK_STEP_TAB", "NK_STEP_IMPL"):
+                       ("tiled", {"NK_STEP_TAB": "0", "NK_RARE_TILED": "1"}),
+                       ("pools", {"NK_STEP_TAB": "0", "NK_POOL_MIN": "0"}), ("pools_tiled_tables", {"NK_STEP_TAB": "force", "NK_RARE_TILED": "1", "NK_POOL_MIN": "0"})):
+        for k in keys:
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         eng = _engine(tb, st.copy())
-        eng.step(23)
+        if label.startswith("pools"):
+            eng.sort_by_mode()
+        eng.step(11)
+        if label.startswith("pools"):
+            eng.sort_by_mode()              # a maintenance pass in the middle of the run is neutral, too
+        eng.step(12)
         results[label] = (eng.particles(), eng.results())
         eng.close()
     p0, r0 = results["direct"]
@@ -270,6 +277,39 @@ def test_step_kernel_variants_agree(name, golden_dir, monkeypatch):
             assert np.array_equal(p[f], p0[f], equal_nan=True), f"{label}: {f} differs from the direct kernel"
         assert np.array_equal(r["subvol_N_p"], r0["subvol_N_p"])
         _close(f"{label} T_sv", r["subvol_temperature"], r0["subvol_temperature"], 1e-13)
+
+
+def test_sort_by_mode_orders_compacts_and_pools(golden_dir, monkeypatch):
+    """nk_sort_by_mode: live particles ordered by mode, every mode region followed by its spare slots, nothing lost; with
+    pools the slots freed by absorption are reused by emitted particles of the same mode, so the order stays exact."""
+    import torch
+    monkeypatch.setenv("NK_POOL_MIN", "0")
+    tb, st, _ = _load("c2_crossplane", golden_dir)
+    eng = _engine(tb, st.copy(), cap_factor=3.0)
+    before = eng.particles(flush=False)
+    eng.sort_by_mode()
+    n, alive = eng.slot_count()
+    assert alive == before["ids"].shape[0] and n > alive                 # spare slots were added
+    after = eng.particles(flush=False)
+    for f in before:
+        assert np.array_equal(before[f], after[f], equal_nan=True), f
+    md = eng.t["mode"][:n].cpu().numpy()
+    live = md[md >= 0]
+    assert (np.diff(live) >= 0).all(), "live particles are not ordered by mode"
+    # every run of one mode is followed by free slots (its pool) before the next mode starts
+    starts = np.nonzero(np.diff(np.concatenate(([-2], md))) != 0)[0]
+    assert (md[starts[1::2]] == -1).all() if md[starts[0]] >= 0 else True
+    eng.step(40)
+    n2, alive2 = eng.slot_count()
+    md2 = eng.t["mode"][:n2].cpu().numpy()
+    live2 = md2[md2 >= 0]
+    foreign = np.count_nonzero(np.diff(live2) < 0)
+    assert n2 == n, "slot range grew although every mode had spare slots"
+    assert foreign <= 0.02 * alive2, f"{foreign} of {alive2} particles sit outside the region of their mode after 40 steps"
+    eng.sort_by_mode(pools=False)
+    n3, alive3 = eng.slot_count()
+    assert n3 == alive3 == alive2
+    assert bool((eng.t["mode"][:n3] >= 0).all()) and bool((torch.diff(eng.t["mode"][:n3]) >= 0).all())
 
 
 def test_energy_table_on_device_matches_numpy(golden_dir):

@@ -1,5 +1,5 @@
 """world_size-2 check of the particle-shard protocol on CPU (gloo): two ranks, each owning half of the
-particles and half of every reservoir's mode table, exchanging only the per-SV sum vector per step,
+particles and every second copy that a reservoir-table entry emits, exchanging only the per-SV sum vector per step,
 must reproduce the single-rank run (same keyed draws): identical particle census and integer state,
 temperatures equal up to the order of the floating-point sums."""
 import os
@@ -19,15 +19,13 @@ def _worker(rank, world, port, fixture, out_dir):
     sys.path.insert(0, ROOT)
     import torch
     from oracle import gen_golden, nk_oracle as nko
-    from nanokappa_b200.parallel import mode_range, shard_bounds
+    from nanokappa_b200.parallel import shard_bounds
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     tb, st, _ = gen_golden.load_fixture(fixture)
     lo, hi = shard_bounds(rank, world, st.positions.shape[0])
     mine = nko.shard_state(st, lo, hi)
-    Q, J = tb["omega"].shape
-    m_lo, m_hi = mode_range(rank, world, Q * J)
 
     def reduce_fn(v):
         t = torch.from_numpy(np.ascontiguousarray(v))
@@ -37,7 +35,7 @@ def _worker(rank, world, port, fixture, out_dir):
     rng = nko.KeyedRNG(SEED)
     with np.errstate(all="ignore"):
         for _ in range(STEPS):
-            nko.run_timestep_sharded(tb, mine, rng, reduce_fn, m_lo, m_hi)
+            nko.run_timestep_sharded(tb, mine, rng, reduce_fn, rank, world)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ids=mine.ids, modes=mine.modes, positions=mine.positions,
              occupation=mine.occupation, facets=mine.collision_facets, T=mine.subvol_temperature, N=mine.subvol_N_p)
     dist.barrier()
@@ -72,14 +70,22 @@ def test_two_rank_shards_equal_single_rank(name, golden_dir, tmp_path):
     assert np.array_equal(r[0]["T"], r[1]["T"]), "ranks disagree on T_sv after the all-reduce"
 
 
-def test_mode_and_particle_partitions_cover_everything():
-    from nanokappa_b200.parallel import mode_range, shard_bounds
+def test_particle_partition_and_emission_deal_cover_everything():
+    from nanokappa_b200.parallel import emission_owner, shard_bounds
+    from oracle import nk_oracle as nko
     for world in (1, 2, 3, 4, 8):
         for n in (0, 1, 7, 178746, 10 ** 8 + 3):
-            spans = [mode_range(r, world, n) for r in range(world)]
+            spans = [shard_bounds(r, world, n) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
-            assert [shard_bounds(r, world, n) for r in range(world)] == spans
+        # consecutive copies of one table entry go to consecutive ranks, whatever the entry has emitted before; the host
+        # helper and the oracle agree (the device keeps the deal counter in 8 bits)
+        for fire in (0, 1, 200, 255, 256, 1000):
+            for mode in (0, 5, 178745):
+                owners = [emission_owner(fire, k, mode, world) for k in range(2 * world)]
+                assert sorted(owners[:world]) == list(range(world))
+                assert owners[:world] == owners[world:]
+                assert owners == [int(nko.emission_owner(fire, k, mode, world)) for k in range(2 * world)]
 
 
 def test_rebalance_plan_is_balanced_conservative_and_deterministic():
