@@ -524,13 +524,14 @@ def sustained_run(a, eng, world, rank, local, one_step, barrier, peak):
     eng.profile_begin()
     barrier()
     marks[0].record()
-    resorts, sort_s = 0, 0.0
+    resorts, sort_ev = 0, []
     for k in range(steps):
         if every > 0 and k > 0 and k % every == 0:
-            t0 = time.perf_counter()
+            s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+            s0.record()
             eng.sort_by_mode()
-            eng.synchronize()
-            sort_s += time.perf_counter() - t0
+            s1.record()
+            sort_ev.append((s0, s1))
             resorts += 1
         one_step()
         if (k + 1) % 100 == 0:
@@ -550,7 +551,7 @@ def sustained_run(a, eng, world, rank, local, one_step, barrier, peak):
     per100 = [marks[i].elapsed_time(marks[i + 1]) / 100.0 for i in range(steps // 100)]
     kstep_ms = prof["k_step"] / max(nprof, 1)
     return {"value": 0.5 * (n0 + n1) * steps / (ms * 1e-3), "unit": "updates/s", "steps": steps, "ms_per_step": ms / steps,
-            "resort_every": every, "resorts": resorts, "resort_ms_each": 1e3 * sort_s / max(resorts, 1),
+            "resort_every": every, "resorts": resorts, "resort_ms_each": sum(x.elapsed_time(y) for x, y in sort_ev) / max(resorts, 1),
             "ms_per_step_by_100": per100, "kstep_avg_ms": kstep_ms,
             "kstep_roofline_frac": BYTES_PER_UPDATE * alive_local / (kstep_ms * 1e-3) / 1e9 / peak, "clocks": clocks}
 

@@ -397,11 +397,13 @@ class Population(PopulationSetup):
         eng = self.engine
         n, _ = eng.slot_count()
         t = eng.t
-        pos = torch.stack((t['px'][:n], t['py'][:n], t['pz'][:n]), dim=1).contiguous()
+        live = t['mode'][:n] >= 0                   # the slot range holds free slots too (spare slots of the mode pools)
+        pos = torch.stack((t['px'][:n][live], t['py'][:n][live], t['pz'][:n][live]), dim=1).contiguous()
+        n = int(pos.shape[0])
         sv, counts = None, torch.zeros(self.n_of_subvols, dtype=torch.int64, device=eng.device)
         from ..engine import _dp
         from .._lib import check
-        svt = torch.empty(n, dtype=torch.int32, device=eng.device)
+        svt = torch.empty(max(n, 1), dtype=torch.int32, device=eng.device)
         check(eng.ctx, eng.L.nk_classify(eng.ctx, n, _dp(pos), _dp(svt), _dp(counts)), 'nk_classify')
         eng.synchronize()
         if self.world > 1:
