@@ -316,40 +316,94 @@ NK_DEVI double nk_particle_T(const NkP& P, const double* svc, const double* sv_a
 
 // ------------------------------------------------------------------------------------------------
 // Mesh.find_boundary (Mesh.py:806-856) for one ray.  `faces` may point to shared memory.
+//
+// Two stages per triangle.  Stage 1 (every lane, no divergence, ~23 FP64 instructions): an FMA-contracted copy of the
+// plane test gives an approximate hit parameter ta = |num| / |den| through a Newton reciprocal and an approximate hit point;
+// the triangle is skipped when that point lies outside its (margin-widened) bounding box, when the ray moves away from the
+// plane, or when ta cannot beat the running minimum.  Every skip is CONSERVATIVE: the approximations are accurate to
+// 1e-10 x mesh scale wherever |num| and |den| are not tiny, the margins are 1e-6 x mesh scale and 1 %, and whatever is tiny,
+// non-finite or far outside the mesh is "ambiguous" and goes to stage 2.  Stage 2 (the few surviving candidates) is the
+// reference's arithmetic, operation by operation: IEEE division, unfused products, the 1e-10 tolerances.  So the result
+// -- facet, t, and the first-minimum tie rule -- is exactly what the unfiltered loop gives.
 // ------------------------------------------------------------------------------------------------
-NK_DEVI void nk_ray_faces(const NkFace* faces, int F, double x, double y, double z, double vx, double vy, double vz,
+// stage 2: the reference's test of one triangle, operation by operation (Mesh.py:818-856)
+NK_DEVI void nk_ray_face_exact(const NkFace& T, double x, double y, double z, double vx, double vy, double vz, double& tbest, int& fbest) {
+    double num = nk_add(dot3(x, y, z, T.nx, T.ny, T.nz), T.k);
+    double den = dot3(vx, vy, vz, T.nx, T.ny, T.nz);
+    // t = -num/den can only reach the tolerance when num and den have opposite signs (0, inf and NaN quotients are rejected
+    // below anyway): skip the IEEE division for the planes the ray moves away from
+    if (!((num < 0.0 && den > 0.0) || (num > 0.0 && den < 0.0))) return;
+    // |num| * rcp(|den|) is within a few ulp of t: a plane whose approximate t exceeds the best one by more than 1e-12
+    // relative can never satisfy t < tbest below, so the IEEE division is skipped for it
+    if (tbest < CUDART_INF && fabs(num) * nk_rcp(fabs(den)) > tbest * (1.0 + 1e-12)) return;
+    double t = -nk_div(num, den);
+    if (!(t >= NK_TOL) || isinf(t)) return;                   // also rejects NaN
+    if (!(t < tbest)) return;                                 // cannot become the first minimum
+    double cx = nk_add(x, nk_mul(t, vx)), cy = nk_add(y, nk_mul(t, vy)), cz = nk_add(z, nk_mul(t, vz));
+    if (!(cx >= T.lox && cy >= T.loy && cz >= T.loz && cx <= T.hix && cy <= T.hiy && cz <= T.hiz)) return;
+    double dx = nk_sub(cx, T.ox), dy = nk_sub(cy, T.oy), dz = nk_sub(cz, T.oz);
+    double a = T.ia0 * dx + T.ia1 * dy + T.ia2 * dz;
+    double b = T.ib0 * dx + T.ib1 * dy + T.ib2 * dz;
+    double w = nk_sub(1.0, nk_add(a, b));
+    const double lo = -NK_TOL, hi = 1.0 + NK_TOL;
+    if (!(a >= lo && a <= hi && b >= lo && b <= hi && w >= lo && w <= hi)) return;
+    tbest = t; fbest = (int)T.facet;
+}
+// Small meshes (a box is 12 triangles) staged per block: every thread walks all faces with the exact test; the pre-filter
+// below costs more than it saves there.
+NK_DEVI void nk_ray_faces_small(const NkFace* faces, int F, double x, double y, double z, double vx, double vy, double vz,
+                                double& tbest, int& fbest) {
+    for (int f = 0; f < F; ++f) nk_ray_face_exact(faces[f], x, y, z, vx, vy, vz, tbest, fbest);
+}
+
+struct NkRayPre {               // per-ray constants of the pre-filter
+    double eps_n, den_thr, graze_lim;
+};
+NK_DEVI NkRayPre nk_ray_pre(double mesh_scale, double x, double y, double z, double vx, double vy, double vz) {
+    NkRayPre r;
+    const double vn1 = fabs(vx) + fabs(vy) + fabs(vz);
+    const double xs = fabs(x) + fabs(y) + fabs(z);
+    // |num| below eps_n (rounding noise x 1e3) -> ambiguous; an origin far outside the mesh (or NaN) makes everything ambiguous
+    r.eps_n = (xs <= 10.0 * mesh_scale) ? 1e-11 * (xs + mesh_scale) : CUDART_INF;
+    r.den_thr = 1e-3 * vn1;
+    // a grazing ray (|den| <= den_thr, including the exact zeros of symmetric mode tables) meets the plane at t >= |num| / den_thr,
+    // i.e. at an L1 distance >= 1e3 |num| from its origin: beyond every point of the mesh when that exceeds 2 (|x|_1 + 3 scale)
+    r.graze_lim = (xs <= 10.0 * mesh_scale) ? 2.0 * (xs + 3.0 * mesh_scale) / 999.0 : CUDART_INF;
+    return r;
+}
+// stage 1: true when the triangle certainly cannot be the first hit (all comparisons are false for NaN -> not skipped)
+NK_DEVI bool nk_ray_face_skip(const NkFace& T, const NkRayPre& r, double x, double y, double z, double vx, double vy, double vz, double tb_hi) {
+    const double nf = fma(x, T.nx, fma(y, T.ny, fma(z, T.nz, T.k)));
+    const double df = fma(vx, T.nx, fma(vy, T.ny, vz * T.nz));
+    const double an = fabs(nf), ad = fabs(df);
+    const bool opposite = (__double2hiint(nf) ^ __double2hiint(df)) < 0;
+    const double ta = an * nk_rcp(ad);
+    const bool outside = (fabs(fma(ta, vx, x) - T.mx) > T.ex) | (fabs(fma(ta, vy, y) - T.my) > T.ey) | (fabs(fma(ta, vz, z) - T.mz) > T.ez);
+    return (ad > r.den_thr) ? ((an > r.eps_n) & (!opposite | outside | (ta > tb_hi))) : (an > r.graze_lim);
+}
+NK_DEVI void nk_ray_faces(const NkFace* faces, int F, double mesh_scale, double x, double y, double z, double vx, double vy, double vz,
                           double& tbest, int& fbest) {
-    for (int f = 0; f < F; ++f) {
-        const NkFace& T = faces[f];
-        double num = nk_add(dot3(x, y, z, T.nx, T.ny, T.nz), T.k);
-        double den = dot3(vx, vy, vz, T.nx, T.ny, T.nz);
-        // t = -num/den can only reach the tolerance when num and den have opposite signs (0, inf and NaN quotients are
-        // rejected below anyway): skip the IEEE division for the planes the ray moves away from -- half of a convex mesh
-        if (!((num < 0.0 && den > 0.0) || (num > 0.0 && den < 0.0))) continue;
-        // conservative filter before the IEEE division: |num| * rcp(|den|) is within a few ulp of t, so a face whose
-        // approximate t exceeds the best one by more than 1e-12 relative can never satisfy t < tbest below.  Only
-        // skips work; every accepted face still goes through the exact arithmetic.
-        if (tbest < CUDART_INF && fabs(num) * nk_rcp(fabs(den)) > tbest * (1.0 + 1e-12)) continue;
-        double t = -nk_div(num, den);
-        if (!(t >= NK_TOL) || isinf(t)) continue;                 // also rejects NaN
-        if (!(t < tbest)) continue;                               // cannot become the first minimum
-        double cx = nk_add(x, nk_mul(t, vx)), cy = nk_add(y, nk_mul(t, vy)), cz = nk_add(z, nk_mul(t, vz));
-        if (!(cx >= T.lox && cy >= T.loy && cz >= T.loz && cx <= T.hix && cy <= T.hiy && cz <= T.hiz)) continue;
-        double dx = nk_sub(cx, T.ox), dy = nk_sub(cy, T.oy), dz = nk_sub(cz, T.oz);
-        double a = T.ia0 * dx + T.ia1 * dy + T.ia2 * dz;
-        double b = T.ib0 * dx + T.ib1 * dy + T.ib2 * dz;
-        double w = nk_sub(1.0, nk_add(a, b));
-        const double lo = -NK_TOL, hi = 1.0 + NK_TOL;
-        if (!(a >= lo && a <= hi && b >= lo && b <= hi && w >= lo && w <= hi)) continue;
-        tbest = t; fbest = (int)T.facet;
+    const NkRayPre r = nk_ray_pre(mesh_scale, x, y, z, vx, vy, vz);
+    double tb_hi = tbest * 1.01;                                  // inf stays inf
+    int f = 0;
+    // two triangles per round: their pre-filters are independent chains of FP64 instructions that overlap, and one branch
+    // covers both (a stale tb_hi for the second one is only less strict)
+    for (; f + 1 < F; f += 2) {
+        const bool s0 = nk_ray_face_skip(faces[f], r, x, y, z, vx, vy, vz, tb_hi);
+        const bool s1 = nk_ray_face_skip(faces[f + 1], r, x, y, z, vx, vy, vz, tb_hi);
+        if (s0 & s1) continue;
+        if (!s0) nk_ray_face_exact(faces[f], x, y, z, vx, vy, vz, tbest, fbest);
+        if (!s1) nk_ray_face_exact(faces[f + 1], x, y, z, vx, vy, vz, tbest, fbest);
+        tb_hi = tbest * 1.01;
     }
+    if (f < F && !nk_ray_face_skip(faces[f], r, x, y, z, vx, vy, vz, tb_hi)) nk_ray_face_exact(faces[f], x, y, z, vx, vy, vz, tbest, fbest);
 }
 
 NK_DEVI void nk_find_boundary_1(const NkP& P, const NkFace* faces, double x, double y, double z,
                                 double vx, double vy, double vz,
                                 double& xc, double& yc, double& zc, double& tc, int& fc) {
     double tbest = CUDART_INF; int fbest = -1;
-    nk_ray_faces(faces, P.F, x, y, z, vx, vy, vz, tbest, fbest);
+    nk_ray_faces_small(faces, P.F, x, y, z, vx, vy, vz, tbest, fbest);
     tc = tbest; fc = fbest;
     xc = nk_add(x, nk_mul(tbest, vx)); yc = nk_add(y, nk_mul(tbest, vy)); zc = nk_add(z, nk_mul(tbest, vz));   // inf*0 = NaN like NumPy
 }
@@ -444,6 +498,14 @@ __device__ __forceinline__ bool nk_event_advance(const NkP& P, const NkGeo& G, N
                 const double* rou = P.roulette + (size_t)fr * P.M;
                 double target = nk_mul(u_pick, rou[P.M - 1]);
                 int lo = 0, hi = P.M;                            // searchsorted left
+                if (P.rou_guide) {
+                    // monotonic table: u_pick in [b/K, (b+1)/K) brackets the answer between two guide entries (exact: the
+                    // product with the total is monotonic in u), which cuts 18 dependent loads to 4-5
+                    const int K = P.rou_guide_k;
+                    const int b = min((int)(u_pick * (double)K), K - 1);
+                    const int* g = P.rou_guide + (size_t)fr * (K + 1);
+                    lo = g[b]; hi = g[b + 1];
+                }
                 while (lo < hi) { int mid = (lo + hi) >> 1; if (rou[mid] < target) lo = mid + 1; else hi = mid; }
                 p.mode = min(lo, P.M - 1);
                 p.omode = p.mode;
@@ -479,7 +541,7 @@ __device__ __forceinline__ void nk_boundary_events(const NkP& P, const NkGeo& G,
     nk_event_begin(p, st);
     while (nk_event_advance(P, G, p, st, step, acc)) {
         double tbest = CUDART_INF; int fbest = -1;
-        nk_ray_faces(G.faces, P.F, p.x, p.y, p.z, p.vx, p.vy, p.vz, tbest, fbest);
+        nk_ray_faces_small(G.faces, P.F, p.x, p.y, p.z, p.vx, p.vy, p.vz, tbest, fbest);
         nk_event_ray_done(P, p, st, tbest, fbest);
     }
 }

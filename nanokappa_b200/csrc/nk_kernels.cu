@@ -31,6 +31,7 @@
 #include <vector>
 #include <cmath>
 #include <cstdlib>
+#include <algorithm>
 
 #include "../../include/nk_b200.h"
 #include "nk_device.cuh"
@@ -197,11 +198,18 @@ int nk_set_mesh(nk_ctx* ctx, int F, const double* fn, const double* fk, const do
                 const int32_t* ffptr, const int32_t* ffaces, const double* bounds) {
     cudaSetDevice(ctx->device);
     std::vector<NkFace> faces(F);
+    // scale of the mesh for the error bounds of the ray pre-filter: largest |coordinate| of the bounding box / |plane offset|
+    double mesh_scale = 1e-300;
+    for (int k = 0; k < 6; ++k) mesh_scale = std::max(mesh_scale, std::fabs(bounds[k]));
+    for (int f = 0; f < F; ++f) mesh_scale = std::max(mesh_scale, std::fabs(fk[f]));
+    ctx->P.mesh_scale = mesh_scale;
     for (int f = 0; f < F; ++f) {
         NkFace& T = faces[f];
         T.nx = fn[3 * f]; T.ny = fn[3 * f + 1]; T.nz = fn[3 * f + 2]; T.k = fk[f];
         T.lox = flo[3 * f] - NK_TOL; T.loy = flo[3 * f + 1] - NK_TOL; T.loz = flo[3 * f + 2] - NK_TOL;
         T.hix = fhi[3 * f] + NK_TOL; T.hiy = fhi[3 * f + 1] + NK_TOL; T.hiz = fhi[3 * f + 2] + NK_TOL;
+        T.mx = 0.5 * (T.lox + T.hix); T.my = 0.5 * (T.loy + T.hiy); T.mz = 0.5 * (T.loz + T.hiz);
+        T.ex = 0.5 * (T.hix - T.lox) + 1e-6 * mesh_scale; T.ey = 0.5 * (T.hiy - T.loy) + 1e-6 * mesh_scale; T.ez = 0.5 * (T.hiz - T.loz) + 1e-6 * mesh_scale;
         T.ox = fo[3 * f]; T.oy = fo[3 * f + 1]; T.oz = fo[3 * f + 2];
         // inverse of A = face_basis_matrix (columns b1, b2, n), rows 0 and 1, by cofactors
         const double* A = fb + 9 * f;
@@ -212,7 +220,7 @@ int nk_set_mesh(nk_ctx* ctx, int F, const double* fn, const double* fk, const do
         T.facet = (double)ff[f];
     }
     NkP& P = ctx->P;
-    P.F = F; P.nf = nf;
+    P.F = F; P.nf = nf; ctx->rare_attr_set = false;
     NkFace* dfaces; NK_UP(dfaces, NkFace, faces.data(), (size_t)F); P.faces = dfaces;
     int* di; double* dd;
     NK_UP(di, int, bc, nf); P.facet_bc = di;
@@ -360,7 +368,7 @@ static int nk_alloc_scratch(nk_ctx* ctx) {
         if (cudaMalloc(&dt2, (size_t)P.M * P.S * sizeof(double2)) == cudaSuccess) { ctx->owned.push_back(dt2); P.hot_tab = dt2; }
         else cudaGetLastError();          // not enough memory: the direct variant is used
     }
-    ctx->tab_dirty = true; ctx->step_blocks = 0;
+    ctx->tab_dirty = true; ctx->step_blocks = 0; ctx->rare_attr_set = false;
     return 0;
 }
 
@@ -428,6 +436,29 @@ int nk_set_boundary_luts(nk_ctx* ctx, int Fr, const double* spec, const uint8_t*
     NK_UP(di, int, so, n); P.spec_out = di;
     NK_UP(dd, double, rou, n); P.roulette = dd;
     ctx->has_rough = Fr > 0; P.has_rough = Fr > 0;
+    // guide table for the diffuse pick (nk_event_advance): only valid when every row is non-decreasing -- the reference's
+    // creation rates can go negative (Population.py:906-939), and on such a row the plain bisection's answer depends on its
+    // probe sequence, so those set-ups keep the full bisection
+    P.rou_guide = nullptr; P.rou_guide_k = 0;
+    bool monotonic = Fr > 0 && P.M > 0;
+    for (size_t f = 0; monotonic && f < (size_t)Fr; ++f)
+        for (int m = 1; m < P.M; ++m)
+            if (!(rou[f * P.M + m] >= rou[f * P.M + m - 1])) { monotonic = false; break; }
+    if (monotonic) {
+        int K = 16384;
+        while (K > 256 && (size_t)Fr * (K + 1) * sizeof(int) > ((size_t)64 << 20)) K >>= 1;
+        std::vector<int> guide((size_t)Fr * (K + 1));
+        for (size_t f = 0; f < (size_t)Fr; ++f) {
+            const double* row = rou + f * P.M;
+            const double total = row[P.M - 1];
+            for (int b = 0; b <= K; ++b) {
+                const double thr = ((double)b / (double)K) * total;
+                guide[f * (K + 1) + b] = (int)(std::lower_bound(row, row + P.M, thr) - row);
+            }
+        }
+        NK_UP(di, int, guide.data(), guide.size());
+        P.rou_guide = di; P.rou_guide_k = K;
+    }
     return 0;
 }
 
@@ -697,6 +728,17 @@ int nk_init_collisions(nk_ctx* ctx) {
 }
 
 #define NK_TAB_MAX_ENTRIES (6LL << 20)      // 96 MB of {n0, decay} pairs
+
+// per-(mode, subvolume) tables {n0, decay} of the table variant for the step that comes next (T_sv changed)
+static int nk_refresh_tables(nk_ctx* ctx, int variant) {
+    const NkP& P = ctx->P;
+    if (variant == 4) {
+        k_mode_tables<<<ctx->n_sm * 8, 256, nk_hot_smem_bytes(P.S), ctx->stream>>>(P);
+        NK_CK(cudaGetLastError());
+        ctx->tab_dirty = false;
+    }
+    return 0;
+}
 static size_t nk_step_smem(const NkP& P) { return (nk_sv_smem_doubles(P.S) + 8 * (size_t)P.S) * 8 + ((size_t)P.S + 2) * 4 + nk_hot_smem_bytes(P.S) + 32; }
 
 // chunked launch of the streaming kernel for the host-buffer pipeline: chunk c waits for its upload event and
@@ -711,6 +753,7 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     const NkP& P = ctx->P;
     size_t smem = nk_step_smem(P);
     const bool fast = P.is_slice && P.interp == NK_INTERP_NEAREST;
+    const int kind = fast ? NK_KIND_FAST : ((P.is_slice && P.interp == NK_INTERP_LINEAR) ? NK_KIND_SLICE_LINEAR : NK_KIND_GENERAL);
     // the step counter and the relaxation flag are mirrored on the host (every mutation goes through this
     // library), so the launch-uniform RELAX / FLUX variants can be chosen without a device read-back
     const bool relax = ctx->h_relax_pending;
@@ -723,11 +766,7 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     // rebuild costs what the leaner inner loop saves (profiles/README.md)
     if (ctx->use_tab && fast && P.hot_tab &&
         (ctx->force_tab || (ctx->h_slots_hint >= 2 * (long long)P.M * P.S && (long long)P.M * P.S <= NK_TAB_MAX_ENTRIES))) variant = 4;
-    if (variant == 4 && ctx->tab_dirty) {
-        k_mode_tables<<<ctx->n_sm * 8, 256, nk_hot_smem_bytes(P.S), ctx->stream>>>(P);
-        NK_CK(cudaGetLastError());
-        ctx->tab_dirty = false;
-    }
+    if (ctx->tab_dirty && nk_refresh_tables(ctx, variant)) return -1;
     // experiment (NK_L2_PERSIST=1): keep the (mode, subvolume) table in the persisting part of the L2 while 8 GB of particle
     // state stream through it
     if (variant == 4 && ctx->l2_persist && !ctx->l2_window_set) {
@@ -744,14 +783,14 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
         if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
         ctx->l2_window_set = true;
     }
-    nk_step_fn kern = nk_pick_step(variant, ctx->has_rough, fast, relax, flux);
+    nk_step_fn kern = nk_pick_step(variant, ctx->has_rough, kind, relax, flux);
     if (!ctx->step_blocks || ctx->step_blocks_variant != variant) {
         int per_sm = 0;
         for (int r = 0; r < 2; ++r) for (int f = 0; f < 2; ++f) {       // every variant may need the opt-in shared memory size
-            nk_step_fn k = nk_pick_step(variant, ctx->has_rough, fast, r, f);
+            nk_step_fn k = nk_pick_step(variant, ctx->has_rough, kind, r, f);
             if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nk_pick_step(variant, ctx->has_rough, fast, true, true), NK_STEP_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nk_pick_step(variant, ctx->has_rough, kind, true, true), NK_STEP_THREADS, smem);
         if (per_sm < 1) per_sm = 1;
         ctx->step_blocks = per_sm * ctx->n_sm;
         ctx->step_blocks_variant = variant;
@@ -775,16 +814,15 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     ctx->last_variant = variant;
     }
     if (phase == 1) return 0;
-    const size_t fin_smem = (3 * (size_t)P.S + 2 * (size_t)nk_acc_len(P.S, P.R)) * 8;
+    const size_t fin_smem = nk_rare_fin_doubles(P.S, P.R) * 8;
     const bool tiled = P.F > NK_RARE_FACES || ctx->force_tiled;
     ctx->last_rare_tiled = tiled;
-    const size_t rare_smem = fin_smem + (tiled ? NK_TILE_SMEM_BYTES : 0);
+    const size_t rare_smem = tiled ? fin_smem + NK_TILE_SMEM_BYTES : nk_rare_smem_bytes(P.S, P.R, P.F, P.nf);
     if (!ctx->rare_attr_set) {
-        // k_rare keeps ~25 KB of static shared memory (triangles + facet tables): opt in when static + dynamic exceed 48 KB
-        const int want = (int)(fin_smem + NK_TILE_SMEM_BYTES);
-        if (want + 26 * 1024 > 48 * 1024) {
-            cudaFuncSetAttribute(k_rare<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem);
-            cudaFuncSetAttribute(k_rare<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem);
+        const int want = (int)std::max(fin_smem + NK_TILE_SMEM_BYTES, nk_rare_smem_bytes(P.S, P.R, P.F, P.nf));
+        if (want > 48 * 1024) {
+            cudaFuncSetAttribute(k_rare<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+            cudaFuncSetAttribute(k_rare<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
             cudaFuncSetAttribute(k_rare_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
             cudaFuncSetAttribute(k_rare_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
         }
@@ -793,10 +831,11 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     // one item per thread; the number of items is known on the device only, so size the grid for ~5 % of the slots
     // (hits + emission are 0.2-2 % of the particles per step; more items are covered by the grid-stride loop)
     const long long want_blocks = (ctx->h_slots_hint / 20 + NK_RARE_THREADS - 1) / NK_RARE_THREADS;
-    const int rare_blocks = (int)std::min<long long>((long long)ctx->n_sm * 16, std::max<long long>(ctx->n_sm, want_blocks));
+    const int rare_blocks = (int)std::min<long long>((long long)ctx->n_sm * 32, std::max<long long>(ctx->n_sm, want_blocks));
+    const int tiled_blocks = (int)std::min<long long>((long long)ctx->n_sm * 16, std::max<long long>(ctx->n_sm, (ctx->h_slots_hint / 20 + NK_RARE_TILED_THREADS - 1) / NK_RARE_TILED_THREADS));
     if (tiled) {
-        if (fuse_finalize) k_rare_tiled<true><<<rare_blocks, NK_RARE_THREADS, rare_smem, ctx->stream>>>(P);
-        else k_rare_tiled<false><<<rare_blocks, NK_RARE_THREADS, rare_smem, ctx->stream>>>(P);
+        if (fuse_finalize) k_rare_tiled<true><<<tiled_blocks, NK_RARE_TILED_THREADS, rare_smem, ctx->stream>>>(P);
+        else k_rare_tiled<false><<<tiled_blocks, NK_RARE_TILED_THREADS, rare_smem, ctx->stream>>>(P);
     } else {
         if (fuse_finalize) k_rare<true><<<rare_blocks, NK_RARE_THREADS, rare_smem, ctx->stream>>>(P);
         else k_rare<false><<<rare_blocks, NK_RARE_THREADS, rare_smem, ctx->stream>>>(P);
@@ -805,11 +844,7 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     nk_prof_mark(ctx);
     if (fuse_finalize) {
         ctx->h_step += 1; ctx->h_relax_pending = true; ctx->tab_dirty = true;
-        if (variant == 4) {            // next step's tables right away (T_sv is final once k_rare has finished)
-            k_mode_tables<<<ctx->n_sm * 8, 256, nk_hot_smem_bytes(P.S), ctx->stream>>>(P);
-            NK_CK(cudaGetLastError());
-            ctx->tab_dirty = false;
-        }
+        if (nk_refresh_tables(ctx, variant)) return -1;      // next step's tables right away (T_sv is final once k_rare has finished)
         nk_prof_mark(ctx);
     }
     ctx->last_variant = variant;
@@ -828,11 +863,7 @@ int nk_step_finalize(nk_ctx* ctx) {
     k_finalize<<<1, threads, 3 * (size_t)P.S * 8, ctx->stream>>>(P);
     NK_CK(cudaGetLastError());
     ctx->h_step += 1; ctx->h_relax_pending = true; ctx->tab_dirty = true;
-    if (ctx->last_variant == 4) {
-        k_mode_tables<<<ctx->n_sm * 8, 256, nk_hot_smem_bytes(P.S), ctx->stream>>>(P);
-        NK_CK(cudaGetLastError());
-        ctx->tab_dirty = false;
-    }
+    if (nk_refresh_tables(ctx, ctx->last_variant)) return -1;
     nk_prof_mark(ctx);
     return 0;
 }
@@ -871,8 +902,9 @@ int nk_flush_relaxation(nk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (nk_check_ready(ctx)) return -1;
     size_t smem = nk_sv_smem_doubles(ctx->P.S) * 8 + nk_hot_smem_bytes(ctx->P.S);
-    if (ctx->P.is_slice && ctx->P.interp == NK_INTERP_NEAREST) k_flush_relax<true><<<ctx->n_sm * 8, 256, smem, ctx->stream>>>(ctx->P);
-    else k_flush_relax<false><<<ctx->n_sm * 8, 256, smem, ctx->stream>>>(ctx->P);
+    if (ctx->P.is_slice && ctx->P.interp == NK_INTERP_NEAREST) k_flush_relax<NK_KIND_FAST><<<ctx->n_sm * 8, 256, smem, ctx->stream>>>(ctx->P);
+    else if (ctx->P.is_slice && ctx->P.interp == NK_INTERP_LINEAR) k_flush_relax<NK_KIND_SLICE_LINEAR><<<ctx->n_sm * 8, 256, smem, ctx->stream>>>(ctx->P);
+    else k_flush_relax<NK_KIND_GENERAL><<<ctx->n_sm * 8, 256, smem, ctx->stream>>>(ctx->P);
     NK_CK(cudaGetLastError());
     k_clear_relax<<<1, 1, 0, ctx->stream>>>(ctx->P);
     NK_CK(cudaGetLastError());

@@ -27,7 +27,7 @@ __host__ __device__ static inline size_t nk_sv_smem_doubles(int S) { return (siz
 // Mesh.find_boundary operator seam: one ray per thread, the triangles stream through shared memory in TMA-staged tiles
 // (nk_tiles.cuh).  Launch with NK_TILE_SMEM_BYTES of dynamic shared memory.
 #define NK_RAY_THREADS 256
-__global__ void __launch_bounds__(NK_RAY_THREADS) k_find_boundary(NkP P, long long n, const double* __restrict__ x,
+__global__ void __launch_bounds__(NK_RAY_THREADS, 4) k_find_boundary(NkP P, long long n, const double* __restrict__ x,
                                                                    const double* __restrict__ v, double* __restrict__ xc,
                                                                    double* __restrict__ tc, int* __restrict__ fc) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(NK_RAY_THREADS) k_find_boundary(NkP P, long lo
 }
 
 // first collision of every live slot (Population.py:308-316): P = N rays against all F triangles
-__global__ void __launch_bounds__(NK_RAY_THREADS) k_init_collisions(NkP P) {
+__global__ void __launch_bounds__(NK_RAY_THREADS, 4) k_init_collisions(NkP P) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     NkTilePipe tp;
     nk_tiles_init(tp, tile_smem, P);

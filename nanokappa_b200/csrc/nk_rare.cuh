@@ -138,7 +138,7 @@ __device__ __forceinline__ void nk_emit_particle(const NkP& P, const NkGeo& G, d
     double x0, y0, z0;
     nk_emit_setup(P, r, m, id, uface, us, ur, p, x0, y0, z0);
     double t = CUDART_INF; int cf = -1;
-    nk_ray_faces(G.faces, P.F, x0, y0, z0, p.vx, p.vy, p.vz, t, cf);
+    nk_ray_faces_small(G.faces, P.F, x0, y0, z0, p.vx, p.vy, p.vz, t, cf);
     if (nk_emit_post(P, acc, r, dt_in, x0, y0, z0, t, cf, p)) nk_boundary_events(P, G, p, step, acc);
     nk_emit_finish(P, acc, p, with_flux);
 }
@@ -201,21 +201,24 @@ __device__ __forceinline__ void nk_emit_one_to_one(const NkP& P, const NkGeo& G,
 // load hit-list entry w: from its dense record when it has one, from the particle arrays otherwise; cold fields
 // (collision facet / point) always come from the arrays, the id only when a rough wall needs it
 __device__ __forceinline__ long long nk_load_hit(const NkP& P, unsigned int w, NkParticle& p) {
-    long long i;
+    // the slot comes from the hit list (4 B, coalesced), so the record and the four cold fields are independent loads in
+    // flight together: one DRAM round trip less on the item's dependency chain
+    const long long i = P.hitlist[w];
+    const int cf = P.cfacet[i];
+    const double cx = P.cx[i], cy = P.cy[i], cz = P.cz[i];
     if ((long long)w < P.hitrec_cap) {
         const double4* r = reinterpret_cast<const double4*>(P.hitrec + w);
         const double4 a = r[0], b = r[1];
         p.x = a.x; p.y = a.y; p.z = a.z; p.tc = a.w; p.occ = b.x;
-        i = __double2loint(b.y); p.mode = __double2hiint(b.y); p.omode = __double2loint(b.z);
+        p.mode = __double2hiint(b.y); p.omode = __double2loint(b.z);
     } else {
-        i = P.hitlist[w];
         p.x = P.px[i]; p.y = P.py[i]; p.z = P.pz[i]; p.tc = P.tc[i]; p.occ = P.occ[i];
         p.mode = P.mode[i]; p.omode = P.omode[i];
     }
     const NkMode m = P.mprop[p.mode];
     p.vx = m.vx; p.vy = m.vy; p.vz = m.vz;
     p.omega = (p.omode == p.mode) ? m.omega : P.mprop[p.omode].omega;
-    p.cf = P.cfacet[i]; p.cx = P.cx[i]; p.cy = P.cy[i]; p.cz = P.cz[i];
+    p.cf = cf; p.cx = cx; p.cy = cy; p.cz = cz;
     p.id = -1; p.slot = i; p.alive = true; p.mode_changed = false; p.occ_changed = false;
     return i;
 }
@@ -412,12 +415,22 @@ __global__ void __launch_bounds__(1024) k_finalize(NkP P) {
 //   k_rare_tiled  larger meshes: the threads of a block advance their items in lock step -- everybody runs until it
 //                 needs a ray (or is done), then the block sweeps the triangle tiles together (nk_tiles.cuh) -- so a
 //                 tile is fetched once per block and round instead of once per ray.
-#define NK_RARE_THREADS 128
+#ifndef NK_RARE_THREADS
+#define NK_RARE_THREADS 128         // (64-thread blocks with 8 blocks/SM were measured: 0.134 vs 0.123 ms on the film, equal on the rough bar)
+#endif
 #define NK_RARE_FACES 128
 #define NK_RARE_FACETS 64
 #ifndef NK_RARE_MIN_BLOCKS
 #define NK_RARE_MIN_BLOCKS 4
 #endif
+// dynamic shared memory of k_rare: [closing block scratch 3S | block accumulators 2 nacc | faces | facet tables]
+__host__ __device__ inline size_t nk_rare_fin_doubles(int S, int R) { return 3 * (size_t)S + 2 * (size_t)nk_acc_len(S, R); }
+__host__ __device__ inline size_t nk_rare_smem_bytes(int S, int R, int F, int nf) {
+    size_t b = nk_rare_fin_doubles(S, R) * 8;
+    if (F <= NK_RARE_FACES) b += (size_t)F * sizeof(NkFace);
+    if (nf <= NK_RARE_FACETS) b += (size_t)nf * (6 * 8 + 4 * 4);
+    return b + 16;
+}
 
 // merge of a block's private accumulators + the closing protocol shared by both kernels
 __device__ __forceinline__ void nk_rare_merge(const NkP& P, const double* racc, const long long* rq) {
@@ -460,9 +473,6 @@ __device__ __forceinline__ void nk_rare_close(const NkP& P, double* sm_fin, int*
 
 template <bool FUSE>
 __global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(NkP P) {
-    __shared__ NkFace sfaces[NK_RARE_FACES];
-    __shared__ int sfi[4 * NK_RARE_FACETS];
-    __shared__ double sfd[6 * NK_RARE_FACETS];
     extern __shared__ double sm_fin[];
     __shared__ int s_last;
     NkGeo G;
@@ -472,20 +482,25 @@ __global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(Nk
     // blocks beyond the work list (most of them when few particles hit a wall) go straight to the closing protocol
     const bool has_work = (unsigned long long)blockIdx.x * blockDim.x < (unsigned long long)P.dyn->n_hits + P.dyn->n_emit;
     if (has_work) {
+        double* extra = sm_fin + nk_rare_fin_doubles(P.S, P.R);
         if (P.F <= NK_RARE_FACES) {
             const double* src = reinterpret_cast<const double*>(P.faces);
-            double* dst = reinterpret_cast<double*>(sfaces);
-            for (int k = threadIdx.x; k < P.F * (int)(sizeof(NkFace) / 8); k += blockDim.x) dst[k] = src[k];
+            NkFace* sfaces = reinterpret_cast<NkFace*>(extra);
+            for (int k = threadIdx.x; k < P.F * (int)(sizeof(NkFace) / 8); k += blockDim.x) extra[k] = src[k];
             G.faces = sfaces;
+            extra += (size_t)P.F * (sizeof(NkFace) / 8);
         }
         if (P.nf <= NK_RARE_FACETS) {
-            for (int k = threadIdx.x; k < P.nf; k += blockDim.x) {
-                sfi[k] = P.facet_bc[k]; sfi[NK_RARE_FACETS + k] = P.facet_partner[k];
-                sfi[2 * NK_RARE_FACETS + k] = P.facet_res[k]; sfi[3 * NK_RARE_FACETS + k] = P.facet_rough[k];
+            const int nf = P.nf;
+            double* sfd = extra;                                  // normals (3 nf), centroids (3 nf)
+            int* sfi = reinterpret_cast<int*>(extra + 6 * nf);    // bc, partner, res, rough (nf each)
+            for (int k = threadIdx.x; k < nf; k += blockDim.x) {
+                sfi[k] = P.facet_bc[k]; sfi[nf + k] = P.facet_partner[k];
+                sfi[2 * nf + k] = P.facet_res[k]; sfi[3 * nf + k] = P.facet_rough[k];
             }
-            for (int k = threadIdx.x; k < 3 * P.nf; k += blockDim.x) { sfd[k] = P.facet_normal[k]; sfd[3 * NK_RARE_FACETS + k] = P.facet_centroid[k]; }
-            G.bc = sfi; G.partner = sfi + NK_RARE_FACETS; G.res = sfi + 2 * NK_RARE_FACETS; G.rough = sfi + 3 * NK_RARE_FACETS;
-            G.normal = sfd; G.centroid = sfd + 3 * NK_RARE_FACETS;
+            for (int k = threadIdx.x; k < 3 * nf; k += blockDim.x) { sfd[k] = P.facet_normal[k]; sfd[3 * nf + k] = P.facet_centroid[k]; }
+            G.bc = sfi; G.partner = sfi + nf; G.res = sfi + 2 * nf; G.rough = sfi + 3 * nf;
+            G.normal = sfd; G.centroid = sfd + 3 * nf;
         }
         // block-private accumulators: thousands of items would otherwise hammer the same ~40 global addresses
         double* racc = sm_fin + 3 * P.S;
@@ -521,8 +536,9 @@ __global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(Nk
 #define NK_ITEM_EMIT_NEXT 1      // emission entry: pick the next copy that belongs to this rank
 #define NK_ITEM_EMIT_RAY 2       // waiting for the first-collision ray of a new particle
 #define NK_ITEM_EVENTS 3         // inside the boundary event loop
+#define NK_RARE_TILED_THREADS 128    // rays that share one fetch of a triangle tile
 template <bool FUSE>
-__global__ void __launch_bounds__(NK_RARE_THREADS, 2) k_rare_tiled(NkP P) {
+__global__ void __launch_bounds__(NK_RARE_TILED_THREADS, 2) k_rare_tiled(NkP P) {
     extern __shared__ __align__(128) unsigned char rare_smem[];
     __shared__ int s_last;
     double* sm_fin = reinterpret_cast<double*>(rare_smem + NK_TILE_SMEM_BYTES);
@@ -620,7 +636,7 @@ __global__ void __launch_bounds__(NK_RARE_THREADS, 2) k_rare_tiled(NkP P) {
 
 // apply the deferred lifetime_scattering so that `occ` is what the reference holds after run_timestep
 // (same arithmetic as the head of k_step, so flushing between steps is bit-neutral)
-template <bool FAST>
+template <int KIND>
 __global__ void __launch_bounds__(256) k_flush_relax(NkP P) {
     extern __shared__ double sm[];
     NkSvSmem s = nk_load_sv(P, sm);
@@ -637,7 +653,7 @@ __global__ void __launch_bounds__(256) k_flush_relax(NkP P) {
         nk_ld256(&P.mhot[md].t[0], mt);
         double omega = om == md ? ma.x : P.mhot[om].omega;
         double be0; int g0;
-        P.occ[i] = nk_relax_particle<FAST>(P, s, h, P.px[i], P.py[i], P.pz[i], md, omega, nk_mul(P.hbar, omega), mt, P.occ[i], be0, g0);
+        P.occ[i] = nk_relax_particle<KIND>(P, s, h, P.px[i], P.py[i], P.pz[i], md, omega, nk_mul(P.hbar, omega), mt, P.occ[i], be0, g0);
     }
 }
 __global__ void k_clear_relax(NkP P) { P.dyn->relax_pending = 0; }

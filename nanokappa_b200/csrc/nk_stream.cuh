@@ -107,14 +107,29 @@ __device__ __forceinline__ void nk_ld256(const double* p, double4& v) {
 }
 
 
+// Kernel kinds (compile-time): how subvolume and particle temperature are found
+#define NK_KIND_GENERAL 0        // grid / voronoi subvolumes (nearest centre by squared distance), nearest or RBF temperature
+#define NK_KIND_FAST 1           // slice subvolumes + nearest temperature rule (the Si/Ge thin-film configurations)
+#define NK_KIND_SLICE_LINEAR 2   // slice subvolumes + linear interpolation between the slice centres (parameters_test.txt)
+
+// interp1d(kind='linear', fill_value='extrapolate') on the slice axis, given the slice g that holds xa (Population.py:570-573):
+// idx = searchsorted(centres, xa) clipped to [1, S-1] follows from g and one comparison with the centre of slice g
+__device__ __forceinline__ double nk_linear_T(const NkP& P, const NkSvSmem& s, const NkSvHot& h, double xa, int g) {
+    int idx = xa > s.sv_axis[g] ? g + 1 : g;
+    idx = max(1, min(idx, P.S - 1));
+    const double xl = s.sv_axis[idx - 1], xh = s.sv_axis[idx];
+    const double inv = h.tw[idx];                                              // 1 / (xh - xl), see nk_load_hot
+    return ((xa - xl) * inv) * s.T_sv[idx] + ((xh - xa) * inv) * s.T_sv[idx - 1];
+}
+
 // lifetime_scattering of one particle (Population.py:1701-1710) at its position BEFORE the drift of the
 // next step.  Returns the relaxed occupation; be0 / g0 = equilibrium occupation and slice used (FAST).
-template <bool FAST>
+template <int KIND>
 __device__ __forceinline__ double nk_relax_particle(const NkP& P, const NkSvSmem& s, const NkSvHot& h, double x, double y, double z,
                                                     int mode, double omega, double a, const double4& mt, double occ,
                                                     double& be0, int& g0) {
     double tau;
-    if (FAST) {
+    if (KIND == NK_KIND_FAST) {
         const double xa = P.axis == 0 ? x : (P.axis == 1 ? y : z);
         double lo_b, hi_b;
         g0 = nk_slice_lookup(P, h.midp, s.sv_mid, xa, lo_b, hi_b);                        // interp1d 'nearest'
@@ -134,13 +149,11 @@ __device__ __forceinline__ double nk_relax_particle(const NkP& P, const NkSvSmem
         // temperature only feeds occupations, so reciprocals replace IEEE divisions (1e-16 relative), and the lifetime
         // comes from the tau slabs of the mode record already in registers whenever T lies inside them.
         double Ti;
-        if (P.is_slice && P.interp == NK_INTERP_LINEAR && P.S > 1) {
+        if (KIND == NK_KIND_SLICE_LINEAR) {
             const double xa = P.axis == 0 ? x : (P.axis == 1 ? y : z);
-            int idx = nk_searchsorted_left(s.sv_axis, P.S, xa, P.sv_inv_dx);
-            idx = max(1, min(idx, P.S - 1));
-            const double xl = s.sv_axis[idx - 1], xh = s.sv_axis[idx];
-            const double inv = h.tw[idx];                                              // 1 / (xh - xl), see nk_load_hot
-            Ti = ((xa - xl) * inv) * s.T_sv[idx] + ((xh - xa) * inv) * s.T_sv[idx - 1];
+            double lo_b, hi_b;
+            const int g = nk_slice_lookup(P, h.midp, s.sv_mid, xa, lo_b, hi_b);
+            Ti = P.S > 1 ? nk_linear_T(P, s, h, xa, g) : s.T_sv[0];
         } else {
             Ti = nk_particle_T(P, s.svc, s.sv_axis, s.sv_mid, s.T_sv, x, y, z, -1);
         }
@@ -235,7 +248,7 @@ __device__ __forceinline__ void nk_emit_scan(const NkP& P) {
 
 // one live particle: deferred relaxation -> drift -> (if no collision this step) subvolume + energy bins.
 // Returns true when the particle's collision falls inside this step (it then goes to the hit list).
-template <bool HAS_ROUGH, bool FAST, bool RELAX, bool FLUX>
+template <bool HAS_ROUGH, int KIND, bool RELAX, bool FLUX>
 __device__ __forceinline__ bool nk_step_particle(const NkP& P, const NkSvSmem& s, const NkSvHot& h, long long* binE, long long* binF,
                                                  double* binX, unsigned int* binC, int md, int om, double& x, double& y, double& z,
                                                  double& tc, double& occ) {
@@ -248,12 +261,12 @@ __device__ __forceinline__ bool nk_step_particle(const NkP& P, const NkSvSmem& s
     const double a = nk_mul(P.hbar, omega);
     const double dt = P.dt;
     double be0 = 0.0; int g0 = -1;
-    if (RELAX) occ = nk_relax_particle<FAST>(P, s, h, x, y, z, md, omega, a, mt, occ, be0, g0);
+    if (RELAX) occ = nk_relax_particle<KIND>(P, s, h, x, y, z, md, omega, a, mt, occ, be0, g0);
     x = nk_add(x, nk_mul(ma.y, dt)); y = nk_add(y, nk_mul(ma.z, dt)); z = nk_add(z, nk_mul(ma.w, dt));
     tc = nk_sub(tc, 1.0);
     if (tc < 0.0) return true;
     int sv;
-    if (FAST) {
+    if (KIND != NK_KIND_GENERAL) {
         // nearest centre of a slice stack = 1-D lookup; inside 1e-6 A of a slice boundary the full
         // squared-distance comparison decides, so the index equals the reference's
         const double xa = P.axis == 0 ? x : (P.axis == 1 ? y : z);
@@ -264,7 +277,9 @@ __device__ __forceinline__ bool nk_step_particle(const NkP& P, const NkSvSmem& s
         sv = nk_classify(P, s.svc, s.sv_mid, x, y, z);
     }
     double be1 = be0;
-    if (!(FAST && RELAX && sv == g0)) be1 = nk_bose_fast(a, omega, h.invb[sv]);
+    // (a per-(mode, subvolume) table of this occupation for the general kinds was measured: no gain -- the gather costs what
+    //  the exponential saves, profiles/README.md)
+    if (!(KIND == NK_KIND_FAST && RELAX && sv == g0)) be1 = nk_bose_fast(a, omega, h.invb[sv]);
     const double e = a * (occ - be1);
     nk_bin_add(binE + sv, binX + sv, e, NK_QE);
     atomicAdd(binC + sv, 1u);
@@ -330,7 +345,7 @@ __device__ __forceinline__ void nk_flush_bins(const NkP& P, const long long* bin
 }
 
 // ---- variant A: direct 128-bit global loads/stores (any capacity) ------------------------------------------
-template <bool HAS_ROUGH, bool FAST, bool RELAX, bool FLUX>
+template <bool HAS_ROUGH, int KIND, bool RELAX, bool FLUX>
 __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step(NkP P) {
     extern __shared__ double sm[];
     NkSvSmem s = nk_load_sv(P, sm);
@@ -366,8 +381,8 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step(Nk
             if (HAS_ROUGH) OM = *reinterpret_cast<const int2*>(P.omode + base);
         }
         bool h0 = false, h1 = false;
-        if (base < n && MD.x >= 0) h0 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.x, OM.x, X.x, Y.x, Z.x, TC.x, OC.x);
-        if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle<HAS_ROUGH, FAST, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.y, OM.y, X.y, Y.y, Z.y, TC.y, OC.y);
+        if (base < n && MD.x >= 0) h0 = nk_step_particle<HAS_ROUGH, KIND, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.x, OM.x, X.x, Y.x, Z.x, TC.x, OC.x);
+        if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle<HAS_ROUGH, KIND, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.y, OM.y, X.y, Y.y, Z.y, TC.y, OC.y);
         nk_push_hits(P, lane, h0, h1, base, X, Y, Z, TC, OC, MD, OM);
         if (inb) {
             *reinterpret_cast<double2*>(P.px + base) = X;
@@ -511,17 +526,23 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step_ta
 
 // ---- launch-uniform variants: RELAX (a deferred relaxation is pending), FLUX (convergence step), rough walls present ----
 typedef void (*nk_step_fn)(NkP);
-template <bool TAB, bool A, bool B, bool C, bool D>
-static nk_step_fn nk_pick5() { return TAB ? (nk_step_fn)k_step_tab<A, B, C, D> : (nk_step_fn)k_step<A, B, C, D>; }
-template <bool TAB, bool A, bool B, bool C>
-static nk_step_fn nk_pick4(bool d) { return d ? nk_pick5<TAB, A, B, C, true>() : nk_pick5<TAB, A, B, C, false>(); }
-template <bool TAB, bool A, bool B>
-static nk_step_fn nk_pick3(bool c, bool d) { return c ? nk_pick4<TAB, A, B, true>(d) : nk_pick4<TAB, A, B, false>(d); }
-template <bool TAB, bool A>
-static nk_step_fn nk_pick2(bool b, bool c, bool d) { return b ? nk_pick3<TAB, A, true>(c, d) : nk_pick3<TAB, A, false>(c, d); }
-template <bool TAB>
-static nk_step_fn nk_pick1(bool a, bool b, bool c, bool d) { return a ? nk_pick2<TAB, true>(b, c, d) : nk_pick2<TAB, false>(b, c, d); }
-// variant 4 = per-(mode, subvolume) tables (needs FAST), 0 = direct
-static nk_step_fn nk_pick_step(int variant, bool rough, bool fast, bool relax, bool flux) {
-    return variant == 4 ? nk_pick1<true>(rough, true, relax, flux) : nk_pick1<false>(rough, fast, relax, flux);
+template <int KIND>
+static nk_step_fn nk_pick_kind(bool a, bool c, bool d) {
+    return a ? (c ? (d ? (nk_step_fn)k_step<true, KIND, true, true> : (nk_step_fn)k_step<true, KIND, true, false>)
+                  : (d ? (nk_step_fn)k_step<true, KIND, false, true> : (nk_step_fn)k_step<true, KIND, false, false>))
+             : (c ? (d ? (nk_step_fn)k_step<false, KIND, true, true> : (nk_step_fn)k_step<false, KIND, true, false>)
+                  : (d ? (nk_step_fn)k_step<false, KIND, false, true> : (nk_step_fn)k_step<false, KIND, false, false>));
+}
+static nk_step_fn nk_pick_tab(bool a, bool c, bool d) {
+    return a ? (c ? (d ? (nk_step_fn)k_step_tab<true, true, true, true> : (nk_step_fn)k_step_tab<true, true, true, false>)
+                  : (d ? (nk_step_fn)k_step_tab<true, true, false, true> : (nk_step_fn)k_step_tab<true, true, false, false>))
+             : (c ? (d ? (nk_step_fn)k_step_tab<false, true, true, true> : (nk_step_fn)k_step_tab<false, true, true, false>)
+                  : (d ? (nk_step_fn)k_step_tab<false, true, false, true> : (nk_step_fn)k_step_tab<false, true, false, false>));
+}
+// variant 4 = per-(mode, subvolume) tables of {n0, decay} (needs NK_KIND_FAST), 0 = direct
+static nk_step_fn nk_pick_step(int variant, bool rough, int kind, bool relax, bool flux) {
+    if (variant == 4) return nk_pick_tab(rough, relax, flux);
+    return kind == NK_KIND_FAST ? nk_pick_kind<NK_KIND_FAST>(rough, relax, flux)
+                                : (kind == NK_KIND_SLICE_LINEAR ? nk_pick_kind<NK_KIND_SLICE_LINEAR>(rough, relax, flux)
+                                                                : nk_pick_kind<NK_KIND_GENERAL>(rough, relax, flux));
 }

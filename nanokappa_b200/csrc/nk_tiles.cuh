@@ -4,16 +4,16 @@
 //
 // The reference intersects P rays with all F triangles through dense (P, F) temporaries (Population.py:810 chunks P).
 // Here the rays of a block keep their running minimum in registers while the triangles stream through shared memory in
-// tiles of NK_TILE_FACES records (160 B each), staged by the bulk async-copy engine (cp.async.bulk, SASS UBLKCP) into two
+// tiles of NK_TILE_FACES records (208 B each), staged by the bulk async-copy engine (cp.async.bulk, SASS UBLKCP) into two
 // stages guarded by one mbarrier each: the copy of tile t+1 overlaps the sweep of tile t.  Every thread reads the same
-// triangle at the same time (shared-memory broadcast), so the kernel is bound by the FP64 pipe: 11 DADD/DMUL per
-// (ray, triangle) for the plane test plus a reciprocal-based filter that keeps the IEEE division for the few candidates
-// that can still beat the running minimum (nk_ray_faces).  A mesh of at most one tile is loaded once per block and stays
+// triangle at the same time (shared-memory broadcast), so the kernel is bound by the FP64 pipe: ~23 FP64 instructions per
+// (ray, triangle) in the divergence-free pre-filter of nk_ray_faces, the reference's exact arithmetic only for the few
+// candidates that survive it.  A mesh of at most one tile is loaded once per block and stays
 // resident.  Tiles are swept in face order with a strict `<`, so ties resolve to the lowest face index like np.argmax.
 #pragma once
 
-#define NK_TILE_FACES 128
-#define NK_TILE_STAGE_BYTES (NK_TILE_FACES * (int)sizeof(NkFace))           // 20 KB
+#define NK_TILE_FACES 96
+#define NK_TILE_STAGE_BYTES (NK_TILE_FACES * (int)sizeof(NkFace))           // 19.5 KB
 #define NK_TILE_SMEM_BYTES (2 * NK_TILE_STAGE_BYTES + 128)                  // two stages + the mbarriers
 
 __device__ __forceinline__ unsigned int nk_smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
@@ -78,7 +78,10 @@ __device__ __forceinline__ void nk_tiles_init(NkTilePipe& tp, unsigned char* sme
 __device__ __forceinline__ void nk_tiles_sweep(NkTilePipe& tp, const NkP& P, bool need, double x, double y, double z,
                                                double vx, double vy, double vz, double& tbest, int& fbest) {
     if (tp.resident) {
-        if (need) nk_ray_faces(tp.buf, P.F, x, y, z, vx, vy, vz, tbest, fbest);
+        if (need) {
+            if (P.F <= 32) nk_ray_faces_small(tp.buf, P.F, x, y, z, vx, vy, vz, tbest, fbest);
+            else nk_ray_faces(tp.buf, P.F, P.mesh_scale, x, y, z, vx, vy, vz, tbest, fbest);
+        }
         return;
     }
     const int F = P.F, nt = (F + NK_TILE_FACES - 1) / NK_TILE_FACES;
@@ -91,7 +94,7 @@ __device__ __forceinline__ void nk_tiles_sweep(NkTilePipe& tp, const NkP& P, boo
         const int b = t & 1;
         nk_mbar_wait(&tp.bar[b], b ? tp.parity1 : tp.parity0);
         if (b) tp.parity1 ^= 1u; else tp.parity0 ^= 1u;
-        if (need) nk_ray_faces(tp.buf + (size_t)b * NK_TILE_FACES, min(NK_TILE_FACES, F - t * NK_TILE_FACES), x, y, z, vx, vy, vz, tbest, fbest);
+        if (need) nk_ray_faces(tp.buf + (size_t)b * NK_TILE_FACES, min(NK_TILE_FACES, F - t * NK_TILE_FACES), P.mesh_scale, x, y, z, vx, vy, vz, tbest, fbest);
         if (t + 2 < nt) {
             __syncthreads();                         // everybody has left stage b: refill it
             if (threadIdx.x == 0) nk_tile_issue(tp, P, b, t + 2);

@@ -10,9 +10,11 @@
 #define NK_EMIT_CMAX 64         // copies of one mode a reservoir may emit per step (id packing)
 #define NK_EMIT_ID_BASE (1LL << 62)
 
-// one triangle, everything find_boundary needs (Mesh.py:806-856), 20 doubles = 160 B
+// one triangle, everything find_boundary needs (Mesh.py:806-856), 26 doubles = 208 B (a multiple of 16: bulk-copyable)
 struct NkFace {
     double nx, ny, nz, k;        // plane: x.n + k = 0
+    double mx, my, mz;           // centre of the widened AABB                     } conservative pre-filter of nk_ray_faces:
+    double ex, ey, ez;           // its half extents + 1e-6 x mesh scale           } never decides a hit, only skips faces
     double lox, loy, loz;        // face AABB already widened by -tol / +tol (Mesh.py:828-829)
     double hix, hiy, hiz;
     double ox, oy, oz;           // vertex 0
@@ -87,6 +89,7 @@ struct NkP {
     const int* res_face_ptr; const int* res_faces; const double* res_face_cdf;
     const double* face_vertices;      // (F,3,3)
     double blo[3], bhi[3];
+    double mesh_scale;                // max |coordinate| / |plane offset| of the mesh (error bounds of the ray pre-filter)
     // ---- subvolumes
     int S, is_slice, axis, interp;
     const double* svc;                // (S,3)
@@ -129,6 +132,9 @@ struct NkP {
     // ---- rough-wall LUTs (Fr, M)
     int has_rough;                    // 0: no rough facet, the omega-carrying mode is always the mode itself (omode == mode)
     int Fr; const double* specularity; const unsigned char* true_spec; const int* spec_out; const double* roulette;
+    // guide table of the diffuse roulette (only when every row is non-decreasing): rou_guide[f][b] = first index whose cumulative
+    // rate reaches (b / rou_guide_k) x total, so the bisection starts inside a bracket of ~M / rou_guide_k entries
+    const int* rou_guide; int rou_guide_k;
     // ---- particles (borrowed)
     long long cap;
     double *px, *py, *pz, *tc, *occ;

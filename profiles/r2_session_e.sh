@@ -1,0 +1,11 @@
+set -x
+cd $GRAFT_REPO_ROOT
+python -m pytest tests -m gpu -q -x > gpurun_out/r2e_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2e_pytest.log; tail -4 gpurun_out/r2e_pytest.log
+for lib in libnk_b200.so libnk_b200_rare5.so libnk_b200_rare6.so; do
+  NK_LIB=$PWD/nanokappa_b200/$lib python bench.py --case c1 --eta 5 --particles 2e7 --steps 20 --warmup 5 --no-cpu --sustained-steps 0 --e2e-calls 1 > gpurun_out/r2e_c1_$lib.json 2> gpurun_out/r2e_c1_$lib.err
+  python -c "import json,sys; d=json.load(open('gpurun_out/r2e_c1_$lib.json')); r=d['roofline']; print('$lib c1', d['value'], d['ms_per_step'], r['avg_launch_ms'], r['frac'], r['kernel_share_of_step'])"
+  NK_LIB=$PWD/nanokappa_b200/$lib python bench.py --particles 1e8 --steps 20 --warmup 5 --no-cpu --sustained-steps 0 --e2e-calls 1 > gpurun_out/r2e_film_$lib.json 2> gpurun_out/r2e_film_$lib.err
+  python -c "import json,sys; d=json.load(open('gpurun_out/r2e_film_$lib.json')); r=d['roofline']; print('$lib film', d['value'], d['ms_per_step'], r['avg_launch_ms'], r['frac'], r['kernel_share_of_step'])"
+done
+NK_STEP_TAB=0 python bench.py --case c1 --eta 5 --particles 2e7 --steps 20 --warmup 5 --no-cpu --sustained-steps 0 --e2e-calls 1 > gpurun_out/r2e_c1_notab.json 2> gpurun_out/r2e_c1_notab.err
+python -c "import json,sys; d=json.load(open('gpurun_out/r2e_c1_notab.json')); r=d['roofline']; print('c1 no be_tab', d['value'], d['ms_per_step'], r['avg_launch_ms'], r['frac'], r['kernel_share_of_step'])"
