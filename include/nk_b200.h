@@ -208,6 +208,15 @@ int nk_get_results(nk_ctx* ctx, double* T_sv, double* E_sv, int64_t* N_sv, doubl
                    double* kappa_sv, double* kappa, double* res_E_bal, double* res_flux,
                    int64_t* N_leaving, double* total_energy);
 
+/* The same without stalling the device: nk_snapshot_results enqueues a copy of the results block as it will be after the steps
+ * enqueued so far (pinned host ring of four; *ticket identifies it) and returns at once, so the caller can enqueue the next
+ * batch of steps before it looks at the numbers; nk_get_snapshot waits for that copy only.  This is how the command line
+ * writes its convergence.txt rows (every n_dt_to_conv steps, Population.py:1762-1767) while the GPU keeps stepping. */
+int nk_snapshot_results(nk_ctx* ctx, int* ticket);
+int nk_get_snapshot(nk_ctx* ctx, int ticket, double* T_sv, double* E_sv, int64_t* N_sv, double* flux,
+                    double* kappa_sv, double* kappa, double* res_E_bal, double* res_flux,
+                    int64_t* N_leaving, double* total_energy);
+
 /* Population.contains_check (Population.py:1712-1722), detection half: the slots of the live particles that lie outside
  * the mesh bounding box by more than tol (upstream: 1e-10) are written to slots_dev (device, capacity `cap`; unordered),
  * their number to *n_found (may exceed cap: call again with a larger buffer).  The caller re-draws those particles

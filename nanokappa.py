@@ -68,6 +68,11 @@ def main(argv=None):
     geo = Geometry(args)
     phonons = Phonon(args, 0)
     pop = Population(args, geo, phonons)
+    # the steps between two convergence rows go to the GPU as one batch and the rows are read back asynchronously
+    # (Population.step_batching); NK_STEP_BATCH=0 restores one launch sequence per run_timestep call
+    pop.step_batching = os.environ.get('NK_STEP_BATCH', '1') != '0'
+    loop_start = datetime.now()
+    step0 = pop.current_timestep
     flag = True
     while flag:
         pop.run_timestep(geo, phonons)
@@ -82,6 +87,8 @@ def main(argv=None):
                 go = torch.tensor([int(datetime.now() - start_time < max_time)], device='cuda')
                 dist.all_reduce(go, op=dist.ReduceOp.MIN)
                 flag = flag and bool(go.item())
+    pop.engine.synchronize()
+    loop_time = (datetime.now() - loop_start).total_seconds()
     print('Saving end of run particle data...')
     pop.write_final_state(geo)
     pop.f.close()
@@ -91,6 +98,8 @@ def main(argv=None):
     n_updates = pop.current_timestep * pop.N_p
     print('---------- o ----------- o ------------- o ------------')
     print("Total time: {}  ({:.3e} particle-timestep updates/s incl. set-up and output)".format(total, n_updates / max(total.total_seconds(), 1e-9)))
+    print("Time loop: {:.3f} s for {} timesteps  ({:.3e} particle-timestep updates/s incl. the every-10 / every-100-step output)".format(
+        loop_time, pop.current_timestep - step0, (pop.current_timestep - step0) * pop.N_p / max(loop_time, 1e-9)))
     print('---------- o ----------- o ------------- o ------------')
     if output_file is not None:
         sys.stdout = sys.__stdout__

@@ -63,6 +63,8 @@ SIGNATURES = {
     "nk_profile_begin": (C.c_int, [VP]),
     "nk_profile_end": (C.c_int, [VP, VP, c_lp]),
     "nk_get_results": (C.c_int, [VP] + [VP] * 10),
+    "nk_snapshot_results": (C.c_int, [VP, C.POINTER(C.c_int)]),
+    "nk_get_snapshot": (C.c_int, [VP, C.c_int] + [VP] * 10),
     "nk_energy_table": (C.c_int, [C.c_int, C.c_int, VP, VP, C.c_int, VP, C.c_double, C.c_double, C.c_double, C.c_double, VP]),
     "nk_advance_host": (C.c_int, [VP, C.c_int64, C.c_int] + [VP] * 12 + [c_lp, VP, VP, VP]),
     "nk_last_transfer_bytes": (C.c_int, [VP, c_lp, c_lp]),

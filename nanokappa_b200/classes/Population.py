@@ -574,12 +574,23 @@ class Population(PopulationSetup):
         if self.current_timestep == 0:
             print('Simulating...')
         if (self.current_timestep % 100) == 0:
-            # particle dump: every 100 steps like the reference while it is the cheap text file; the binary checkpoint of a
-            # large population (1 GB per 1e7 particles, ~1 s) every NK_DUMP_EVERY steps (default 1000; 0 = only at the end)
-            every = 100
-            if self.N_p > float(os.environ.get('NK_TEXT_DUMP_PERIODIC_MAX', 2e5)):
-                every = int(os.environ.get('NK_DUMP_EVERY', 1000))
-            if every > 0 and (self.current_timestep % every) == 0:
+            # particle dump: every 100 steps like the reference while it is the cheap text file.  For a large population the
+            # dump is the binary checkpoint (1 GB per 1e7 particles) and 100 steps are milliseconds of GPU time, so it is
+            # written by the wall clock instead -- when NK_DUMP_MIN_SECONDS (default 600) have passed since the last one --
+            # or every NK_DUMP_EVERY steps when that is set; the end-of-run dump is always written
+            small = self.N_p <= float(os.environ.get('NK_TEXT_DUMP_PERIODIC_MAX', 2e5))
+            now = datetime.now()
+            if not hasattr(self, '_last_dump'):
+                self._last_dump = now
+            if small:
+                due = True
+            elif 'NK_DUMP_EVERY' in os.environ:
+                every = int(os.environ['NK_DUMP_EVERY'])
+                due = every > 0 and (self.current_timestep % every) == 0
+            else:
+                due = (now - self._last_dump).total_seconds() >= float(os.environ.get('NK_DUMP_MIN_SECONDS', 600))
+            if due:
+                self._last_dump = now
                 self.write_final_state(geometry, final=False)
             elif self.current_timestep > 0 and hasattr(self.view, 'mean_T'):
                 self.write_subvolume_state(geometry)
@@ -597,16 +608,23 @@ class Population(PopulationSetup):
         if every > 0 and self.current_timestep > 0 and (self.current_timestep % every) == 0 and \
                 self.N_p >= float(os.environ.get('NK_RESORT_MIN', 1e6)):
             self.engine.sort_by_mode()
-        if self.sharded is not None:
-            if self.current_timestep > 0 and (self.current_timestep % 100) == 0:
-                self.sharded.rebalance()               # live counts drift with position-dependent absorption
-            self.sharded.step(1)
-        else:
-            self.engine.step(1)
+        if self.sharded is not None and self.current_timestep > 0 and (self.current_timestep % 100) == 0:
+            self.sharded.rebalance()               # live counts drift with position-dependent absorption
+        self._advance_device()
         self.current_timestep += 1
         self.t = self.current_timestep * self.dt
         if (self.current_timestep % self.n_dt_to_conv) == 0:
-            r = self._pull_results()
+            if self.step_batching and self._tickets:
+                # the next batch goes to the device BEFORE the host looks at this row, so the GPU never waits for the
+                # formatting and the file write (not across a 100-step boundary: that branch inspects the particles)
+                ticket = self._tickets.pop(0)
+                if (self.current_timestep % 100) != 0:
+                    self._enqueue_batch()
+                r = self.engine.results(ticket)
+                self.subvol_temperature, self.subvol_energy, self.subvol_N_p = r['subvol_temperature'], r['subvol_energy'], r['subvol_N_p']
+                self.N_p, self.N_leaving, self.total_energy = r['N_p'], r['N_leaving'], r['total_energy']
+            else:
+                r = self._pull_results()
             self.subvol_heat_flux = r['subvol_heat_flux']
             if geometry.subvol_type == 'slice':
                 self.subvol_kappa, self.kappa = r['subvol_kappa'], r['kappa']
@@ -614,8 +632,45 @@ class Population(PopulationSetup):
                 self.calculate_kappa(geometry)
             self.res_heat_flux, self.res_energy_balance = r['res_heat_flux'], r['res_energy_balance']
             self.write_convergence(geometry)
-        elif (self.current_timestep % 100) == 99:
+        elif (self.current_timestep % 100) == 99 and not self.step_batching:
             self._pull_results()
+
+    # The command line sets `step_batching`: the timesteps between two convergence rows (n_dt_to_conv = 10) are enqueued as
+    # ONE nk_step call followed by an asynchronous snapshot of the results block, and the calls of run_timestep in between
+    # only advance the host's step counter.  The device then runs up to one batch ahead of `current_timestep`; it is level
+    # with it at every multiple of n_dt_to_conv -- where rows are written -- and of 100 -- where particles are dumped,
+    # checked and re-sorted.  Library users who inspect particles between arbitrary steps leave it off (the default).
+    step_batching = False
+
+    def _enqueue_batch(self):
+        B = self.n_dt_to_conv
+        nxt = (self._enqueued_until // B + 1) * B
+        try:
+            nxt = min(nxt, max(int(self.args.iterations[0]), self._enqueued_until + 1))
+        except Exception:
+            pass
+        n = nxt - self._enqueued_until
+        if self.sharded is not None:
+            self.sharded.step(n)
+        else:
+            self.engine.step(n)
+        self._enqueued_until = nxt
+        if (nxt % B) == 0:
+            self._tickets.append(self.engine.snapshot_results())
+
+    def _advance_device(self):
+        if not hasattr(self, '_enqueued_until'):
+            self._enqueued_until, self._tickets = self.current_timestep, []
+        if not self.step_batching or (self.sharded is not None and not self.sharded.fused and self.world > 1):
+            if self._enqueued_until <= self.current_timestep:          # (a batch enqueued before batching was switched off)
+                if self.sharded is not None:
+                    self.sharded.step(1)
+                else:
+                    self.engine.step(1)
+                self._enqueued_until = self.current_timestep + 1
+            return
+        if self._enqueued_until <= self.current_timestep:
+            self._enqueue_batch()
 
     # ---- the reference's per-step methods as seams.  On the GPU drift, emission, boundary scattering and the
     # per-subvolume sums are ONE fused pass over the particles (k_step + k_rare) and the lifetime scattering is deferred to
@@ -628,10 +683,13 @@ class Population(PopulationSetup):
         """Population.drift (Population.py:790-795) -- opens a fused timestep on the device."""
         if getattr(self, '_seam_open', False):
             raise Exception('drift() was already called for this timestep; finish it with lifetime_scattering().')
-        if self.sharded is not None:
-            self.sharded.step(1)
-        else:
-            self.engine.step(1)
+        if getattr(self, '_enqueued_until', self.current_timestep) > self.current_timestep:
+            raise Exception('the device is ahead of current_timestep (step_batching): finish the batch with run_timestep().')
+        batching, self.step_batching = self.step_batching, False
+        try:
+            self._advance_device()
+        finally:
+            self.step_batching = batching
         self._seam_open = True
 
     def _seam_done(self, name):
@@ -814,7 +872,11 @@ class Population(PopulationSetup):
         self.f.close()
 
     def write_convergence(self, geometry):
-        a2s = lambda a, f: np.array2string(np.asarray(a), formatter={'float_kind': f.format}, max_line_width=10 ** 9, threshold=10 ** 9).strip('[]') + ' '
+        """One row of convergence.txt (Population.py:2027-2069).  The reference formats every vector with np.array2string and
+        strips the brackets; the plain joins below give the same characters at a twentieth of the cost (a row every ten
+        timesteps is the host's main job while the GPU steps)."""
+        def a2s(a, f):
+            return ' '.join(f.format(v) for v in np.asarray(a, dtype=float).reshape(-1)) + ' '
         line = datetime.now().strftime('%Y-%m-%dT%H:%M:%S.%f ')
         line += '{:>8d} '.format(int(self.current_timestep))
         line += '{:>12.5e} '.format(self.t)
@@ -828,20 +890,25 @@ class Population(PopulationSetup):
         line += a2s(self.subvol_energy, '{:>12.5e}')
         for i in range(self.n_of_subvols):
             line += a2s(self.subvol_heat_flux[i, :], '{:>14.6e}')
-        line += np.array2string(np.asarray(self.subvol_N_p).astype(int), formatter={'int': '{:>10d}'.format}, max_line_width=10 ** 9, threshold=10 ** 9).strip('[]') + ' '
+        line += ' '.join('{:>10d}'.format(int(v)) for v in np.asarray(self.subvol_N_p).reshape(-1)) + ' '
         if geometry.subvol_type == 'slice':
             line += a2s(self.subvol_kappa, '{:>12.5e}')
             line += '{:>13.6e} '.format(self.kappa)
         else:
             line += a2s(self.svcon_kappa, '{:>14.7e}')
         self.f = open(os.path.join(self.results_folder_name, 'convergence.txt'), 'a+')
-        self.f.writelines(line.replace('\n', ' ') + '\n')
+        self.f.write(line.replace('\n', ' ') + '\n')
         self.f.close()
 
     def write_final_state(self, geometry, final=True):
         """particle_data.txt / subvolumes.txt / subvol_connections.txt (Population.py:2071-2151).  `final=False` marks the
         every-100-steps call of run_timestep."""
         time = datetime.now().strftime('%Y-%m-%dT%H:%M:%S.%f')
+        if getattr(self, '_enqueued_until', self.current_timestep) > self.current_timestep:
+            # a run stopped by --max_sim_time in the middle of a batch: the device state is a few steps ahead; what is saved
+            # is that state, under its own step number
+            self.current_timestep = self._enqueued_until
+            self.t = self.current_timestep * self.dt
         # the reference dumps ~60 bytes of text per particle every 100 steps (0.5 s per 1e5 particles -- a thousand times the
         # cost of the 100 timesteps themselves here -- and 6 GB at 1e8): the exact binary checkpoint (also a valid restart
         # point) replaces the text file above NK_TEXT_DUMP_MAX particles, and above NK_TEXT_DUMP_PERIODIC_MAX for the

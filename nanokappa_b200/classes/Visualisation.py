@@ -38,9 +38,34 @@ class Visualisation(Constants):
 
     def read_convergence(self):
         """Positional parse of convergence.txt: column order is an interface (Population.open_convergence)."""
+        # the file only grows while a run is alive: parse the rows that are new since the last call (the every-100-steps
+        # postprocess of a 10 000-step run would otherwise re-parse up to a thousand rows a hundred times)
+        cache = getattr(self, '_conv_cache', None)
+        size = os.path.getsize(self.convergence_file)
+        if cache is None or cache['file'] != self.convergence_file or size < cache['offset']:
+            cache = self._conv_cache = dict(file=self.convergence_file, offset=0, stamps=[], nums=[])
         with open(self.convergence_file, 'r') as f:
-            rows = [ln.split() for ln in f.readlines()[1:] if ln.strip()]
-        data = np.array(rows)
+            if cache['offset'] == 0:
+                f.readline()                                        # header
+            else:
+                f.seek(cache['offset'])
+            new = f.read()
+            cache['offset'] = f.tell()
+        for ln in new.splitlines():
+            p = ln.split()
+            if p:
+                cache['stamps'].append(p[0])
+                cache['nums'].append(np.array(p[1:], dtype=float))
+        stamps = np.array(cache['stamps'])
+        num = np.array(cache['nums'], dtype=float).reshape(len(cache['nums']), -1)
+
+        class _Cols:                                                # data[:, a:b] of the text table, already numeric
+            def __getitem__(_, key):
+                rows, cols = key
+                if isinstance(cols, int):
+                    return stamps[rows] if cols == 0 else num[rows, cols - 1]
+                return num[rows, slice(cols.start - 1, cols.stop - 1)]
+        data = _Cols()
         S = self.n_of_subvols = self.geometry.n_of_subvols
         R = self.n_of_reservoirs = self.geometry.n_of_reservoirs
         C = self.n_of_subvol_con = self.geometry.n_of_subvol_con

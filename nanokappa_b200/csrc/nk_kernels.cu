@@ -62,6 +62,7 @@ struct nk_ctx {
     int step_blocks_variant = -1;
     bool force_tiled = false;      // NK_RARE_TILED=1: use the tiled rare-path kernel also for small meshes (tests)
     bool rare_attr_set = false;
+    double* snap_host[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t snap_ev[4] = {nullptr, nullptr, nullptr, nullptr}; int snap_len = 0; unsigned snap_next = 0;
     bool last_rare_tiled = false;
     int* sort_count = nullptr; int* sort_cursor = nullptr; int* mode_first_dev = nullptr; long long* sort_totals = nullptr;
     bool use_tab = true;           // NK_STEP_TAB=0 disables the per-(mode, subvolume) table variant
@@ -185,6 +186,7 @@ void nk_destroy(nk_ctx* ctx) {
     if (ctx->cold_host) cudaFreeHost(ctx->cold_host);
     if (ctx->ev_cold) cudaEventDestroy(ctx->ev_cold);
     if (ctx->patch_count_dev) cudaFree(ctx->patch_count_dev);
+    for (int k = 0; k < 4; ++k) { if (ctx->snap_host[k]) cudaFreeHost(ctx->snap_host[k]); if (ctx->snap_ev[k]) cudaEventDestroy(ctx->snap_ev[k]); }
     delete ctx;
 }
 
@@ -912,14 +914,9 @@ int nk_flush_relaxation(nk_ctx* ctx) {
     return 0;
 }
 
-int nk_get_results(nk_ctx* ctx, double* T_sv, double* E_sv, int64_t* N_sv, double* flux, double* kappa_sv, double* kappa,
-                   double* res_E_bal, double* res_flux, int64_t* N_leaving, double* total_energy) {
-    cudaSetDevice(ctx->device);
-    const NkP& P = ctx->P;
+static void nk_unpack_results(const NkP& P, const double* h, double* T_sv, double* E_sv, int64_t* N_sv, double* flux, double* kappa_sv, double* kappa,
+                              double* res_E_bal, double* res_flux, int64_t* N_leaving, double* total_energy) {
     const int S = P.S, R = P.R;
-    std::vector<double> h(nk_out_len(S, R));
-    NK_CK(cudaStreamSynchronize(ctx->stream));
-    NK_CK(cudaMemcpy(h.data(), P.out, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
     if (T_sv) memcpy(T_sv, &h[NK_OUT_T(S, R)], S * 8);
     if (E_sv) memcpy(E_sv, &h[NK_OUT_E(S, R)], S * 8);
     if (N_sv) for (int s = 0; s < S; ++s) N_sv[s] = (int64_t)h[NK_OUT_N(S, R) + s];
@@ -930,6 +927,47 @@ int nk_get_results(nk_ctx* ctx, double* T_sv, double* E_sv, int64_t* N_sv, doubl
     if (res_flux) memcpy(res_flux, &h[NK_OUT_RFLUX(S, R)], 3 * R * 8);
     if (N_leaving) for (int r = 0; r < R; ++r) N_leaving[r] = (int64_t)h[NK_OUT_NLEAVE(S, R) + r];
     if (total_energy) *total_energy = h[NK_OUT_ETOT(S, R)];
+}
+
+int nk_get_results(nk_ctx* ctx, double* T_sv, double* E_sv, int64_t* N_sv, double* flux, double* kappa_sv, double* kappa,
+                   double* res_E_bal, double* res_flux, int64_t* N_leaving, double* total_energy) {
+    cudaSetDevice(ctx->device);
+    const NkP& P = ctx->P;
+    std::vector<double> h(nk_out_len(P.S, P.R));
+    NK_CK(cudaStreamSynchronize(ctx->stream));
+    NK_CK(cudaMemcpy(h.data(), P.out, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    nk_unpack_results(P, h.data(), T_sv, E_sv, N_sv, flux, kappa_sv, kappa, res_E_bal, res_flux, N_leaving, total_energy);
+    return 0;
+}
+
+// Asynchronous variant for callers that keep the device busy: nk_snapshot_results enqueues a copy of the results block (as it
+// is after the steps enqueued so far) into one of four pinned host buffers and returns its ticket; more steps may be enqueued
+// right away.  nk_get_snapshot waits for that copy only and unpacks it like nk_get_results.
+int nk_snapshot_results(nk_ctx* ctx, int* ticket) {
+    cudaSetDevice(ctx->device);
+    const NkP& P = ctx->P;
+    if (!P.out) { ctx->err = "results block not allocated yet"; return -1; }
+    const int len = nk_out_len(P.S, P.R);
+    if (ctx->snap_len != len) {
+        for (int k = 0; k < 4; ++k) {
+            if (ctx->snap_host[k]) cudaFreeHost(ctx->snap_host[k]);
+            NK_CK(cudaMallocHost(&ctx->snap_host[k], (size_t)len * sizeof(double)));
+            if (!ctx->snap_ev[k]) NK_CK(cudaEventCreateWithFlags(&ctx->snap_ev[k], cudaEventDisableTiming));
+        }
+        ctx->snap_len = len;
+    }
+    const int k = (int)(ctx->snap_next++ & 3u);
+    NK_CK(cudaMemcpyAsync(ctx->snap_host[k], P.out, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NK_CK(cudaEventRecord(ctx->snap_ev[k], ctx->stream));
+    *ticket = k;
+    return 0;
+}
+int nk_get_snapshot(nk_ctx* ctx, int ticket, double* T_sv, double* E_sv, int64_t* N_sv, double* flux, double* kappa_sv, double* kappa,
+                    double* res_E_bal, double* res_flux, int64_t* N_leaving, double* total_energy) {
+    cudaSetDevice(ctx->device);
+    if (ticket < 0 || ticket > 3 || !ctx->snap_host[ticket]) { ctx->err = "no such results snapshot"; return -1; }
+    NK_CK(cudaEventSynchronize(ctx->snap_ev[ticket]));
+    nk_unpack_results(ctx->P, ctx->snap_host[ticket], T_sv, E_sv, N_sv, flux, kappa_sv, kappa, res_E_bal, res_flux, N_leaving, total_energy);
     return 0;
 }
 

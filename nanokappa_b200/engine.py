@@ -322,13 +322,24 @@ class Engine:
         else:
             self.set_run_state(results_block=z["results_block"])
 
-    def results(self):
+    def snapshot_results(self):
+        """Enqueue a copy of the results block as it will be after the steps enqueued so far; returns a ticket for
+        ``results(ticket)``.  The device is not stalled: more steps can be enqueued before the numbers are looked at."""
+        t = C.c_int()
+        check(self.ctx, self.L.nk_snapshot_results(self.ctx, C.byref(t)), "nk_snapshot_results")
+        return t.value
+
+    def results(self, ticket=None):
         S, R = self.S, self.R
         T = np.zeros(S); E = np.zeros(S); N = np.zeros(S, dtype=np.int64); flux = np.zeros((S, 3)); ksv = np.zeros(S)
         kappa = np.zeros(1); reb = np.zeros(max(R, 1)); rfl = np.zeros((max(R, 1), 3)); nl = np.zeros(max(R, 1), dtype=np.int64)
         etot = np.zeros(1)
-        check(self.ctx, self.L.nk_get_results(self.ctx, _p(T), _p(E), _p(N), _p(flux), _p(ksv), _p(kappa), _p(reb), _p(rfl),
-                                              _p(nl), _p(etot)), "nk_get_results")
+        if ticket is None:
+            check(self.ctx, self.L.nk_get_results(self.ctx, _p(T), _p(E), _p(N), _p(flux), _p(ksv), _p(kappa), _p(reb), _p(rfl),
+                                                  _p(nl), _p(etot)), "nk_get_results")
+        else:
+            check(self.ctx, self.L.nk_get_snapshot(self.ctx, int(ticket), _p(T), _p(E), _p(N), _p(flux), _p(ksv), _p(kappa), _p(reb),
+                                                   _p(rfl), _p(nl), _p(etot)), "nk_get_snapshot")
         return dict(subvol_temperature=T, subvol_energy=E, subvol_N_p=N, subvol_heat_flux=flux, subvol_kappa=ksv,
                     kappa=float(kappa[0]), res_energy_balance=reb[:R], res_heat_flux=rfl[:R], N_leaving=nl[:R],
                     total_energy=float(etot[0]), N_p=int(N.sum()))

@@ -283,3 +283,43 @@ def test_maintenance_resort_does_not_change_the_physics(tmp_path, monkeypatch):
     assert np.array_equal(ra["subvol_heat_flux"], rb["subvol_heat_flux"])
     for k in ("ids", "modes", "positions", "occupation", "n_timesteps", "collision_facets"):
         assert np.array_equal(pa[k], pb[k], equal_nan=True), k
+
+
+def test_step_batching_and_seam_methods_equal_run_timestep(tmp_path):
+    """Three ways to advance a Population by the same 137 steps must leave identical particles and convergence rows:
+    run_timestep one launch sequence per call (library default), run_timestep with the command line's batching (the steps
+    between two convergence rows enqueued as one nk_step call, rows read back from asynchronous snapshots, the device up to a
+    batch ahead), and the reference's own call sequence drift / fill_reservoirs / add_reservoir_particles / boundary_scattering
+    / refresh_temperatures / lifetime_scattering (SURVEY 8b seams)."""
+    text = gen_golden.PARAMS_C1.format(eta=2, n=20000).replace("--iterations 1000", "--iterations 137")
+    rows, parts = {}, {}
+    for label in ("plain", "batched", "seams"):
+        folder = tmp_path / label
+        args, geo, ph, pop = _population(text, folder, seed=5)
+        pop.step_batching = label == "batched"
+        with contextlib.redirect_stdout(io.StringIO()):
+            if label == "seams":
+                for _ in range(137):
+                    pop.drift()
+                    pop.fill_reservoirs(geo, ph)
+                    pop.add_reservoir_particles(geo, ph)
+                    pop.boundary_scattering(geo, ph)
+                    pop.refresh_temperatures(geo, ph)
+                    pop.lifetime_scattering(ph)
+                E = pop.calculate_energy(geo, ph)
+                assert E.shape == (10,) and np.isfinite(E).all() and pop.calculate_heat_flux(geo, ph).shape == (10, 3)
+            else:
+                while pop.current_timestep < 137:
+                    pop.run_timestep(geo, ph)
+            pop.write_final_state(geo)
+        assert pop.current_timestep == 137
+        parts[label] = pop.engine.particles()
+        if label != "seams":
+            with open(os.path.join(folder, "convergence.txt")) as fh:
+                rows[label] = [ln.split()[1:] for ln in fh if not ln.startswith("#")]      # drop the wall-clock column
+    assert len(rows["plain"]) == 14 and rows["plain"] == rows["batched"]
+    for label in ("batched", "seams"):
+        for f in parts["plain"]:
+            assert np.array_equal(parts["plain"][f], parts[label][f], equal_nan=True), f"{label}: {f}"
+    with pytest.raises(Exception):
+        pop.boundary_scattering(geo, ph)          # outside a drift() ... lifetime_scattering() sequence

@@ -128,3 +128,87 @@ def test_rebalance_between_emulated_ranks_keeps_the_union(golden_dir):
         r = s.engine.results()
         assert np.array_equal(r["subvol_N_p"], rs["subvol_N_p"])
         assert np.allclose(r["subvol_temperature"], rs["subvol_temperature"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("name", ["c2_crossplane", "c8_one_to_one"])
+def test_checkpoint_of_two_shards_continues_exactly(name, golden_dir):
+    """a sharded run that is checkpointed in the middle of a convergence window (step 7 of 10) and restored into
+    fresh contexts WITHOUT rebuilding the tables (Engine.checkpoint / Engine.restore: particles, reservoir counters and
+    deal counters, window accumulators, N_leaving, results block) must continue exactly like the uninterrupted run --
+    including the reservoir balances of the convergence row at step 10 and, for one_to_one, the re-emission that depends on
+    the previous step's absorbed counts."""
+    tb, st, _ = gen_golden.load_fixture(os.path.join(golden_dir, name + ".npz"))
+    n = st.positions.shape[0]
+
+    def make():
+        sh = [_engine(tb, st, slice(0, n // 2), 0, 2), _engine(tb, st, slice(n // 2, n), 1, 2)]
+        return sh, [_acc(e) for e in sh]
+
+    def run(shards, accs, k):
+        for _ in range(k):
+            for e in shards:
+                e.step_local()
+            torch.cuda.synchronize()
+            total = accs[0] + accs[1]
+            for a in accs:
+                a.copy_(total)
+            for e in shards:
+                e.step_finalize()
+
+    ref, ref_acc = make()
+    run(ref, ref_acc, 15)
+    a, a_acc = make()
+    run(a, a_acc, 7)
+    saved = [e.checkpoint() for e in a]
+    assert all(int(z["current_timestep"]) == 7 for z in saved)
+    b, b_acc = make()                       # fresh contexts: tables set, rank set, nothing else
+    for e, z in zip(b, saved):
+        e.restore(z)
+    run(b, b_acc, 8)
+    for e_ref, e in zip(ref, b):
+        p0, p1 = e_ref.particles(), e.particles()
+        for f in p0:
+            assert np.array_equal(p0[f], p1[f], equal_nan=True), f"{f} differs after the restart"
+        r0, r1 = e_ref.results(), e.results()
+        for f in ("subvol_temperature", "subvol_energy", "subvol_N_p", "subvol_heat_flux", "res_energy_balance", "res_heat_flux", "N_leaving"):
+            assert np.array_equal(r0[f], r1[f]), f"{f} differs after the restart"
+        s0, s1 = e_ref.run_state(), e.run_state()
+        for f in s0:
+            assert np.array_equal(s0[f], s1[f], equal_nan=True), f"run state {f} differs after the restart"      # kappa_sv is 0/0 in flat slices
+
+
+def test_host_buffer_calls_recycle_holes_at_two_percent_headroom(golden_dir):
+    """step-by-step integration through nk_advance_host with only 2 % spare capacity.  Absorbed particles leave
+    holes (mode = -1) in the caller's arrays; the census of every call puts them on the free-slot ring, so emitted particles
+    reuse them and the slot range stays bounded over 200 calls (it used to grow by every emission until NK_ERR_CAPACITY)."""
+    from nanokappa_b200.engine import Engine
+    from nanokappa_b200._lib import check
+    tb, st, _ = gen_golden.load_fixture(os.path.join(golden_dir, "c2_crossplane.npz"))
+    n0 = st.positions.shape[0]
+    J = tb["omega"].shape[1]
+    eng = Engine(0, seed=SEED)
+    eng.set_tables(tb, res_counter=st.res_counter)
+    eng.allocate(int(n0 * 1.02))
+    eng.load_particles(st.positions, st.modes[:, 0] * J + st.modes[:, 1], st.occupation, ids=st.ids, omodes=st.omega_modes,
+                       n_timesteps=st.n_timesteps, collision_facets=st.collision_facets, collision_positions=st.collision_positions)
+    eng.set_sv_temperature(st.subvol_temperature)
+    eng.set_timestep(0)
+    names = ("px", "py", "pz", "tc", "occ", "mode", "omode", "cfacet", "cx", "cy", "cz", "pid")
+    host = {k: eng.t[k].cpu().clone().pin_memory() for k in names}
+    S = eng.S
+    Tsv = np.zeros(S); Esv = np.zeros(S); Nsv = np.zeros(S, dtype=np.int64)
+    hp = lambda k: C.c_void_p(host[k].data_ptr())
+    n, peak = n0, n0
+    for call in range(200):
+        n_out = C.c_int64()
+        check(eng.ctx, eng.L.nk_advance_host(eng.ctx, n, 1, *[hp(k) for k in names], C.byref(n_out), Tsv.ctypes.data_as(C.c_void_p),
+                                             Esv.ctypes.data_as(C.c_void_p), Nsv.ctypes.data_as(C.c_void_p)), "nk_advance_host")
+        n = n_out.value
+        peak = max(peak, n)
+        live = int((host["mode"][:n] >= 0).sum())
+        assert live == int(Nsv.sum())
+    ids = host["pid"][:n][host["mode"][:n] >= 0].numpy()
+    emitted_alive = int((ids >= 2 ** 62).sum())                 # reservoir particles carry ids above 2^62
+    assert emitted_alive > 0.05 * n0, "the run did not emit enough particles to exercise the recycling"
+    assert peak <= eng.cap and peak <= int(n0 * 1.02) + 512, f"slot range grew to {peak} of capacity {eng.cap}"
+    assert np.unique(ids).shape[0] == ids.shape[0]
