@@ -159,6 +159,9 @@ int nk_get_timestep(nk_ctx* ctx, int64_t* current_timestep);
 /* Mesh.find_boundary(x, v) -> (xc, tc, fc)   Mesh.py:806-856.  fc int32, -1 = no hit (tc = inf). */
 int nk_find_boundary(nk_ctx* ctx, int64_t n, const double* x, const double* v,
                      double* xc, double* tc, int32_t* fc);
+/* Mesh.contains_naive(x)   Mesh.py:785-804 (point-in-solid by crossing parity; set-up at scale: rejection sampling of initial
+ * positions, Population.py:209-246).  inside (n) uint8: 1 inside, 0 outside.  All faces count (no interface faces). */
+int nk_contains(nk_ctx* ctx, int64_t n, const double* x, uint8_t* inside);
 /* SubvolClassifier.predict(x) + Population.get_subvol_id counts  Geometry.py:1212, Population.py:671-683.
  * counts (n_subvols) int64 may be NULL. */
 int nk_classify(nk_ctx* ctx, int64_t n, const double* x, int32_t* sv, int64_t* counts);

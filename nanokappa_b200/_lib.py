@@ -51,6 +51,7 @@ SIGNATURES = {
     "nk_set_timestep": (C.c_int, [VP, C.c_int64]),
     "nk_get_timestep": (C.c_int, [VP, c_lp]),
     "nk_find_boundary": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP]),
+    "nk_contains": (C.c_int, [VP, C.c_int64, VP, VP]),
     "nk_classify": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "nk_occupation": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "nk_lifetime": (C.c_int, [VP, C.c_int64, VP, VP, VP]),

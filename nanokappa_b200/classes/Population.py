@@ -250,6 +250,8 @@ class Population(PopulationSetup):
         occupation = None
         if self._can_init_on_device(geometry, key):
             return self._initialise_on_device(geometry, phonon)
+        if self._can_init_on_device_general(geometry, key):
+            return self._initialise_on_device(geometry, phonon, general=True)
         if key.endswith('.npz'):
             # binary checkpoint written by write_final_state above NK_TEXT_DUMP_MAX particles (the text restart file of the
             # reference, particle_data.txt, is handled below): exact continuation, per rank in a sharded run
@@ -332,7 +334,64 @@ class Population(PopulationSetup):
     def rotation_free(geometry):
         return geometry.rotation is None or not np.any(np.asarray(geometry.rotation, dtype=float) != 0)
 
-    def _initialise_on_device(self, geometry, phonon):
+    def _can_init_on_device_general(self, geometry, key):
+        """Any mesh / any subvolume type: rejection sampling inside the mesh on the device (nk_contains + nk_classify)."""
+        thr = float(os.environ.get('NK_DEVICE_INIT_MIN', 2e5))
+        return key in ('random_subvol', 'random_domain') and self.N_p >= thr and self.T_distribution != 'custom'
+
+    def _sample_positions_on_device(self, geometry, N, g):
+        """Population.py:209-246 on the device: uniform candidates in the bounding box, kept when inside the mesh
+        (Mesh.contains_naive -> nk_contains); for random_subvol every subvolume takes ceil(N V_s / V_filled) of them
+        (SubvolClassifier.predict -> nk_classify) and the concatenation in subvolume order is cut to N, as upstream does.
+        Returns (positions (N,3), subvolume index (N,)) as device tensors."""
+        import torch
+        from ..engine import _dp
+        from .._lib import check
+        eng, dev, S = self.engine, self.engine.device, self.n_of_subvols
+        lo = torch.as_tensor(geometry.bounds[0], device=dev); ext = torch.as_tensor(np.ptp(geometry.bounds, axis=0), device=dev)
+        by_sv = self.args.part_dist[0] == 'random_subvol'
+        if by_sv:
+            vol = np.asarray(geometry.subvol_volume, dtype=float)
+            quota = np.ceil(N * vol / (vol.sum() - vol[self.empty_subvols].sum())).astype(np.int64)
+            quota[self.empty_subvols] = 0
+        else:
+            quota = np.array([N], dtype=np.int64)
+        need = torch.as_tensor(quota, device=dev)
+        fill = float(geometry.volume / np.prod(np.ptp(geometry.bounds, axis=0)))
+        kept_x, kept_sv = [], []
+        while int(need.sum().item()) > 0:
+            m = int(min(8e6, max(4096, 1.3 * int(need.sum().item()) / max(fill, 1e-3))))
+            x = (lo + torch.rand((m, 3), generator=g, dtype=torch.float64, device=dev) * ext).contiguous()
+            inside = torch.empty(m, dtype=torch.uint8, device=dev)
+            check(eng.ctx, eng.L.nk_contains(eng.ctx, m, _dp(x), _dp(inside)), 'nk_contains')
+            x = x[inside.bool()].contiguous()
+            k = int(x.shape[0])
+            if k == 0:
+                continue
+            if by_sv:
+                sv = torch.empty(k, dtype=torch.int32, device=dev)
+                check(eng.ctx, eng.L.nk_classify(eng.ctx, k, _dp(x), _dp(sv), None), 'nk_classify')
+                sv = sv.long()
+            else:
+                sv = torch.zeros(k, dtype=torch.int64, device=dev)
+            order = torch.argsort(sv, stable=True)
+            svs = sv[order]
+            first = torch.searchsorted(svs, torch.arange(need.numel(), device=dev))
+            rank_in_sv = torch.arange(k, device=dev) - first[svs]
+            keep = rank_in_sv < need[svs]
+            take = order[keep]
+            kept_x.append(x[take]); kept_sv.append(sv[take])
+            need = need - torch.bincount(sv[take], minlength=need.numel())
+        X = torch.cat(kept_x); SV = torch.cat(kept_sv)
+        order = torch.argsort(SV, stable=True)[:N]                    # np.vstack(x)[:N]: subvolume order, the tail is cut
+        X = X[order].contiguous()
+        if not by_sv:
+            sv = torch.empty(N, dtype=torch.int32, device=dev)
+            check(eng.ctx, eng.L.nk_classify(eng.ctx, N, _dp(X), _dp(sv), None), 'nk_classify')
+            return X, sv.long()
+        return X, SV[order]
+
+    def _initialise_on_device(self, geometry, phonon, general=False):
         """Box + slice subvolumes: the reference fills every slice with ceil(N V_s / V) uniform points and keeps
         the first N (Population.py:209-246); here each slice's quota is drawn directly inside the slice
         with the device generator (same distribution, no rejection), modes are tiled / drawn as in
@@ -342,16 +401,23 @@ class Population(PopulationSetup):
         dev = eng.device
         from ..parallel import shard_bounds
         lo_i, hi_i = shard_bounds(self.rank, self.world, int(self.N_p))
-        N, S, ax = hi_i - lo_i, self.n_of_subvols, self.slice_axis
+        N, S, ax = hi_i - lo_i, self.n_of_subvols, getattr(self, 'slice_axis', 0)
         g = torch.Generator(device=dev); g.manual_seed(self.seed + 7919 * self.rank)
         cap = int(N * float(os.environ.get('NK_CAPACITY_FACTOR', 1.25))) + 1024
         eng.allocate(cap)
         t = eng.t
         lo = geometry.bounds[0]; ext = np.ptp(geometry.bounds, axis=0)
         key = self.args.part_dist[0]
-        for k, name in enumerate(('px', 'py', 'pz')):
-            t[name][:N] = lo[k] + torch.rand(N, generator=g, dtype=torch.float64, device=dev) * ext[k]
-        if key == 'random_subvol':
+        if general:
+            # arbitrary mesh / subvolumes: the tables must be on the device before nk_contains / nk_classify can run (they are:
+            # set_tables ran in __init__); positions by rejection sampling
+            X, _ = self._sample_positions_on_device(geometry, N, g)
+            t['px'][:N] = X[:, 0]; t['py'][:N] = X[:, 1]; t['pz'][:N] = X[:, 2]
+            del X
+        else:
+            for k, name in enumerate(('px', 'py', 'pz')):
+                t[name][:N] = lo[k] + torch.rand(N, generator=g, dtype=torch.float64, device=dev) * ext[k]
+        if key == 'random_subvol' and not general:
             quota = int(np.ceil(N * geometry.subvol_volume[0] / geometry.subvol_volume.sum()))
             sl = torch.clamp(torch.arange(N, device=dev, dtype=torch.int64) // quota, max=S - 1).to(torch.float64)
             u = torch.rand(N, generator=g, dtype=torch.float64, device=dev)
@@ -375,7 +441,7 @@ class Population(PopulationSetup):
         pos = torch.stack((t['px'][:N], t['py'][:N], t['pz'][:N]), dim=1).contiguous()
         Tp = torch.empty(N, dtype=torch.float64, device=dev)
         check(eng.ctx, eng.L.nk_particle_temperature(eng.ctx, N, _dp(pos), _dp(Tp)), 'nk_particle_temperature')
-        if self.temp_interp_type != 'nearest':      # initial occupation uses the subvolume temperature, not the interpolated one
+        if self.temp_interp_type != 'nearest' or general:      # initial occupation uses the subvolume temperature, not the interpolated one
             sv = torch.empty(N, dtype=torch.int32, device=dev)
             check(eng.ctx, eng.L.nk_classify(eng.ctx, N, _dp(pos), _dp(sv), None), 'nk_classify')
             Tp = torch.as_tensor(self.subvol_temperature, device=dev)[sv.long()]

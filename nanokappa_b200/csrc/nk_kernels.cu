@@ -666,6 +666,14 @@ int nk_find_boundary(nk_ctx* ctx, int64_t n, const double* x, const double* v, d
     NK_CK(cudaGetLastError());
     return 0;
 }
+int nk_contains(nk_ctx* ctx, int64_t n, const double* x, uint8_t* inside) {
+    cudaSetDevice(ctx->device);
+    if (!ctx->P.faces) { ctx->err = "nk_set_mesh first"; return -1; }
+    if (n <= 0) return 0;
+    k_contains<<<nk_grid(n, NK_RAY_THREADS, ctx->n_sm * 4), NK_RAY_THREADS, NK_TILE_SMEM_BYTES, ctx->stream>>>(ctx->P, n, x, inside);
+    NK_CK(cudaGetLastError());
+    return 0;
+}
 int nk_classify(nk_ctx* ctx, int64_t n, const double* x, int32_t* sv, int64_t* counts) {
     cudaSetDevice(ctx->device);
     if (counts) NK_CK(cudaMemsetAsync(counts, 0, ctx->P.S * sizeof(int64_t), ctx->stream));

@@ -67,6 +67,80 @@ __global__ void __launch_bounds__(NK_RAY_THREADS, 4) k_init_collisions(NkP P) {
     }
 }
 
+// Mesh.contains_naive (Mesh.py:785-804) for set-up at scale (rejection sampling of initial positions inside an arbitrary mesh,
+// Population.py:209-246): crossing parity of a ray from the point through all triangles, streamed in tiles.  Two fixed,
+// unrelated directions vote and a third decides when they disagree (a ray that grazes an edge shared by two triangles is
+// counted twice or not at all), exactly as nanokappa_b200.classes.Mesh.contains does on the host.
+__device__ __forceinline__ void nk_parity_faces(const NkFace* faces, int F, double x, double y, double z, double dx, double dy, double dz,
+                                                unsigned int& crossings) {
+    for (int f = 0; f < F; ++f) {
+        const NkFace& T = faces[f];
+        const double den = T.nx * dx + T.ny * dy + T.nz * dz;
+        const double t = -(x * T.nx + y * T.ny + z * T.nz + T.k) / den;
+        if (!(t > NK_TOL) || isinf(t)) continue;
+        const double cx = x + t * dx - T.ox, cy = y + t * dy - T.oy, cz = z + t * dz - T.oz;
+        const double a = T.ia0 * cx + T.ia1 * cy + T.ia2 * cz;
+        const double b = T.ib0 * cx + T.ib1 * cy + T.ib2 * cz;
+        if (a >= 0.0 && b >= 0.0 && a + b <= 1.0) ++crossings;
+    }
+}
+__device__ __forceinline__ unsigned int nk_tiles_parity(NkTilePipe& tp, const NkP& P, bool need, double x, double y, double z,
+                                                        double dx, double dy, double dz) {
+    unsigned int c = 0;
+    if (tp.resident) {
+        if (need) nk_parity_faces(tp.buf, P.F, x, y, z, dx, dy, dz, c);
+        return c;
+    }
+    const int F = P.F, nt = (F + NK_TILE_FACES - 1) / NK_TILE_FACES;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        nk_tile_issue(tp, P, 0, 0);
+        if (nt > 1) nk_tile_issue(tp, P, 1, 1);
+    }
+    for (int t = 0; t < nt; ++t) {
+        const int b = t & 1;
+        nk_mbar_wait(&tp.bar[b], b ? tp.parity1 : tp.parity0);
+        if (b) tp.parity1 ^= 1u; else tp.parity0 ^= 1u;
+        if (need) nk_parity_faces(tp.buf + (size_t)b * NK_TILE_FACES, min(NK_TILE_FACES, F - t * NK_TILE_FACES), x, y, z, dx, dy, dz, c);
+        if (t + 2 < nt) {
+            __syncthreads();
+            if (threadIdx.x == 0) nk_tile_issue(tp, P, b, t + 2);
+        }
+    }
+    return c;
+}
+__global__ void __launch_bounds__(NK_RAY_THREADS, 4) k_contains(NkP P, long long n, const double* __restrict__ x, unsigned char* __restrict__ inside) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    NkTilePipe tp;
+    nk_tiles_init(tp, tile_smem, P);
+    // the three voting directions of Mesh.contains, normalised
+    const double d0x = 0.68273165190000003, d0y = 0.53411270430000004, d0z = 0.49851632270000002;
+    const double d1x = -0.37119428350000001, d1y = 0.82604375110000003, d1z = 0.42415598719999998;
+    const double d2x = 0.29031784669999999, d2y = -0.44782912349999999, d2z = 0.84567710930000001;
+    const double n0 = 1.0 / sqrt(d0x * d0x + d0y * d0y + d0z * d0z), n1 = 1.0 / sqrt(d1x * d1x + d1y * d1y + d1z * d1z),
+                 n2 = 1.0 / sqrt(d2x * d2x + d2y * d2y + d2z * d2z);
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + threadIdx.x;
+        bool live = i < n;
+        double px = 0, py = 0, pz = 0;
+        if (live) {
+            px = x[3 * i]; py = x[3 * i + 1]; pz = x[3 * i + 2];
+            live = px >= P.blo[0] - NK_TOL && py >= P.blo[1] - NK_TOL && pz >= P.blo[2] - NK_TOL &&
+                   px <= P.bhi[0] + NK_TOL && py <= P.bhi[1] + NK_TOL && pz <= P.bhi[2] + NK_TOL;
+            if (!live) inside[i] = 0;
+        }
+        const bool a = nk_tiles_parity(tp, P, live, px, py, pz, d0x * n0, d0y * n0, d0z * n0) & 1u;
+        const bool b = nk_tiles_parity(tp, P, live, px, py, pz, d1x * n1, d1y * n1, d1z * n1) & 1u;
+        const bool tie = live && (a != b);
+        bool res = a && b;
+        if (__syncthreads_or(tie ? 1 : 0)) {
+            const bool c = nk_tiles_parity(tp, P, tie, px, py, pz, d2x * n2, d2y * n2, d2z * n2) & 1u;
+            if (tie) res = c;
+        }
+        if (live) inside[i] = res ? 1 : 0;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_classify(NkP P, long long n, const double* __restrict__ x, int* __restrict__ sv,
                                                    unsigned long long* __restrict__ counts) {
     extern __shared__ double sm[];

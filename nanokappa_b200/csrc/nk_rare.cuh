@@ -63,17 +63,34 @@ __device__ __forceinline__ long long nk_pop_ring(const NkP& P, int ring, long lo
     // a claim beyond the snapshot is not returned: the next prologue clamps the head back
     return old < c[2] ? (long long)P.freelist[base + (old % size)] : -1;
 }
+__device__ __forceinline__ long long nk_pop_mode_ring(const NkP& P, int m) {
+    const long long base = P.mode_first[m], size = P.mode_first[m + 1] - base;
+    return size > 0 ? nk_pop_ring(P, 1 + m, base, size) : -1;
+}
 __device__ __forceinline__ long long nk_take_slot(const NkP& P, int mode) {
     if (P.fr_sorted > 0) {
-        const long long base = P.mode_first[mode], size = P.mode_first[mode + 1] - base;
-        if (size > 0) {
-            const long long s = nk_pop_ring(P, 1 + mode, base, size);
-            if (s >= 0) return s;
+        long long s = nk_pop_mode_ring(P, mode);
+        if (s >= 0) return s;
+        // the pool of this mode is dry (its population fluctuates by ~sqrt(count)): a spare slot of a neighbouring mode keeps
+        // the particle next to its own table rows ...
+        for (int d = 1; d <= 4; ++d) {
+            if (mode - d >= 0 && (s = nk_pop_mode_ring(P, mode - d)) >= 0) return s;
+            if (mode + d < P.M && (s = nk_pop_mode_ring(P, mode + d)) >= 0) return s;
         }
     }
     {
         const long long s = nk_pop_ring(P, 0, P.cap, P.cap);
         if (s >= 0) return s;
+    }
+    if (P.fr_sorted > 0) {
+        // ... and before the slot range grows, any free slot will do: the slots absorbed particles left behind sit in the
+        // rings of THEIR regions, and a population whose total is steady must not creep towards the capacity
+        unsigned int h = (unsigned int)clock64() * 2654435761u + (unsigned int)mode * 40503u + threadIdx.x;
+        for (int t = 0; t < 24; ++t) {
+            h = h * 1664525u + 1013904223u;
+            const long long s = nk_pop_mode_ring(P, (int)((h >> 4) % (unsigned int)P.M));
+            if (s >= 0) return s;
+        }
     }
     long long slot = (long long)nk_agg_inc((unsigned long long*)&P.dyn->n_slots);      // nothing recyclable: append
     if (slot >= P.cap) {

@@ -377,6 +377,14 @@ class Engine:
         self.synchronize()
         return xc.cpu().numpy(), tc.cpu().numpy(), fc.cpu().numpy().astype(int)
 
+    def contains(self, x):
+        """Mesh.contains_naive(x)  (Mesh.py:785-804) -> bool array."""
+        x = self._dev(np.asarray(x, dtype=float).reshape(-1, 3))
+        out = torch.empty(x.shape[0], dtype=torch.uint8, device=self.device)
+        check(self.ctx, self.L.nk_contains(self.ctx, x.shape[0], _dp(x), _dp(out)), "nk_contains")
+        self.synchronize()
+        return out.cpu().numpy().astype(bool)
+
     def classify(self, x, counts=False):
         """SubvolClassifier.predict(x)  (Geometry.py:1212)."""
         x = self._dev(np.asarray(x, dtype=float).reshape(-1, 3))

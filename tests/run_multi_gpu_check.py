@@ -2,7 +2,7 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/run_multi_gpu_check.py
 
-Every rank owns a block of the fixture's particles and a mode range of the reservoirs.  The same shards are
+Every rank owns a block of the fixture's particles and every world-th copy that a reservoir-table entry emits.  The same shards are
 stepped twice -- per-step NCCL all-reduce between nk_step_local / nk_step_finalize, and the fused in-kernel
 exchange over NVLink peer memory -- and both must agree with each other (integers identical, temperatures to
 1e-13) and, gathered on rank 0, with the single-context run of the whole population; the fused run, whose exchange adds

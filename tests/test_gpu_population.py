@@ -323,3 +323,59 @@ def test_step_batching_and_seam_methods_equal_run_timestep(tmp_path):
             assert np.array_equal(parts["plain"][f], parts[label][f], equal_nan=True), f"{label}: {f}"
     with pytest.raises(Exception):
         pop.boundary_scattering(geo, ph)          # outside a drift() ... lifetime_scattering() sequence
+
+
+def test_contains_operator_on_the_stl_mesh(golden_dir):
+    """nk_contains (Mesh.contains_naive, crossing parity over TMA-staged triangle tiles) on the 640-triangle STL cylinder of
+    fixture c9, against the analytic answer for a regular prism: inside the 160-gon and between the caps."""
+    from nanokappa_b200.engine import Engine
+    tb, st, _ = gen_golden.load_fixture(os.path.join(golden_dir, "c9_stl_voronoi.npz"))
+    eng = Engine(0, seed=1)
+    eng.set_tables(tb, res_counter=st.res_counter)
+    r = np.random.default_rng(4)
+    lo, hi = tb["bounds"]
+    x = lo - 0.05 * (hi - lo) + r.random((200000, 3)) * (hi - lo) * 1.1
+    got = eng.contains(x)
+    V = tb["face_vertices"].reshape(-1, 3)
+    ring = np.unique(np.round(V[np.abs(V[:, 2] - lo[2]) < 1e-6][:, :2], 6), axis=0)
+    c = ring.mean(axis=0)
+    ring = ring[np.argsort(np.arctan2(ring[:, 1] - c[1], ring[:, 0] - c[0]))]
+    ring = ring[np.linalg.norm(ring - c, axis=1) > 1.0]                 # drop the centre vertex of the cap fans
+    a, b = ring, np.roll(ring, -1, axis=0)
+    edge = b - a
+    nrm = np.stack((edge[:, 1], -edge[:, 0]), axis=1); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)     # outward (counter-clockwise ring)
+    d = ((x[:, None, :2] - a[None]) * nrm[None]).sum(axis=2).max(axis=1)                                       # > 0: outside the polygon
+    dz = np.maximum(lo[2] - x[:, 2], x[:, 2] - hi[2])
+    dist = np.maximum(d, dz)
+    want = dist < 0
+    clear = np.abs(dist) > 1e-6
+    assert ring.shape[0] == 160 and 0.3 < want.mean() < 0.8
+    assert np.array_equal(got[clear], want[clear]), f"{np.count_nonzero(got[clear] != want[clear])} points misclassified"
+
+
+def test_population_is_initialised_on_the_device_in_an_arbitrary_mesh(tmp_path, monkeypatch):
+    """above NK_DEVICE_INIT_MIN particles the initial positions of ANY geometry are drawn on the device (rejection
+    sampling with nk_contains, per-subvolume quotas with nk_classify, Population.py:209-246) -- here the faceted cylinder with
+    voronoi subvolumes and rough walls: everybody inside the mesh, quotas as upstream, modes tiled, a run that stays sane."""
+    monkeypatch.setenv("NK_DEVICE_INIT_MIN", "100000")
+    text = gen_golden.PARAMS_C4.format(eta=3, n=150000)
+    np.random.seed(12)
+    args, geo, ph, pop = _population(text, tmp_path, seed=8)
+    assert pop.N_p == 150000
+    eng = pop.engine
+    p = eng.particles(flush=False)
+    assert eng.contains(p["positions"]).all()
+    sv = eng.classify(p["positions"])
+    vol = np.asarray(geo.subvol_volume, dtype=float)
+    quota = np.ceil(150000 * vol / vol.sum()).astype(int)
+    counts = np.bincount(sv, minlength=vol.shape[0])
+    assert (counts[:-1] == quota[:-1]).all() and counts[-1] == 150000 - quota[:-1].sum()          # vstack(...)[:N] cuts the last one
+    n_act = int((~ph.inactive_modes_mask).sum())
+    flat = p["modes"][:, 0] * ph.omega.shape[1] + p["modes"][:, 1]
+    assert np.bincount(flat).max() - np.bincount(flat)[np.bincount(flat) > 0].min() <= 1 and np.unique(flat).shape[0] == min(n_act, 150000)
+    assert (p["n_timesteps"] > 0).all() and (p["collision_facets"] >= 0).all()
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(30):
+            pop.run_timestep(geo, ph)
+    assert abs(pop.N_p - 150000) < 0.05 * 150000 and np.isfinite(pop.subvol_temperature).all()
+    assert eng.contains(pop.positions).mean() > 0.999
