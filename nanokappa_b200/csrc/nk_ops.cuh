@@ -92,20 +92,13 @@ __device__ __forceinline__ unsigned int nk_tiles_parity(NkTilePipe& tp, const Nk
         return c;
     }
     const int F = P.F, nt = (F + NK_TILE_FACES - 1) / NK_TILE_FACES;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        nk_tile_issue(tp, P, 0, 0);
-        if (nt > 1) nk_tile_issue(tp, P, 1, 1);
-    }
+    nk_tiles_begin_sweep(tp, P, nt);
     for (int t = 0; t < nt; ++t) {
         const int b = t & 1;
         nk_mbar_wait(&tp.bar[b], b ? tp.parity1 : tp.parity0);
         if (b) tp.parity1 ^= 1u; else tp.parity0 ^= 1u;
         if (need) nk_parity_faces(tp.buf + (size_t)b * NK_TILE_FACES, min(NK_TILE_FACES, F - t * NK_TILE_FACES), x, y, z, dx, dy, dz, c);
-        if (t + 2 < nt) {
-            __syncthreads();
-            if (threadIdx.x == 0) nk_tile_issue(tp, P, b, t + 2);
-        }
+        if (t + 2 < nt) nk_tile_release(tp, P, b, t + 2);
     }
     return c;
 }

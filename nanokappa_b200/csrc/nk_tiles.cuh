@@ -41,6 +41,7 @@ struct NkTilePipe {
     NkFace* buf;                     // two stages of NK_TILE_FACES faces (128-byte aligned shared memory)
     unsigned long long* bar;         // one mbarrier per stage
     unsigned int parity0, parity1;   // phase parities of the two stages (same value in every thread of the block)
+    unsigned int* done;              // per stage: warps that have finished the tile it holds (the last one refills it)
     bool resident;                   // the whole mesh fits stage 0 and has been loaded
 };
 
@@ -55,6 +56,7 @@ __device__ __forceinline__ void nk_tile_issue(const NkTilePipe& tp, const NkP& P
 __device__ __forceinline__ void nk_tiles_init(NkTilePipe& tp, unsigned char* smem, const NkP& P) {
     tp.buf = reinterpret_cast<NkFace*>(smem);
     tp.bar = reinterpret_cast<unsigned long long*>(smem + 2 * NK_TILE_STAGE_BYTES);
+    tp.done = reinterpret_cast<unsigned int*>(smem + 2 * NK_TILE_STAGE_BYTES + 16);
     tp.parity0 = tp.parity1 = 0u;
     tp.resident = false;
     if (threadIdx.x == 0) {
@@ -74,6 +76,31 @@ __device__ __forceinline__ void nk_tiles_init(NkTilePipe& tp, unsigned char* sme
     }
 }
 
+// Steady state of a sweep without block-wide barriers: a warp that has finished the tile in stage b bumps done[b]; the LAST
+// warp to do so refills the stage with tile t + 2 (nobody reads it any more) and everybody else moves on to the other stage, so
+// fast warps run up to one tile ahead of slow ones instead of waiting for them at a __syncthreads per tile.  A warp can only
+// wait for fill k + 1 of a stage after every warp has consumed fill k (the refill is issued by the last consumer), so the
+// parity of the mbarrier never aliases.
+__device__ __forceinline__ void nk_tile_release(const NkTilePipe& tp, const NkP& P, int stage, int next_tile) {
+    __syncwarp();
+    if ((threadIdx.x & 31u) == 0) {
+        const unsigned int nwarps = blockDim.x >> 5;
+        if (atomicAdd(&tp.done[stage], 1u) == nwarps - 1u) {
+            atomicExch(&tp.done[stage], 0u);
+            nk_tile_issue(tp, P, stage, next_tile);
+        }
+    }
+}
+__device__ __forceinline__ void nk_tiles_begin_sweep(const NkTilePipe& tp, const NkP& P, int nt) {
+    __syncthreads();                                 // the readers of the previous sweep are done with both stages
+    if (threadIdx.x == 0) {
+        tp.done[0] = 0u; tp.done[1] = 0u;
+        nk_tile_issue(tp, P, 0, 0);
+        if (nt > 1) nk_tile_issue(tp, P, 1, 1);
+    }
+    __syncthreads();                                 // counters reset before anybody releases a stage
+}
+
 // All threads of the block call this together; threads with need == false only help to keep the pipeline moving.
 __device__ __forceinline__ void nk_tiles_sweep(NkTilePipe& tp, const NkP& P, bool need, double x, double y, double z,
                                                double vx, double vy, double vz, double& tbest, int& fbest) {
@@ -85,19 +112,12 @@ __device__ __forceinline__ void nk_tiles_sweep(NkTilePipe& tp, const NkP& P, boo
         return;
     }
     const int F = P.F, nt = (F + NK_TILE_FACES - 1) / NK_TILE_FACES;
-    __syncthreads();                                 // the readers of the previous sweep are done with both stages
-    if (threadIdx.x == 0) {
-        nk_tile_issue(tp, P, 0, 0);
-        if (nt > 1) nk_tile_issue(tp, P, 1, 1);
-    }
+    nk_tiles_begin_sweep(tp, P, nt);
     for (int t = 0; t < nt; ++t) {
         const int b = t & 1;
         nk_mbar_wait(&tp.bar[b], b ? tp.parity1 : tp.parity0);
         if (b) tp.parity1 ^= 1u; else tp.parity0 ^= 1u;
         if (need) nk_ray_faces(tp.buf + (size_t)b * NK_TILE_FACES, min(NK_TILE_FACES, F - t * NK_TILE_FACES), P.mesh_scale, x, y, z, vx, vy, vz, tbest, fbest);
-        if (t + 2 < nt) {
-            __syncthreads();                         // everybody has left stage b: refill it
-            if (threadIdx.x == 0) nk_tile_issue(tp, P, b, t + 2);
-        }
+        if (t + 2 < nt) nk_tile_release(tp, P, b, t + 2);
     }
 }
