@@ -26,6 +26,46 @@ __device__ __forceinline__ double nk_rcp(double x) {
     return r;
 }
 
+// Branch-free exp for the occupation arithmetic: argument clamped to [-708, 709] (results there are
+// ~1e-308 / ~1e308, i.e. 0 / inf for every use below), Cody-Waite reduction, degree-13 Taylor polynomial on
+// |r| <= ln2/2 (truncation 4e-18), exponent added with integer arithmetic.  Coefficients live in constant
+// memory so that they are DFMA operands instead of 64-bit immediates.
+__constant__ double NK_EXP_C[12] = {
+    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+    1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+__device__ __forceinline__ double nk_exp(double x) {
+    x = fmin(fmax(x, -708.0), 709.0);
+    const double magic = 6755399441055744.0;                      // 2^52 + 2^51: rounds to nearest integer
+    const double t = fma(x, 1.4426950408889634, magic);
+    const int k = __double2loint(t);
+    const double kf = t - magic;
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double p = NK_EXP_C[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) p = fma(p, r, NK_EXP_C[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// Bose-Einstein with the hoisted 1/(k_B T): a = hbar*omega.  exp(x)-1 == 0 only for x == 0 -> inf like 1/0.
+__device__ __forceinline__ double nk_bose_fast(double a, double omega, double invb) {
+    const double d = nk_exp(a * invb) - 1.0;
+    const double v = d > 0.0 ? nk_rcp(d) : CUDART_INF;
+    return (invb > 0.0 && omega > 0.0) ? v : 0.0;
+}
+__device__ __forceinline__ double nk_decay(double dt, double tau) {       // exp(-dt/tau), tau > 0
+    return nk_exp(-dt * nk_rcp(tau));
+}
+
+// Phonon.calculate_occupation for the rare path (absorbed / emitted / diffusely scattered particles and their energy
+// terms): the same lean arithmetic as the streaming kernel (<= 2 ulp; never feeds an integer result) instead of libm's exp
+// and two IEEE divisions, which sat on every item's dependency chain
+__device__ __forceinline__ double nk_bose_lean(double hbar, double kb, double T, double omega) {
+    return nk_bose_fast(hbar * omega, omega, T > 0.0 ? nk_rcp(T * kb) : 0.0);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 keyed by (particle id, step, stream); see oracle/philox.py for the contract
 // ------------------------------------------------------------------------------------------------
@@ -456,7 +496,7 @@ __device__ __forceinline__ bool nk_event_advance(const NkP& P, const NkGeo& G, N
             // I. absorbed by a reservoir (:1565-1608)
             int r = G.res[cfi];
             if (r >= 0) {
-                double e = nk_mul(nk_mul(P.hbar, p.omega), nk_sub(p.occ, nk_bose(P, P.res_T[r], p.omega)));
+                double e = nk_mul(nk_mul(P.hbar, p.omega), nk_sub(p.occ, nk_bose_lean(P.hbar, P.kb, P.res_T[r], p.omega)));
                 const double* n = G.normal + 3 * cfi;
                 double vn = dot3(p.vx, p.vy, p.vz, n[0], n[1], n[2]);
                 NK_RACC_N(P, acc, NK_ACC_NLEAVE(P.S, P.R) + r);
@@ -511,7 +551,7 @@ __device__ __forceinline__ bool nk_event_advance(const NkP& P, const NkGeo& G, N
                 p.omode = p.mode;
                 p.omega = P.mprop[p.mode].omega;
                 double Tc = nk_particle_T(P, P.svc, P.sv_axis, P.sv_mid, P.T_sv, p.cx, p.cy, p.cz, -1);
-                p.occ = nk_bose(P, Tc, p.omega);
+                p.occ = nk_bose_lean(P.hbar, P.kb, Tc, p.omega);
                 p.occ_changed = true;
             }
             NkMode m = P.mprop[p.mode];

@@ -21,7 +21,7 @@ __device__ __forceinline__ void nk_store_after_events(const NkP& P, long long i,
 // (shared memory) copy of the accumulator vector
 __device__ __forceinline__ void nk_accumulate(const NkP& P, double* acc, const NkParticle& p, bool with_flux) {
     int sv = nk_classify(P, P.svc, P.sv_mid, p.x, p.y, p.z);
-    double e = nk_mul(nk_mul(P.hbar, p.omega), nk_sub(p.occ, nk_bose(P, P.T_sv[sv], p.omega)));
+    double e = nk_mul(nk_mul(P.hbar, p.omega), nk_sub(p.occ, nk_bose_lean(P.hbar, P.kb, P.T_sv[sv], p.omega)));
     NK_RACC_E(P, acc, NK_ACC_E(P.S, P.R) + sv, e);
     NK_RACC_N(P, acc, NK_ACC_CNT(P.S, P.R) + sv);
     if (with_flux) {
@@ -132,7 +132,7 @@ __device__ __forceinline__ bool nk_emit_post(const NkP& P, double* acc, int r, d
     p.cx = nk_add(x0, nk_mul(t, p.vx)); p.cy = nk_add(y0, nk_mul(t, p.vy)); p.cz = nk_add(z0, nk_mul(t, p.vz));
     p.tc = nk_sub(nk_div(t, dt), nk_div(dt_in, dt));
     p.x = nk_add(x0, nk_mul(p.vx, dt_in)); p.y = nk_add(y0, nk_mul(p.vy, dt_in)); p.z = nk_add(z0, nk_mul(p.vz, dt_in));
-    p.occ = nk_bose(P, P.res_T[r], p.omega);
+    p.occ = nk_bose_lean(P.hbar, P.kb, P.res_T[r], p.omega);
     NK_RACC_N(P, acc, NK_ACC_NEMIT(P.S, P.R));
     return p.tc < 0.0;
 }

@@ -23,39 +23,6 @@
 #define NK_STEP_MIN_BLOCKS 4
 #endif
 
-// Branch-free exp for the occupation arithmetic: argument clamped to [-708, 709] (results there are
-// ~1e-308 / ~1e308, i.e. 0 / inf for every use below), Cody-Waite reduction, degree-13 Taylor polynomial on
-// |r| <= ln2/2 (truncation 4e-18), exponent added with integer arithmetic.  Coefficients live in constant
-// memory so that they are DFMA operands instead of 64-bit immediates.
-__constant__ double NK_EXP_C[12] = {
-    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
-    1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
-__device__ __forceinline__ double nk_exp(double x) {
-    x = fmin(fmax(x, -708.0), 709.0);
-    const double magic = 6755399441055744.0;                      // 2^52 + 2^51: rounds to nearest integer
-    const double t = fma(x, 1.4426950408889634, magic);
-    const int k = __double2loint(t);
-    const double kf = t - magic;
-    double r = fma(kf, -6.93147180369123816490e-01, x);
-    r = fma(kf, -1.90821492927058770002e-10, r);
-    double p = NK_EXP_C[0];
-#pragma unroll
-    for (int i = 1; i < 12; ++i) p = fma(p, r, NK_EXP_C[i]);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-}
-
-// Bose-Einstein with the hoisted 1/(k_B T): a = hbar*omega.  exp(x)-1 == 0 only for x == 0 -> inf like 1/0.
-__device__ __forceinline__ double nk_bose_fast(double a, double omega, double invb) {
-    const double d = nk_exp(a * invb) - 1.0;
-    const double v = d > 0.0 ? nk_rcp(d) : CUDART_INF;
-    return (invb > 0.0 && omega > 0.0) ? v : 0.0;
-}
-__device__ __forceinline__ double nk_decay(double dt, double tau) {       // exp(-dt/tau), tau > 0
-    return nk_exp(-dt * nk_rcp(tau));
-}
-
 // slice index of a coordinate = searchsorted(mid, xa, 'left') for uniformly spaced slices: arithmetic guess
 // verified against the padded boundary table midp[0..S] (midp[0] = -inf, midp[S] = +inf); the exact
 // bisection runs only when the guess is off (never for in-range coordinates, kept for safety).
