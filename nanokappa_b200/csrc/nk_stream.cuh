@@ -369,56 +369,83 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step(Nk
 // to tabulate {n0, exp(-dt/tau)} once per step (k_mode_tables, M x S entries, the arithmetic of nk_bose_fast /
 // nk_decay, so results are bit-identical to the direct variants) than to evaluate two exponentials and three
 // reciprocals per particle.  Particles are ordered by mode, so a warp gathers from a handful of table rows.
+__device__ __forceinline__ double2 nk_mode_table_entry(const NkP& P, const NkSvHot& h, int m, int sv) {
+    double4 ma, mt;
+    nk_ld256(&P.mhot[m].omega, ma);
+    nk_ld256(&P.mhot[m].t[0], mt);
+    const double a = nk_mul(P.hbar, ma.x);
+    const double be = nk_bose_fast(a, ma.x, h.invb[sv]);
+    const int r = h.tr[sv];
+    const double w = h.tw[sv];
+    double lo = r == 0 ? mt.x : (r == 1 ? mt.y : mt.z);
+    double hi = r == 0 ? mt.y : (r == 1 ? mt.z : mt.w);
+    if (r < 0) {
+        const int it = h.ti[sv];
+        lo = __ldg(P.tau + (size_t)it * P.M + m);
+        hi = __ldg(P.tau + (size_t)(it + 1) * P.M + m);
+    }
+    const double tau = nk_add(nk_mul(lo, nk_sub(1.0, w)), nk_mul(hi, w));
+    const double dec = tau > 0.0 ? nk_decay(P.dt, tau) : 0.0;       // tau <= 0: relax straight to n0
+    return make_double2(be, dec);
+}
 __global__ void __launch_bounds__(256) k_mode_tables(NkP P) {
     extern __shared__ double sm[];
     NkSvHot h = nk_load_hot(P, sm);
     __syncthreads();
     const int S = P.S;
     const long long total = (long long)P.M * S;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int m = (int)(i / S), sv = (int)(i % S);
-        double4 ma, mt;
-        nk_ld256(&P.mhot[m].omega, ma);
-        nk_ld256(&P.mhot[m].t[0], mt);
-        const double a = nk_mul(P.hbar, ma.x);
-        const double be = nk_bose_fast(a, ma.x, h.invb[sv]);
-        const int r = h.tr[sv];
-        const double w = h.tw[sv];
-        double lo = r == 0 ? mt.x : (r == 1 ? mt.y : mt.z);
-        double hi = r == 0 ? mt.y : (r == 1 ? mt.z : mt.w);
-        if (r < 0) {
-            const int it = h.ti[sv];
-            lo = __ldg(P.tau + (size_t)it * P.M + m);
-            hi = __ldg(P.tau + (size_t)(it + 1) * P.M + m);
-        }
-        const double tau = nk_add(nk_mul(lo, nk_sub(1.0, w)), nk_mul(hi, w));
-        const double dec = tau > 0.0 ? nk_decay(P.dt, tau) : 0.0;       // tau <= 0: relax straight to n0
-        P.hot_tab[i] = make_double2(be, dec);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // two entries per round: their exp / reciprocal chains are independent and overlap in the FP64 pipe
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < total; i += 2 * stride) {
+        const long long j = i + stride;
+        const double2 e0 = nk_mode_table_entry(P, h, (int)(i / S), (int)(i % S));
+        const double2 e1 = nk_mode_table_entry(P, h, (int)(j / S), (int)(j % S));
+        P.hot_tab[i] = e0; P.hot_tab[j] = e1;
     }
+    if (i < total) P.hot_tab[i] = nk_mode_table_entry(P, h, (int)(i / S), (int)(i % S));
 }
 
-template <bool HAS_ROUGH, bool RELAX, bool FLUX>
-__device__ __forceinline__ bool nk_step_particle_tab(const NkP& P, const NkSvSmem& s, const NkSvHot& h, long long* binE, long long* binF,
-                                                     double* binX, unsigned int* binC, int md, int om, double& x, double& y, double& z,
-                                                     double& tc, double& occ) {
-    double4 ma;
-    nk_ld256(&P.mhot[md].omega, ma);        // omega, v_g
-    double omega = ma.x;
-    if (HAS_ROUGH && om != md) omega = P.mhot[om].omega;
-    const double a = nk_mul(P.hbar, omega);
-    const double dt = P.dt;
-    const int S = P.S;
-    const double2* __restrict__ row = P.hot_tab + (size_t)md * S;
-    const double2* __restrict__ orow = (HAS_ROUGH && om != md) ? P.hot_tab + (size_t)om * S : row;
-    double be0 = 0.0; int g0 = -1;
+// Two phases per particle so that the gathers of BOTH particles of a thread are in flight before either is consumed (the
+// stall samples of the one-phase version sat on the table-row gather: profiles/r2_film_kstep_tab_hotspots.txt).
+// Phase A: mode record + table row of the slice the particle is in; no side effects, safe for dead slots (mode clamped).
+struct NkTabPre {
+    double4 ma;            // omega, v_g
+    double2 t0;            // {n0, decay} of (mode, slice before the drift)
+    double be0;            // n0 of the omega-carrying mode in that slice
+    double omega;
+    int g0;
+};
+template <bool HAS_ROUGH, bool RELAX>
+__device__ __forceinline__ void nk_step_tab_gather(const NkP& P, const NkSvSmem& s, const NkSvHot& h, int md, int om, double x, double y, double z,
+                                                   NkTabPre& q) {
+    md = max(md, 0); om = max(om, 0);
+    nk_ld256(&P.mhot[md].omega, q.ma);
+    q.omega = q.ma.x;
+    if (HAS_ROUGH && om != md) q.omega = P.mhot[om].omega;
+    q.g0 = -1; q.t0 = make_double2(0.0, 0.0); q.be0 = 0.0;
     if (RELAX) {
         const double xa = P.axis == 0 ? x : (P.axis == 1 ? y : z);
         double lo_b, hi_b;
-        g0 = nk_slice_lookup(P, h.midp, s.sv_mid, xa, lo_b, hi_b);          // interp1d 'nearest'
-        const double2 t0 = __ldg(row + g0);
-        be0 = (HAS_ROUGH && om != md) ? __ldg(orow + g0).x : t0.x;
-        const double relaxed = be0 + (occ - be0) * t0.y;
-        occ = t0.y > 0.0 ? relaxed : be0;
+        q.g0 = nk_slice_lookup(P, h.midp, s.sv_mid, xa, lo_b, hi_b);          // interp1d 'nearest'
+        q.t0 = __ldg(P.hot_tab + (size_t)md * P.S + q.g0);
+        q.be0 = (HAS_ROUGH && om != md) ? __ldg(P.hot_tab + (size_t)om * P.S + q.g0).x : q.t0.x;
+    }
+}
+// Phase B: relaxation, drift, binning.  Returns true when the particle's collision falls inside this step.
+template <bool HAS_ROUGH, bool RELAX, bool FLUX>
+__device__ __forceinline__ bool nk_step_particle_tab(const NkP& P, const NkSvSmem& s, const NkSvHot& h, long long* binE, long long* binF,
+                                                     double* binX, unsigned int* binC, int md, int om, const NkTabPre& q, double& x, double& y, double& z,
+                                                     double& tc, double& occ) {
+    const double4 ma = q.ma;
+    const double a = nk_mul(P.hbar, q.omega);
+    const double dt = P.dt;
+    const int S = P.S;
+    const double2* __restrict__ orow = P.hot_tab + (size_t)((HAS_ROUGH && om != md) ? om : md) * S;
+    const double be0 = q.be0; const int g0 = q.g0;
+    if (RELAX) {
+        const double relaxed = be0 + (occ - be0) * q.t0.y;
+        occ = q.t0.y > 0.0 ? relaxed : be0;
     }
     x = nk_add(x, nk_mul(ma.y, dt)); y = nk_add(y, nk_mul(ma.z, dt)); z = nk_add(z, nk_mul(ma.w, dt));
     tc = nk_sub(tc, 1.0);
@@ -474,8 +501,11 @@ __global__ void __launch_bounds__(NK_STEP_THREADS, NK_STEP_MIN_BLOCKS) k_step_ta
             if (HAS_ROUGH) OM = *reinterpret_cast<const int2*>(P.omode + base);
         }
         bool h0 = false, h1 = false;
-        if (base < n && MD.x >= 0) h0 = nk_step_particle_tab<HAS_ROUGH, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.x, OM.x, X.x, Y.x, Z.x, TC.x, OC.x);
-        if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle_tab<HAS_ROUGH, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.y, OM.y, X.y, Y.y, Z.y, TC.y, OC.y);
+        NkTabPre q0, q1;
+        nk_step_tab_gather<HAS_ROUGH, RELAX>(P, s, h, MD.x, OM.x, X.x, Y.x, Z.x, q0);
+        nk_step_tab_gather<HAS_ROUGH, RELAX>(P, s, h, MD.y, OM.y, X.y, Y.y, Z.y, q1);
+        if (base < n && MD.x >= 0) h0 = nk_step_particle_tab<HAS_ROUGH, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.x, OM.x, q0, X.x, Y.x, Z.x, TC.x, OC.x);
+        if (base + 1 < n && MD.y >= 0) h1 = nk_step_particle_tab<HAS_ROUGH, RELAX, FLUX>(P, s, h, binE, binF, binX, binC, MD.y, OM.y, q1, X.y, Y.y, Z.y, TC.y, OC.y);
         nk_push_hits(P, lane, h0, h1, base, X, Y, Z, TC, OC, MD, OM);
         if (inb) {
             *reinterpret_cast<double2*>(P.px + base) = X;
