@@ -202,3 +202,42 @@ def test_stl_mesh_find_boundary_and_tiled_rare_path(golden_dir):
     assert len(np.unique(fc0)) > 100                      # the rays reach most of the 162 facets
     eng.step(2)
     assert eng.last_step_variant() & 8, "a 640-triangle mesh must go through k_rare_tiled"
+
+
+def test_many_subvolumes_need_the_opt_in_shared_memory():
+    """beyond ~230 subvolumes the block-private bins of k_step / k_rare exceed the 48 KB default of dynamic shared
+    memory; the launches opt in to the larger size (and nk_set_subvols rejects what cannot fit).  A box with an 8 x 8 x 6 grid
+    (384 subvolumes, nearest temperature, rough + periodic walls) against the oracle."""
+    import argument_parser as ap
+    import contextlib
+    import io
+    from nanokappa_b200.classes.Geometry import Geometry
+    from nanokappa_b200.classes.Phonon import Phonon
+    from nanokappa_b200.classes.Population import PopulationSetup
+    from nanokappa_b200._lib import NkError
+    text = """--mat_folder /nonexistent/ --hdf_file synthetic:5 --poscar_file POSCAR
+    --geometry box --dimensions 4e3 4e3 3e3 --scale 1 1 1 --geo_rotation 0 0 0 xyz --subvolumes grid 8 8 6
+    --bound_pos relative -0.1 0.5 0.5 1.1 0.5 0.5 0.5 0.5 -0.1 0.5 0.5 1.1 --bound_cond T T R R P --connect_pos relative 0.5 -0.1 0.5 0.5 1.1 0.5
+    --bound_values 303 297 2 2 --reference_temp local --temp_dist cold --temp_interp nearest --particles total 40000
+    --part_dist random_subvol --timestep 1 --iterations 100 --n_mean 10 --results_folder /tmp --conv_crit 0 10 --output screen
+    --max_sim_time 0-00:00:00"""
+    args = ap.initialise_parser(False).parse_args(text.split())
+    args.results_folder = "/tmp"
+    with contextlib.redirect_stdout(io.StringIO()):
+        geo = Geometry(args)
+        ph = Phonon(args, 0)
+        np.random.seed(0)
+        setup = PopulationSetup(args, geo, ph, seed=0)
+    tb = setup.tables(geo, ph)
+    S = tb["sv_centres"].shape[0]
+    assert S == 384
+    st = _population(tb, ph, 40000, np.full(S, 297.0), setup.res_counter)
+    eng = _engine(tb, st, 4)
+    _run_both(tb, st, eng, 4, 7, check_at={5, 10, 11})
+    # and the limit is reported, not a bare launch failure
+    from nanokappa_b200.engine import Engine
+    big = dict(tb)
+    big["sv_centres"] = np.random.default_rng(0).random((1500, 3)) * 1e3
+    big["sv_volume"] = np.ones(1500)
+    with pytest.raises(NkError, match="n_subvols"):
+        Engine(0, seed=1).set_tables(big)
