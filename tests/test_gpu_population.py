@@ -379,3 +379,33 @@ def test_population_is_initialised_on_the_device_in_an_arbitrary_mesh(tmp_path, 
             pop.run_timestep(geo, ph)
     assert abs(pop.N_p - 150000) < 0.05 * 150000 and np.isfinite(pop.subvol_temperature).all()
     assert eng.contains(pop.positions).mean() > 0.999
+
+
+def test_restart_from_the_binary_checkpoint_through_part_dist(tmp_path, monkeypatch):
+    """above NK_TEXT_DUMP_MAX particles the end-of-run dump is particle_data.npz, and `--part_dist <that file>` must
+    restart from it (the reference's restart workflow, Population.py:284-306, but exact: positions in f64, collision clocks,
+    reservoir counters, the open convergence window).  25 steps, dump, restart, 15 more == 40 uninterrupted steps."""
+    monkeypatch.setenv("NK_TEXT_DUMP_MAX", "1000")
+    text = gen_golden.PARAMS_C2.format(n=8000)
+    args, geo, ph, ref = _population(text, tmp_path / "ref", seed=6)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(40):
+            ref.run_timestep(geo, ph)
+    args, geo, ph, a = _population(text, tmp_path / "a", seed=6)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(25):
+            a.run_timestep(geo, ph)
+        a.write_final_state(geo)
+    ckpt = os.path.join(tmp_path / "a", "particle_data.npz")
+    assert os.path.isfile(ckpt)
+    args, geo, ph, b = _population(text.replace("--part_dist random_subvol", "--part_dist " + ckpt), tmp_path / "b", seed=6)
+    assert b.current_timestep == 25
+    with contextlib.redirect_stdout(io.StringIO()):
+        while b.current_timestep < 40:
+            b.run_timestep(geo, ph)
+    pr, pb = ref.engine.particles(), b.engine.particles()
+    for f in pr:
+        assert np.array_equal(pr[f], pb[f], equal_nan=True), f
+    rr, rb = ref.engine.results(), b.engine.results()
+    for f in ("subvol_temperature", "subvol_energy", "subvol_heat_flux", "res_energy_balance", "res_heat_flux"):
+        assert np.array_equal(rr[f], rb[f]), f
