@@ -337,6 +337,8 @@ int nk_set_phonon(nk_ctx* ctx, int Q, int J, int NT, const double* Tg, const dou
     P.nE = nE; P.hbar = hbar; P.kb = kb; P.V_uc = V_uc; P.n_active = (double)n_active;
     P.dens_norm = (double)Q * V_uc;
     P.Tg_inv_d = 1.0 / (Tg[1] - Tg[0]);
+    P.Tg0 = Tg[0]; P.Tg_d = Tg[1] - Tg[0]; P.Tg_uniform = P.Tg_d > 0.0 ? 1 : 0;
+    for (int i = 0; i < NT && P.Tg_uniform; ++i) if (Tg[i] != P.Tg0 + (double)i * P.Tg_d) P.Tg_uniform = 0;
     P.Ta_inv_d = (nE > 1 && Ta[nE - 1] != Ta[0]) ? (nE - 1) / (Ta[nE - 1] - Ta[0]) : 0.0;
     ctx->h_mode.resize(4 * (size_t)M);
     for (int m = 0; m < M; ++m) { ctx->h_mode[4 * (size_t)m] = mp[m].omega; ctx->h_mode[4 * (size_t)m + 1] = mp[m].vx; ctx->h_mode[4 * (size_t)m + 2] = mp[m].vy; ctx->h_mode[4 * (size_t)m + 3] = mp[m].vz; }

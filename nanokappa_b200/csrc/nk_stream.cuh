@@ -124,9 +124,21 @@ __device__ __forceinline__ double nk_relax_particle(const NkP& P, const NkSvSmem
         } else {
             Ti = nk_particle_T(P, s.svc, s.sv_axis, s.sv_mid, s.T_sv, x, y, z, -1);
         }
-        const int it = nk_T_index(P, Ti);
-        const double t0 = __ldg(P.Tg + it), t1 = __ldg(P.Tg + it + 1);
-        const double w = (Ti - t0) * nk_rcp(t1 - t0);
+        int it; double w;
+        if (KIND == NK_KIND_SLICE_LINEAR && P.Tg_uniform) {
+            // uniform temperature grid (every node is Tg0 + i d exactly): the bracket and the weight by arithmetic, one fix-up
+            // for a quotient that rounded across a node; same index as the search, weight within an ulp or two (it only feeds
+            // occupations)
+            it = max(0, min(__double2int_rd((Ti - P.Tg0) * P.Tg_inv_d), P.NT - 2));
+            double t0 = fma((double)it, P.Tg_d, P.Tg0);
+            if (Ti < t0 && it > 0) { --it; t0 -= P.Tg_d; }
+            else if (Ti >= t0 + P.Tg_d && it < P.NT - 2) { ++it; t0 += P.Tg_d; }
+            w = (Ti - t0) * P.Tg_inv_d;
+        } else {
+            it = nk_T_index(P, Ti);
+            const double t0 = __ldg(P.Tg + it), t1 = __ldg(P.Tg + it + 1);
+            w = (Ti - t0) * nk_rcp(t1 - t0);
+        }
         const int r = it - P.tau_i0;
         double lo = r == 0 ? mt.x : (r == 1 ? mt.y : mt.z);
         double hi = r == 0 ? mt.y : (r == 1 ? mt.z : mt.w);

@@ -114,6 +114,7 @@ struct NkP {
     double2* hot_tab;                 // (M, S) {n0(T_sv), exp(-dt/tau(T_sv))} rebuilt every step (slice + nearest T), or null
     int tau_i0;
     double Tg_inv_d;                  // 1 / (Tg[1]-Tg[0]) guess
+    int Tg_uniform; double Tg0, Tg_d; // Tg[i] == Tg0 + i * Tg_d exactly (phono3py's 0, 10, ... 1000 K): bracket by arithmetic
     int nE; const double* Ea; const double* Ta;
     double Ta_inv_d;                  // (nE-1)/(Ta[nE-1]-Ta[0]): index guess into the E(T) table
     double hbar, kb, V_uc, n_active, dens_norm;   // dens_norm = Q * V_uc
