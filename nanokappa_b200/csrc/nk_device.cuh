@@ -391,9 +391,15 @@ NK_DEVI void nk_ray_face_exact(const NkFace& T, double x, double y, double z, do
 }
 // Small meshes (a box is 12 triangles) staged per block: every thread walks all faces with the exact test; the pre-filter
 // below costs more than it saves there.
-NK_DEVI void nk_ray_faces_small(const NkFace* faces, int F, double x, double y, double z, double vx, double vy, double vz,
+NK_DEVI void nk_ray_faces(const NkFace* faces, int F, double mesh_scale, double x, double y, double z, double vx, double vy, double vz,
+                          double& tbest, int& fbest);
+NK_DEVI void nk_ray_faces_small(const NkFace* faces, int F, double mesh_scale, double x, double y, double z, double vx, double vy, double vz,
                                 double& tbest, int& fbest) {
+#ifdef NK_SMALL_FILTER
+    nk_ray_faces(faces, F, mesh_scale, x, y, z, vx, vy, vz, tbest, fbest);
+#else
     for (int f = 0; f < F; ++f) nk_ray_face_exact(faces[f], x, y, z, vx, vy, vz, tbest, fbest);
+#endif
 }
 
 struct NkRayPre {               // per-ray constants of the pre-filter
@@ -443,7 +449,7 @@ NK_DEVI void nk_find_boundary_1(const NkP& P, const NkFace* faces, double x, dou
                                 double vx, double vy, double vz,
                                 double& xc, double& yc, double& zc, double& tc, int& fc) {
     double tbest = CUDART_INF; int fbest = -1;
-    nk_ray_faces_small(faces, P.F, x, y, z, vx, vy, vz, tbest, fbest);
+    nk_ray_faces_small(faces, P.F, P.mesh_scale, x, y, z, vx, vy, vz, tbest, fbest);
     tc = tbest; fc = fbest;
     xc = nk_add(x, nk_mul(tbest, vx)); yc = nk_add(y, nk_mul(tbest, vy)); zc = nk_add(z, nk_mul(tbest, vz));   // inf*0 = NaN like NumPy
 }
@@ -581,7 +587,7 @@ __device__ __forceinline__ void nk_boundary_events(const NkP& P, const NkGeo& G,
     nk_event_begin(p, st);
     while (nk_event_advance(P, G, p, st, step, acc)) {
         double tbest = CUDART_INF; int fbest = -1;
-        nk_ray_faces_small(G.faces, P.F, p.x, p.y, p.z, p.vx, p.vy, p.vz, tbest, fbest);
+        nk_ray_faces_small(G.faces, P.F, P.mesh_scale, p.x, p.y, p.z, p.vx, p.vy, p.vz, tbest, fbest);
         nk_event_ray_done(P, p, st, tbest, fbest);
     }
 }

@@ -62,6 +62,7 @@ struct nk_ctx {
     int step_blocks_variant = -1;
     bool force_tiled = false;      // NK_RARE_TILED=1: use the tiled rare-path kernel also for small meshes (tests)
     bool rare_attr_set = false;
+    int rare_blocks_per_sm = 16;   // NK_RARE_BLOCKS_PER_SM: grid cap of the rare-path kernel (items beyond it are taken by the grid-stride loop)
     double* snap_host[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t snap_ev[4] = {nullptr, nullptr, nullptr, nullptr}; int snap_len = 0; unsigned snap_next = 0;
     bool last_rare_tiled = false;
     int* sort_count = nullptr; int* sort_cursor = nullptr; int* mode_first_dev = nullptr; long long* sort_totals = nullptr;
@@ -164,6 +165,7 @@ int nk_create(int device, nk_ctx** out) {
     if (const char* e = getenv("NK_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));   // experiment: 32 / 64 / 128
     if (const char* e = getenv("NK_STEP_TAB")) { ctx->use_tab = strcmp(e, "0") != 0; ctx->force_tab = !strcmp(e, "force"); }
     ctx->force_tiled = getenv_is_one("NK_RARE_TILED");
+    if (const char* e = getenv("NK_RARE_BLOCKS_PER_SM")) ctx->rare_blocks_per_sm = std::max(1, atoi(e));
     NkDyn z; memset(&z, 0, sizeof(z));
     ctx->P.dyn = nk_upload<NkDyn>(ctx, &z, 1);
     *out = ctx;
@@ -843,7 +845,7 @@ static int nk_step_kernels(nk_ctx* ctx, bool fuse_finalize, const NkChunkPlan* p
     // one item per thread; the number of items is known on the device only, so size the grid for ~5 % of the slots
     // (hits + emission are 0.2-2 % of the particles per step; more items are covered by the grid-stride loop)
     const long long want_blocks = (ctx->h_slots_hint / 20 + NK_RARE_THREADS - 1) / NK_RARE_THREADS;
-    const int rare_blocks = (int)std::min<long long>((long long)ctx->n_sm * 32, std::max<long long>(ctx->n_sm, want_blocks));
+    const int rare_blocks = (int)std::min<long long>((long long)ctx->n_sm * ctx->rare_blocks_per_sm, std::max<long long>(ctx->n_sm, want_blocks));
     const int tiled_blocks = (int)std::min<long long>((long long)ctx->n_sm * 16, std::max<long long>(ctx->n_sm, (ctx->h_slots_hint / 20 + NK_RARE_TILED_THREADS - 1) / NK_RARE_TILED_THREADS));
     if (tiled) {
         if (fuse_finalize) k_rare_tiled<true><<<tiled_blocks, NK_RARE_TILED_THREADS, rare_smem, ctx->stream>>>(P);

@@ -155,7 +155,7 @@ __device__ __forceinline__ void nk_emit_particle(const NkP& P, const NkGeo& G, d
     double x0, y0, z0;
     nk_emit_setup(P, r, m, id, uface, us, ur, p, x0, y0, z0);
     double t = CUDART_INF; int cf = -1;
-    nk_ray_faces_small(G.faces, P.F, x0, y0, z0, p.vx, p.vy, p.vz, t, cf);
+    nk_ray_faces_small(G.faces, P.F, P.mesh_scale, x0, y0, z0, p.vx, p.vy, p.vz, t, cf);
     if (nk_emit_post(P, acc, r, dt_in, x0, y0, z0, t, cf, p)) nk_boundary_events(P, G, p, step, acc);
     nk_emit_finish(P, acc, p, with_flux);
 }

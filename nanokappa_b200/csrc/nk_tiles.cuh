@@ -106,7 +106,7 @@ __device__ __forceinline__ void nk_tiles_sweep(NkTilePipe& tp, const NkP& P, boo
                                                double vx, double vy, double vz, double& tbest, int& fbest) {
     if (tp.resident) {
         if (need) {
-            if (P.F <= 32) nk_ray_faces_small(tp.buf, P.F, x, y, z, vx, vy, vz, tbest, fbest);
+            if (P.F <= 32) nk_ray_faces_small(tp.buf, P.F, P.mesh_scale, x, y, z, vx, vy, vz, tbest, fbest);
             else nk_ray_faces(tp.buf, P.F, P.mesh_scale, x, y, z, vx, vy, vz, tbest, fbest);
         }
         return;
