@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(NK_RARE_THREADS, NK_RARE_MIN_BLOCKS) k_rare(Nk
         __syncthreads();
         const unsigned int nh = P.dyn->n_hits, ne = P.dyn->n_emit;
         const long long step = P.dyn->step;
-        const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
+        const bool with_flux = ((unsigned int)(step + 1) % (unsigned int)P.n_dt_to_conv) == 0u;     // 32-bit: a 64-bit modulo per thread is ~100 instructions
         for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < nh + ne; w += gridDim.x * blockDim.x) {
             if (w < nh) {
                 nk_hit_entry(P, G, racc, w, step, with_flux);
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(NK_RARE_TILED_THREADS, 2) k_rare_tiled(NkP P) 
         __syncthreads();
         const unsigned int nh = P.dyn->n_hits, ne = P.dyn->n_emit;
         const long long step = P.dyn->step;
-        const bool with_flux = ((step + 1) % P.n_dt_to_conv) == 0;
+        const bool with_flux = ((unsigned int)(step + 1) % (unsigned int)P.n_dt_to_conv) == 0u;     // 32-bit: a 64-bit modulo per thread is ~100 instructions
         for (unsigned int w0 = blockIdx.x * blockDim.x; w0 < nh + ne; w0 += gridDim.x * blockDim.x) {     // block-uniform
             const unsigned int w = w0 + threadIdx.x;
             NkParticle p;

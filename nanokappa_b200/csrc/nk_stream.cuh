@@ -189,11 +189,11 @@ __device__ __forceinline__ void nk_emit_scan(const NkP& P) {
     // Every rank advances the WHOLE table (identical on all ranks) and keeps the entries of which it owns at least one copy:
     // copies are dealt round-robin per entry (nk_emit_owner), so each rank injects 1/world of every mode and its per-mode
     // particle numbers stay in balance with what it absorbs.
-    const long long total = (long long)P.R * P.M;
+    const unsigned int total = (unsigned int)P.R * (unsigned int)P.M;       // (R, Q*J) entries: far below 2^32; 32-bit index arithmetic
     const long long step = P.dyn->step;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(e / P.M);
-        const int m = (int)(e % P.M);
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int r = (int)(e / (unsigned int)P.M);
+        const int m = (int)(e % (unsigned int)P.M);
         const size_t idx = (size_t)e;
         const double prob = P.enter_prob[idx];
         const double fixed = floor(prob);
@@ -404,13 +404,15 @@ __global__ void __launch_bounds__(256) k_mode_tables(NkP P) {
     extern __shared__ double sm[];
     NkSvHot h = nk_load_hot(P, sm);
     __syncthreads();
-    const int S = P.S;
-    const long long total = (long long)P.M * S;
-    const long long stride = (long long)gridDim.x * blockDim.x;
+    // 32-bit index arithmetic: the table has at most NK_TAB_MAX_ENTRIES (6 Mi) entries, and a 64-bit division per entry cost
+    // more instructions than the two exponentials
+    const unsigned int S = (unsigned int)P.S;
+    const unsigned int total = (unsigned int)P.M * S;
+    const unsigned int stride = gridDim.x * blockDim.x;
     // two entries per round: their exp / reciprocal chains are independent and overlap in the FP64 pipe
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + stride < total; i += 2 * stride) {
-        const long long j = i + stride;
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < total && i + stride < total; i += 2 * stride) {
+        const unsigned int j = i + stride;
         const double2 e0 = nk_mode_table_entry(P, h, (int)(i / S), (int)(i % S));
         const double2 e1 = nk_mode_table_entry(P, h, (int)(j / S), (int)(j % S));
         P.hot_tab[i] = e0; P.hot_tab[j] = e1;
