@@ -477,6 +477,7 @@ def gpu_arm(a):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         e2e["seconds"] = float(e2e_t.item())
     e2e_value = e2e["updates_global"] / e2e["seconds"]
+    ceiling = pcie_ceiling(world, dev, e2e["h2d"] / max(n, 1), e2e["d2h"] / max(n, 1), barrier) if not a.no_ceiling else None
 
     if rank == 0:
         cpu_val, cpu_dt, cpu_upd = (None, None, None)
@@ -493,7 +494,10 @@ def gpu_arm(a):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(a, n, "gpu"),
             "clocks": clocks, "gpu_launches": int((2 + (1 if prof.get("k_finalize", 0.0) > 0 else 0)) * a.steps),
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                    "timesteps_per_call": 1, "calls": e2e["calls"], "api": e2e["api"], "numa_node_rank0": numa},
+                    "timesteps_per_call": 1, "calls": e2e["calls"], "api": e2e["api"], "numa_node_rank0": numa,
+                    "pcie_ceiling": ceiling,
+                    "frac_of_pcie_ceiling": (e2e_value / ceiling["equal_work_updates_per_s"]) if ceiling else None,
+                    "frac_of_ceiling_with_dependent_download": (e2e_value / ceiling["with_dependent_occupation_download_updates_per_s"]) if ceiling else None},
             "roofline": roofline, "cpu_baseline": cpu, "sustained": sustained,
             "particles_alive": int(n_alive1),
         }
@@ -554,6 +558,56 @@ def sustained_run(a, eng, world, rank, local, one_step, barrier, peak):
             "resort_every": every, "resorts": resorts, "resort_ms_each": sum(x.elapsed_time(y) for x, y in sort_ev) / max(resorts, 1),
             "ms_per_step_by_100": per100, "kstep_avg_ms": kstep_ms,
             "kstep_roofline_frac": BYTES_PER_UPDATE * alive_local / (kstep_ms * 1e-3) / 1e9 / peak, "clocks": clocks}
+
+
+def pcie_ceiling(world, dev, up_bytes, down_bytes, barrier, gb=1.0):
+    """What the host<->device link of THIS box gives the e2e number: every rank copies `gb` GB up and `gb` GB
+    down at the same time (two streams, pinned buffers, all ranks together, nothing else running), timed with CUDA events.  A
+    step moves `up_bytes` up and `down_bytes` down per particle, so a rank cannot exceed min(h2d / up_bytes, d2h / down_bytes)
+    updates/s.  `sum_updates_per_s` adds the ranks' limits; `equal_work_updates_per_s` = world x the slowest rank's limit is the
+    one that bounds bench.py's e2e (every rank holds the same number of particles and the time is the max over ranks) -- on the
+    8-GPU boxes of this pool the two halves of the node differ by 40 % (tests/run_pcie_ceiling.py, profiles/r2_pcie_ceiling_8gpu.json)."""
+    import torch
+    import torch.distributed as dist
+    nelem = int(gb * 1e9 / 8)
+    up_h = torch.empty(nelem, dtype=torch.float64, pin_memory=True).fill_(1.0)
+    dn_h = torch.empty(nelem, dtype=torch.float64, pin_memory=True)
+    up_d = torch.empty(nelem, dtype=torch.float64, device=dev)
+    dn_d = torch.ones(nelem, dtype=torch.float64, device=dev)
+    s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    rate = {}
+    for phase in ("both", "d2h_alone"):
+        for rep in range(2):                               # first repetition = warm-up
+            barrier()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            if phase == "both":
+                with torch.cuda.stream(s_up):
+                    e[0].record(); up_d.copy_(up_h, non_blocking=True); e[1].record()
+            with torch.cuda.stream(s_dn):
+                e[2].record(); dn_h.copy_(dn_d, non_blocking=True); e[3].record()
+            torch.cuda.synchronize()
+        if phase == "both":
+            rate["h2d"] = gb / (e[0].elapsed_time(e[1]) * 1e-3)
+            rate["d2h"] = gb / (e[2].elapsed_time(e[3]) * 1e-3)
+        else:
+            rate["d2h_alone"] = gb / (e[2].elapsed_time(e[3]) * 1e-3)
+    mine = torch.tensor([rate["h2d"], rate["d2h"], rate["d2h_alone"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+    else:
+        allv = [mine]
+    h2d = [float(v[0]) for v in allv]; d2h = [float(v[1]) for v in allv]; d2h_alone = [float(v[2]) for v in allv]
+    lim = [min(u * 1e9 / up_bytes, d * 1e9 / down_bytes) for u, d in zip(h2d, d2h)]
+    # the occupations (8 B per particle) are final only after the step's temperatures, which depend on every particle: their
+    # download cannot overlap the uploads, so a rank needs at least up_bytes / h2d + 8 / d2h_alone per particle
+    dep = [1e9 / (up_bytes / u + 8.0 / d) for u, d in zip(h2d, d2h_alone)]
+    del up_h, dn_h, up_d, dn_d
+    return {"h2d_gbs_per_rank": h2d, "d2h_gbs_per_rank": d2h, "d2h_alone_gbs_per_rank": d2h_alone, "gb_each_way": gb,
+            "bytes_up_per_particle": up_bytes, "bytes_down_per_particle": down_bytes,
+            "sum_updates_per_s": sum(lim), "equal_work_updates_per_s": world * min(lim),
+            "with_dependent_occupation_download_updates_per_s": world * min(dep),
+            "how": "concurrent pinned H2D + D2H copies on two streams (then D2H alone), all ranks at once, CUDA events, measured in this run"}
 
 
 def e2e_run(a, eng, n, world, rank, one_step, dev, fused=False):
@@ -623,6 +677,7 @@ def e2e_run(a, eng, n, world, rank, one_step, dev, fused=False):
 def main():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", 1)))
+    p.add_argument("--no-ceiling", dest="no_ceiling", action="store_true", help="skip the PCIe ceiling measurement next to e2e")
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])

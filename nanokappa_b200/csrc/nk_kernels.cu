@@ -519,13 +519,14 @@ int nk_set_slot_count(nk_ctx* ctx, int64_t n_slots) {
     // every free slot (mode < 0) of [0, n_slots) on the global ring, so holes in the caller's arrays are recycled
     NK_CK(cudaMemsetAsync(ctx->P.fr_ctr, 0, 3 * ((size_t)ctx->P.M + 1) * sizeof(long long), ctx->stream));
     ctx->P.n_rings = 1; ctx->P.fr_sorted = 0;
-    unsigned long long* dc; NK_CK(cudaMalloc(&dc, 8)); NK_CK(cudaMemsetAsync(dc, 0, 8, ctx->stream));
+    unsigned long long* dc = (unsigned long long*)ctx->sort_totals;       // persistent scratch: no allocation (and no implicit device sync) per call
+    NK_CK(cudaMemsetAsync(dc, 0, 8, ctx->stream));
     k_census<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->P, dc);
     k_census_publish<<<1, 1, 0, ctx->stream>>>(ctx->P);
+    NK_CK(cudaGetLastError());
     unsigned long long hc = 0;
     NK_CK(cudaStreamSynchronize(ctx->stream));
     NK_CK(cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost));
-    cudaFree(dc);
     if (nk_read_dyn(ctx, &d)) return -1;
     d.n_alive = (long long)hc;
     return nk_write_dyn(ctx, &d);
