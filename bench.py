@@ -607,7 +607,10 @@ def pcie_ceiling(world, dev, up_bytes, down_bytes, barrier, gb=1.0):
             "bytes_up_per_particle": up_bytes, "bytes_down_per_particle": down_bytes,
             "sum_updates_per_s": sum(lim), "equal_work_updates_per_s": world * min(lim),
             "with_dependent_occupation_download_updates_per_s": world * min(dep),
-            "how": "concurrent pinned H2D + D2H copies on two streams (then D2H alone), all ranks at once, CUDA events, measured in this run"}
+            "how": "concurrent pinned H2D + D2H copies on two streams (then D2H alone), all ranks at once, CUDA events, measured in this run",
+            "note": "the dependent-download figure uses the upload rate seen WITH a concurrent download; where the host memory system "
+                    "rather than the link limits the copies (several ranks on one box) the call's uploads run partly without one and "
+                    "the e2e value can exceed it -- it is a bound only at 1 rank"}
 
 
 def e2e_run(a, eng, n, world, rank, one_step, dev, fused=False):
