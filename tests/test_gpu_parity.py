@@ -202,6 +202,38 @@ def test_step_parity_fixed_draws(name, golden_dir):
     assert eng.timestep() == n_steps
 
 
+def test_step_parity_from_an_empty_population(golden_dir):
+    """Edge case: no particle at all at step 0 (and therefore empty subvolumes for many steps).  The reservoirs fill the film
+    from both ends; the reference's per-SV normalisation divides by N_s = 0 in the empty slices, so their temperatures are
+    NaN (Population.py:716-728) and stay NaN once the first particles arrive -- the CUDA path must reproduce the census, the
+    per-particle state and the NaN pattern, not crash on the empty hit / emission lists of step 1."""
+    tb, st, _ = _load("c2_crossplane", golden_dir)
+    for f in ("positions", "modes", "omega", "group_vel", "occupation", "n_timesteps", "collision_facets", "collision_positions",
+              "collision_cond", "temperatures", "ids", "omega_modes", "subvol_id", "energies"):
+        v = getattr(st, f)
+        if v is not None:
+            setattr(st, f, v[:0].copy())
+    from nanokappa_b200.engine import Engine
+    eng = Engine(0, seed=SEED)
+    eng.set_tables(tb, res_counter=st.res_counter)
+    eng.allocate(4096)
+    J = tb["omega"].shape[1]
+    eng.load_particles(st.positions, st.modes[:, 0] * J + st.modes[:, 1], st.occupation, ids=st.ids, omodes=st.omega_modes,
+                       n_timesteps=st.n_timesteps, collision_facets=st.collision_facets, collision_positions=st.collision_positions)
+    eng.set_sv_temperature(st.subvol_temperature)
+    eng.set_timestep(0)
+    assert eng.slot_count() == (0, 0)
+    rng = nko.KeyedRNG(SEED)
+    with np.errstate(all="ignore"):
+        for k in range(1, 16):
+            nko.run_timestep(tb, st, rng)
+            eng.step(1)
+            if k in (1, 2, 5, 10, 15):
+                res = _compare_step(k, eng, st, tb)
+                assert np.array_equal(np.isnan(res["subvol_temperature"]), np.isnan(st.subvol_temperature))
+    assert st.ids.shape[0] > 0 and np.isnan(st.subvol_temperature).any()
+
+
 def test_multi_step_call_equals_single_steps(golden_dir):
     """nk_step(n) in one call == n calls, and flushing the deferred relaxation in between is neutral."""
     tb, st, _ = _load("c1_mixed", golden_dir)
@@ -361,6 +393,8 @@ def test_error_conventions_of_the_c_abi(golden_dir):
     assert L.nk_advance_host(eng.ctx, eng.cap + 1, 1, *bufs, C.byref(n_out), None, None, None) != 0
     assert "capacity" in msg(eng.ctx)
     assert L.nk_bind_particles(eng.ctx, 3, *bufs) != 0 and "capacity" in msg(eng.ctx)      # must be even and >= 2
+    assert L.nk_bind_particles(eng.ctx, 2 ** 31, *bufs) != 0 and "2^31" in msg(eng.ctx)    # slots are 32-bit indices
+    assert L.nk_bind_particles(eng.ctx, eng.cap, *bufs) == 0                               # and the valid call still binds
     assert L.nk_set_reservoir_mode(eng.ctx, 9, None) != 0 and "unknown" in msg(eng.ctx)
     h2d, d2h = C.c_int64(-1), C.c_int64(-1)
     assert L.nk_last_transfer_bytes(eng.ctx, C.byref(h2d), C.byref(d2h)) == 0 and h2d.value == 0 and d2h.value == 0
